@@ -1,0 +1,225 @@
+/*
+ * tpugan_b200.h — C ABI of libtpugan_b200.so
+ *
+ * B200-native (sm_100a) point-neighbourhood kernels behind the call surfaces
+ * that TPU-GAN (zijieli-Jlee/Temporal-Pointcloud-Upsampling-GAN) imports from
+ * its un-vendored native dependencies.  Every entry point below names the
+ * reference call site (file:line under the reference tree) whose native op it
+ * replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers
+ *     unless a parameter is documented as a host scalar.
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library
+ *     never allocates or frees device memory and keeps no state between calls.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     no call synchronises the device or reads anything back to the host.
+ *   - return value: TPG_OK (0) or a negative TPG_E* code; the message of the
+ *     last failure on the calling thread is returned by tpg_last_error().
+ *   - tensors are dense row-major ("contiguous") float32 / int32 / int64.
+ *   - `lengths*` pointers may be NULL (all clouds full length).
+ *
+ * Canonical numerics
+ *   squared distance  d2 = sum_d (a_d - b_d)^2, accumulated sequentially for
+ *   d = 0..D-1 in fp32 with SEPARATE multiply and add (no FMA contraction);
+ *   neighbour order is (d2, index) lexicographic ascending, so ties go to the
+ *   lowest index.
+ */
+#ifndef TPUGAN_B200_H_
+#define TPUGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPG_ABI_VERSION 1
+
+typedef void* tpg_stream_t; /* cudaStream_t */
+
+enum {
+  TPG_OK = 0,
+  TPG_EINVAL = -1,       /* bad shape / argument                         */
+  TPG_EUNSUPPORTED = -2, /* argument combination outside the built range */
+  TPG_ECUDA = -3,        /* a CUDA runtime call or launch failed         */
+  TPG_EWORKSPACE = -4    /* workspace pointer NULL or too small          */
+};
+
+/* reduce ops of tpg_group_reduce_* */
+enum { TPG_REDUCE_MAX = 0, TPG_REDUCE_SUM = 1, TPG_REDUCE_MIN = 2 };
+
+/* which Chamfer directions to evaluate */
+enum { TPG_CHAMFER_FWD = 1, TPG_CHAMFER_REV = 2, TPG_CHAMFER_BOTH = 3 };
+
+/* ---- library ---------------------------------------------------------- */
+int tpg_abi_version(void);
+const char* tpg_last_error(void);
+/* number of kernel launches issued by this library on the calling process
+ * since load (bench.py's "gpu_launches" claim is read from here). */
+uint64_t tpg_launch_count(void);
+
+/* ---- K1/K2: k nearest neighbours ---------------------------------------
+ * replaces pytorch3d.ops.knn_points(p1, p2, lengths1, lengths2, K,
+ *   return_sorted=True) — reference call sites gcn_lib/pointnet/gcn.py:16,38,
+ *   discriminator.py:15,33, gcn_lib/interpolation.py:47,
+ *   gcn_lib/graph_utils.py:71.
+ * p1 [B,P1,D], p2 [B,P2,D] -> dists [B,P1,K] (squared), idx [B,P1,K] int64.
+ * Slots beyond min(K, lengths2[b]) and rows beyond lengths1[b] hold 0 / 0.
+ * 1 <= D <= 256, 1 <= K <= 1024.                                          */
+int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
+                const int64_t* lengths2, int B, int P1, int P2, int D, int K,
+                float* dists, int64_t* idx, tpg_stream_t stream);
+
+/* ---- K3: fixed-radius nearest neighbours --------------------------------
+ * replaces frnn.frnn_grid_points(points1, points2, lengths1, lengths2, K, r,
+ *   return_sorted=True) — discriminator.py:27, loss.py:105,142,229,256,261,
+ *   gcn_lib/interpolation.py:20,33, gcn_lib/graph_utils.py:46,
+ *   gcn_lib/pointnet/gcn.py:30.
+ * The K nearest points with d2 < r*r (strict), ordered by (d2, idx); unused
+ * slots hold dist -1 / idx -1.  D = 3 (2 also accepted).
+ * r_per_cloud: device [B] or NULL, in which case the host scalar `r` is used.
+ * workspace: tpg_frnn_workspace_bytes() bytes.                             */
+size_t tpg_frnn_workspace_bytes(int B, int P1, int P2, int D, int K);
+int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* lengths1,
+                 const int64_t* lengths2, int B, int P1, int P2, int D, int K,
+                 float r, const float* r_per_cloud, float* dists, int64_t* idx,
+                 void* workspace, size_t workspace_bytes, tpg_stream_t stream);
+
+/* ---- K4: ball query ------------------------------------------------------
+ * replaces pointnet2_ops.pointnet2_utils.ball_query(radius, nsample, xyz,
+ *   new_xyz) used inside QueryAndGroup — discriminator.py:190.
+ * xyz [B,N,3], new_xyz [B,M,3] -> idx [B,M,nsample] int32: the `nsample`
+ * LOWEST indices with d2 < radius^2, slots beyond the hit count repeat the
+ * first hit, no hit -> all 0.                                              */
+int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N,
+                       int M, float radius, int nsample, int32_t* idx,
+                       tpg_stream_t stream);
+
+/* ---- K5: farthest point sampling -----------------------------------------
+ * (a) replaces pointnet2_utils.furthest_point_sample(xyz, npoint) —
+ *     discriminator.py:114.  Starts at index 0, skips points with
+ *     x^2+y^2+z^2 <= 1e-3, ties -> lowest index.  xyz [B,N,3] -> idx
+ *     [B,npoint] int32.
+ * (b) replaces sampling.farthest_point_sampling(pts, k, initial_idx) —
+ *     sampling.py:50-106 (numba loop sampling.py:36-44).  pts [B,N,D] (D<=3),
+ *     start [B] int64 -> idx [B,k] int64 and, when dist_rows != NULL, the
+ *     [B,k,N] rows of squared distances the reference returns.             */
+size_t tpg_fps_workspace_bytes(int B, int N); /* 0 for N <= 8192 */
+int tpg_fps_f32(const float* xyz, int B, int N, int npoint, int32_t* idx,
+                void* workspace, size_t workspace_bytes, tpg_stream_t stream);
+int tpg_fps_start_f32(const float* pts, int B, int N, int D, int k,
+                      const int64_t* start, int64_t* idx, float* dist_rows,
+                      void* workspace, size_t workspace_bytes,
+                      tpg_stream_t stream);
+
+/* ---- K6: grouping / gather ------------------------------------------------
+ * replaces pointnet2_utils.grouping_operation(features, idx) —
+ *   gcn_lib/pointnet/gcn.py:207,261, discriminator.py:270,273 — and
+ *   pointnet2_utils.gather_operation(features, idx) — discriminator.py:132
+ *   (the k == 1 case).
+ * f [B,C,N], idx [B,M,k] int32 -> out [B,C,M,k] = f[b,c,idx[b,m,j]].
+ * center != NULL ([B,C,M]) fuses the "- centre" of gcn.py:209 /
+ * discriminator.py:271: out = f[b,c,idx] - center[b,c,m].
+ * Backward: grad_f [B,C,N] = sum over (m,j) with idx == n of grad_out, in
+ * ascending (m,j) order, through an inverse index (CSR) built once per idx
+ * tensor by tpg_inverse_index_build and shared by every grouping call that
+ * reuses that idx.
+ *   seg_offsets [B,N+1] int32, seg_items [B,L] int32 (L = M*k; item = m*k+j). */
+int tpg_group_fwd_f32(const float* f, const int32_t* idx, const float* center,
+                      int B, int C, int N, int M, int k, float* out,
+                      tpg_stream_t stream);
+size_t tpg_inverse_index_workspace_bytes(int B, int N, int L);
+int tpg_inverse_index_build(const int32_t* idx, int B, int N, int L,
+                            int32_t* seg_offsets, int32_t* seg_items,
+                            void* workspace, size_t workspace_bytes,
+                            tpg_stream_t stream);
+int tpg_group_bwd_f32(const float* grad_out, const int32_t* seg_offsets,
+                      const int32_t* seg_items, int B, int C, int N, int L,
+                      float* grad_f, tpg_stream_t stream);
+
+/* ---- K7: fused gather + reduce over the k neighbours ---------------------
+ * replaces grouping_operation followed by torch.max(dim=-1) —
+ *   gcn_lib/pointnet/gcn.py:261-263 — without materialising [B,C,M,k].
+ * out [B,C,M]; arg [B,C,M] int32 (slot j of the first extremum; may be NULL,
+ * ignored for SUM).  Backward routes grad_out[b,c,m] to f[b,c,idx[b,m,arg]]
+ * (MAX/MIN) or to every neighbour (SUM) through the same CSR.              */
+int tpg_group_reduce_fwd_f32(const float* f, const int32_t* idx, int B, int C,
+                             int N, int M, int k, int op, float* out,
+                             int32_t* arg, tpg_stream_t stream);
+int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg,
+                             const int32_t* seg_offsets,
+                             const int32_t* seg_items, int B, int C, int N,
+                             int M, int k, int op, float* grad_f,
+                             tpg_stream_t stream);
+
+/* ---- K8: three_nn / three_interpolate -------------------------------------
+ * replaces pointnet2_utils.three_nn(unknown, known) and
+ *   three_interpolate(features, idx, weight) (north_star surface; no call
+ *   site in the reference tree).
+ * unknown [B,n,3], known [B,m,3] -> dist [B,n,3] = sqrt(d2), idx [B,n,3] int32.
+ * f [B,c,m], idx, w [B,n,3] -> out [B,c,n] = sum_k w_k f[idx_k].           */
+int tpg_three_nn_f32(const float* unknown, const float* known, int B, int n,
+                     int m, float* dist, int32_t* idx, tpg_stream_t stream);
+int tpg_three_interpolate_fwd_f32(const float* f, const int32_t* idx,
+                                  const float* w, int B, int c, int m, int n,
+                                  float* out, tpg_stream_t stream);
+int tpg_three_interpolate_bwd_f32(const float* grad_out, const float* w,
+                                  const int32_t* seg_offsets,
+                                  const int32_t* seg_items, int B, int c, int m,
+                                  int n, float* grad_f, tpg_stream_t stream);
+
+/* ---- K9: Chamfer distance ---------------------------------------------------
+ * replaces chamferdist.ChamferDistance.forward (two knn_points(K=1) searches +
+ *   reductions + the pytorch3d knn backward) — loss.py:125,176,224,280.
+ * src [B,P1,D], tgt [B,P2,D].  directions: TPG_CHAMFER_*.
+ * fwd writes per-point nearest squared distance / index for each evaluated
+ * direction (d_src,i_src: src->tgt [B,P1]; d_tgt,i_tgt: tgt->src [B,P2]) and
+ * the per-cloud sums sum_src [B], sum_tgt [B] (fixed summation order).
+ * bwd: grad_src/grad_tgt (either may be NULL) from per-cloud upstream
+ * gradients g_src [B], g_tgt [B] (d loss / d sum_src[b], d sum_tgt[b]):
+ *   grad_src[i] = 2 g_src (s_i - t_nn(i)) + sum_{j: nn(j)=i} 2 g_tgt (s_i - t_j)
+ * the scattered part summed in ascending j through a CSR over i_tgt.
+ * workspace: tpg_chamfer_bwd_workspace_bytes().                             */
+int tpg_chamfer_fwd_f32(const float* src, const float* tgt,
+                        const int64_t* lengths_src, const int64_t* lengths_tgt,
+                        int B, int P1, int P2, int D, int directions,
+                        float* d_src, int32_t* i_src, float* d_tgt,
+                        int32_t* i_tgt, float* sum_src, float* sum_tgt,
+                        tpg_stream_t stream);
+size_t tpg_chamfer_bwd_workspace_bytes(int B, int P1, int P2);
+int tpg_chamfer_bwd_f32(const float* src, const float* tgt,
+                        const int64_t* lengths_src, const int64_t* lengths_tgt,
+                        const int32_t* i_src, const int32_t* i_tgt,
+                        const float* g_src, const float* g_tgt, int B, int P1,
+                        int P2, int D, int directions, float* grad_src,
+                        float* grad_tgt, void* workspace,
+                        size_t workspace_bytes, tpg_stream_t stream);
+
+/* ---- K10: SPH cubic-kernel field interpolation ----------------------------
+ * replaces gcn_lib.cubic_interpolation(query_pos, field, pos, cutoff) —
+ *   gcn_lib/interpolation.py:103-123 (graph :16-80, l2dist :11-14, kernel
+ *   :92-100) — batched over the S samples that train_step_final.py:54-65
+ *   loops over in Python.
+ * query [S,Q,3], field [S,P,F], pos [S,P,3] -> out [S,Q,F].  F <= 16.       */
+size_t tpg_cubic_interp_workspace_bytes(int S, int Q, int P);
+int tpg_cubic_interp_f32(const float* query, const float* field,
+                         const float* pos, int S, int Q, int P, int F,
+                         float cutoff, float* out, void* workspace,
+                         size_t workspace_bytes, tpg_stream_t stream);
+
+/* ---- point-major gathers ---------------------------------------------------
+ * replaces pytorch3d.ops.knn_gather(x, idx) (north_star surface) and the
+ *   advanced-indexing row gather index_points(points, idx) —
+ *   discriminator.py:43-60, loss.py:10-27.
+ * x [B,N,U], idx [B,L] int64 -> out [B,L,U] = x[b, idx[b,l], :].  An index of
+ * -1 (index_points on FRNN output, loss.py:273-275) wraps to row N-1 exactly
+ * as Python negative indexing does.                                        */
+int tpg_gather_rows_f32(const float* x, const int64_t* idx, int B, int N, int U,
+                        int L, float* out, tpg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPUGAN_B200_H_ */

@@ -1,0 +1,97 @@
+// ball_query.cu — K4: pointnet2_ops ball_query semantics (QueryAndGroup,
+// discriminator.py:190): the `nsample` LOWEST indices with d2 < r^2 in index order,
+// remaining slots repeat the first hit, no hit -> 0.
+//
+// Design: one warp per query centre scans the cloud 32 points at a time in index
+// order; __ballot_sync + popc of the lower lanes gives each hit its output slot, so
+// hits are written in index order without atomics, and the warp leaves the loop as
+// soon as nsample hits are found (for dense fluid clouds that is after a few hundred
+// points, which is why this op is latency- rather than bandwidth-bound).  The 8
+// warps of a CTA scan the same cloud, so every 128-byte line is fetched from L2 once
+// per CTA and re-served from L1.
+#include "common.cuh"
+
+namespace tpg {
+
+constexpr int BQ_THREADS = 256;
+
+__global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(const float* __restrict__ xyz,
+                                                                const float* __restrict__ new_xyz,
+                                                                int B, int N, int M, float r2, int ns,
+                                                                int32_t* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const long long wq = (long long)blockIdx.x * (BQ_THREADS / 32) + (threadIdx.x >> 5);
+  if (wq >= (long long)B * M) return;
+  const int b = (int)(wq / M);
+  const float* c = new_xyz + (size_t)wq * 3;
+  const float cx = c[0], cy = c[1], cz = c[2];
+  const float* p = xyz + (size_t)b * N * 3;
+  int32_t* out = idx + (size_t)wq * ns;
+  int cnt = 0, first = -1;
+  for (int j0 = 0; j0 < N && cnt < ns; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    if (j < N) {
+      const float d = sqdist3(cx, cy, cz, p[(size_t)j * 3], p[(size_t)j * 3 + 1], p[(size_t)j * 3 + 2]);
+      hit = d < r2;
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) {
+      if (first < 0) first = j0 + __ffs(m) - 1;
+      const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+      if (hit && slot < ns) out[slot] = j;
+      cnt += __popc(m);
+    }
+  }
+  cnt = min(cnt, ns);
+  const int fill = first < 0 ? 0 : first;
+  for (int s = cnt + lane; s < ns; s += 32) out[s] = fill;
+}
+
+// x [B,N,U], idx [B,L] int64 -> out [B,L,U]; negative indices wrap (Python indexing).
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int B,
+                                   int N, int U, int L, float* __restrict__ out) {
+  const long long total = (long long)B * L * U;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / U;
+    const int u = (int)(e - row * U);
+    const int b = (int)(row / L);
+    long long j = idx[row];
+    if (j < 0) j += N;
+    out[e] = x[((size_t)b * N + (size_t)j) * U + u];
+  }
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+
+TPG_API int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int M, float radius,
+                               int nsample, int32_t* idx, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && N >= 0 && M >= 0 && nsample >= 1, TPG_EINVAL, "ball_query: bad size");
+  if (B == 0 || M == 0) return TPG_OK;
+  TPG_REQUIRE(xyz && new_xyz && idx, TPG_EINVAL, "ball_query: null pointer");
+  const float r2 = radius * radius;
+  const long long warps = (long long)B * M;
+  const long long blocks = (warps + BQ_THREADS / 32 - 1) / (BQ_THREADS / 32);
+  TPG_REQUIRE(blocks <= 0x7fffffffLL, TPG_EUNSUPPORTED, "ball_query: too many queries");
+  ball_query_kernel<<<(unsigned)blocks, BQ_THREADS, 0, as_stream(stream)>>>(xyz, new_xyz, B, N, M, r2, nsample, idx);
+  TPG_CHECK_LAUNCH("ball_query_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_gather_rows_f32(const float* x, const int64_t* idx, int B, int N, int U, int L, float* out,
+                                tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && N >= 0 && U >= 0 && L >= 0, TPG_EINVAL, "gather_rows: bad size");
+  const long long total = (long long)B * L * U;
+  if (total == 0) return TPG_OK;
+  TPG_REQUIRE(x && idx && out, TPG_EINVAL, "gather_rows: null pointer");
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_rows_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, idx, B, N, U, L, out);
+  TPG_CHECK_LAUNCH("gather_rows_kernel");
+  return TPG_OK;
+}

@@ -1,0 +1,269 @@
+// chamfer.cu — K9: Chamfer distance forward + backward.
+//
+// Replaces chamferdist.ChamferDistance (two pytorch3d knn_points(K=1) searches, the
+// per-cloud sums and the pytorch3d knn backward) — loss.py:125,176,224,280.
+//
+// Forward: nearest neighbour with K = 1 needs no list, so lanes own QUERIES here
+// (unlike knn.cu): each thread keeps NN_R queries in registers, the candidate cloud
+// streams through shared memory as float4 and every LDS.128 is a warp-wide
+// broadcast feeding NN_R distance evaluations.  The strict '<' over an ascending
+// scan gives the lowest index on ties.  Per-cloud sums use a fixed-shape reduction
+// (deterministic).
+// Backward: the direct term is a coalesced elementwise pass; the scattered term
+// (points of the other cloud whose nearest neighbour is this point) is gathered
+// through the same CSR machinery as the grouping backward — no atomics.
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace tpg {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_TJ = 1024;
+
+template <int R>
+__global__ void __launch_bounds__(NN_THREADS) nn1_kernel(const float* __restrict__ qpts,
+                                                         const float* __restrict__ cpts,
+                                                         const int64_t* __restrict__ qlen,
+                                                         const int64_t* __restrict__ clen, int Pq, int Pc, int D,
+                                                         float* __restrict__ d_out, int32_t* __restrict__ i_out) {
+  __shared__ float4 tile[NN_TJ];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int nq = qlen ? min((int)qlen[b], Pq) : Pq;
+  const int nc = clen ? min((int)clen[b], Pc) : Pc;
+  const float* qb = qpts + (size_t)b * Pq * D;
+  const float* cb = cpts + (size_t)b * Pc * D;
+  const float INF = __int_as_float(0x7f800000);
+  float4 q[R];
+  float best[R];
+  int bi[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = (blockIdx.x * R + r) * NN_THREADS + tid;
+    q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nq) {
+      const float* p = qb + (size_t)i * D;
+      q[r].x = p[0];
+      if (D > 1) q[r].y = p[1];
+      if (D > 2) q[r].z = p[2];
+      if (D > 3) q[r].w = p[3];
+    }
+    best[r] = INF;
+    bi[r] = -1;
+  }
+  for (int t0 = 0; t0 < nc; t0 += NN_TJ) {
+    const int tn = min(NN_TJ, nc - t0);
+    __syncthreads();
+    for (int j = tid; j < tn; j += NN_THREADS) {
+      const float* p = cb + (size_t)(t0 + j) * D;
+      float4 v = make_float4(p[0], 0.f, 0.f, 0.f);
+      if (D > 1) v.y = p[1];
+      if (D > 2) v.z = p[2];
+      if (D > 3) v.w = p[3];
+      tile[j] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < tn; ++j) {
+      const float4 c = tile[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float d = 0.0f;
+        d = sq_acc(d, q[r].x, c.x);
+        d = sq_acc(d, q[r].y, c.y);
+        d = sq_acc(d, q[r].z, c.z);
+        d = sq_acc(d, q[r].w, c.w);
+        if (d < best[r]) { best[r] = d; bi[r] = t0 + j; }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = (blockIdx.x * R + r) * NN_THREADS + tid;
+    if (i < Pq) {
+      const bool ok = i < nq && bi[r] >= 0;
+      d_out[(size_t)b * Pq + i] = ok ? best[r] : 0.0f;
+      i_out[(size_t)b * Pq + i] = ok ? bi[r] : 0;
+    }
+  }
+}
+
+// per-cloud sum of d[b, 0:len) with a fixed reduction shape (deterministic)
+__global__ void __launch_bounds__(1024) cloud_sum_kernel(const float* __restrict__ d, const int64_t* __restrict__ len,
+                                                         int P, float* __restrict__ out) {
+  __shared__ float ws[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = len ? min((int)len[b], P) : P;
+  float acc = 0.0f;
+  for (int i = tid; i < n; i += 1024) acc += d[(size_t)b * P + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  if (lane == 0) ws[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float v = ws[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0) out[b] = v;
+  }
+}
+
+// gradient of one cloud ("mine") given the other ("their"):
+//   direct     : + 2 g_mine (x_i - y_nn(i))                       (my own search)
+//   scattered  : - sum_{j in seg(i)} 2 g_their (y_j - x_i)         (their search hit me)
+// order matches the oracle: forward direction first, then the reverse direction.
+struct ChamferBwdArgs {
+  const float* mine;     // [B,Pm,D]
+  const float* their;    // [B,Pt,D]
+  const int64_t* mlen;
+  const int32_t* nn_mine;   // [B,Pm]  my nearest in `their`   (null: direction not evaluated)
+  const float* g_mine;      // [B]
+  const int32_t* off;       // CSR over their nn (keys = my points) (null: direction not evaluated)
+  const int32_t* items;     // [B,Pt]
+  const float* g_their;     // [B]
+  int Pm, Pt, D;
+  int scattered_first;      // 1 when the scattered term belongs to the forward direction
+  float* grad;              // [B,Pm,D]
+};
+
+__global__ void __launch_bounds__(256) chamfer_bwd_kernel(ChamferBwdArgs a) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.Pm) return;
+  const int nm = a.mlen ? min((int)a.mlen[b], a.Pm) : a.Pm;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i < nm) {
+    const float* xp = a.mine + ((size_t)b * a.Pm + i) * a.D;
+    for (int d = 0; d < a.D; ++d) x[d] = xp[d];
+    const float* tb = a.their + (size_t)b * a.Pt * a.D;
+    for (int phase = 0; phase < 2; ++phase) {
+      const bool do_scatter = (phase == 0) == (a.scattered_first != 0);
+      if (do_scatter) {
+        if (a.off) {
+          const float two_g = __fmul_rn(2.0f, a.g_their[b]);
+          const int s0 = a.off[(size_t)b * (a.Pm + 1) + i], s1 = a.off[(size_t)b * (a.Pm + 1) + i + 1];
+          for (int p = s0; p < s1; ++p) {
+            const float* y = tb + (size_t)a.items[(size_t)b * a.Pt + p] * a.D;
+            for (int d = 0; d < a.D; ++d) acc[d] = __fsub_rn(acc[d], __fmul_rn(two_g, __fsub_rn(y[d], x[d])));
+          }
+        }
+      } else if (a.nn_mine) {
+        const float two_g = __fmul_rn(2.0f, a.g_mine[b]);
+        const float* y = tb + (size_t)a.nn_mine[(size_t)b * a.Pm + i] * a.D;
+        for (int d = 0; d < a.D; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(two_g, __fsub_rn(x[d], y[d])));
+      }
+    }
+  }
+  float* g = a.grad + ((size_t)b * a.Pm + i) * a.D;
+  for (int d = 0; d < a.D; ++d) g[d] = acc[d];
+}
+
+static int launch_nn1(const float* q, const float* c, const int64_t* ql, const int64_t* cl, int B, int Pq, int Pc,
+                      int D, float* d_out, int32_t* i_out, cudaStream_t st) {
+  if (Pq == 0) return TPG_OK;
+  // enough CTAs for >= 2 waves with R = 2, otherwise one query per thread
+  const long long ctas_r2 = (long long)B * ceil_div(Pq, NN_THREADS * 2);
+  if (ctas_r2 >= 2LL * num_sms()) {
+    dim3 grid(ceil_div(Pq, NN_THREADS * 2), B);
+    nn1_kernel<2><<<grid, NN_THREADS, 0, st>>>(q, c, ql, cl, Pq, Pc, D, d_out, i_out);
+  } else {
+    dim3 grid(ceil_div(Pq, NN_THREADS), B);
+    nn1_kernel<1><<<grid, NN_THREADS, 0, st>>>(q, c, ql, cl, Pq, Pc, D, d_out, i_out);
+  }
+  TPG_CHECK_LAUNCH("nn1_kernel");
+  return TPG_OK;
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+
+TPG_API int tpg_chamfer_fwd_f32(const float* src, const float* tgt, const int64_t* lengths_src,
+                                const int64_t* lengths_tgt, int B, int P1, int P2, int D, int directions,
+                                float* d_src, int32_t* i_src, float* d_tgt, int32_t* i_tgt, float* sum_src,
+                                float* sum_tgt, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0, TPG_EINVAL, "chamfer_fwd: negative size");
+  TPG_REQUIRE(D >= 1 && D <= 4, TPG_EUNSUPPORTED, "chamfer_fwd: D=%d outside [1,4]", D);
+  TPG_REQUIRE(directions >= 1 && directions <= 3, TPG_EINVAL, "chamfer_fwd: bad directions %d", directions);
+  TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "chamfer_fwd: B > 65535");
+  if (B == 0) return TPG_OK;
+  cudaStream_t st = as_stream(stream);
+  if (directions & TPG_CHAMFER_FWD) {
+    TPG_REQUIRE(d_src && i_src && sum_src, TPG_EINVAL, "chamfer_fwd: null forward outputs");
+    int rc = launch_nn1(src, tgt, lengths_src, lengths_tgt, B, P1, P2, D, d_src, i_src, st);
+    if (rc) return rc;
+    cloud_sum_kernel<<<B, 1024, 0, st>>>(d_src, lengths_src, P1, sum_src);
+    TPG_CHECK_LAUNCH("cloud_sum_kernel");
+  }
+  if (directions & TPG_CHAMFER_REV) {
+    TPG_REQUIRE(d_tgt && i_tgt && sum_tgt, TPG_EINVAL, "chamfer_fwd: null reverse outputs");
+    int rc = launch_nn1(tgt, src, lengths_tgt, lengths_src, B, P2, P1, D, d_tgt, i_tgt, st);
+    if (rc) return rc;
+    cloud_sum_kernel<<<B, 1024, 0, st>>>(d_tgt, lengths_tgt, P2, sum_tgt);
+    TPG_CHECK_LAUNCH("cloud_sum_kernel");
+  }
+  return TPG_OK;
+}
+
+static size_t chamfer_csr_bytes(int B, int keys, int items) {
+  return align_up(sizeof(int32_t) * (size_t)B * (keys + 1), 256) + align_up(sizeof(int32_t) * (size_t)B * items, 256);
+}
+
+TPG_API size_t tpg_chamfer_bwd_workspace_bytes(int B, int P1, int P2) {
+  const size_t build = csr_workspace_bytes(B, P1 > P2 ? P1 : P2, P1 > P2 ? P1 : P2);
+  return chamfer_csr_bytes(B, P1, P2) + chamfer_csr_bytes(B, P2, P1) + build;
+}
+
+TPG_API int tpg_chamfer_bwd_f32(const float* src, const float* tgt, const int64_t* lengths_src,
+                                const int64_t* lengths_tgt, const int32_t* i_src, const int32_t* i_tgt,
+                                const float* g_src, const float* g_tgt, int B, int P1, int P2, int D,
+                                int directions, float* grad_src, float* grad_tgt, void* workspace,
+                                size_t workspace_bytes, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0, TPG_EINVAL, "chamfer_bwd: negative size");
+  TPG_REQUIRE(D >= 1 && D <= 4, TPG_EUNSUPPORTED, "chamfer_bwd: D=%d outside [1,4]", D);
+  TPG_REQUIRE(directions >= 1 && directions <= 3, TPG_EINVAL, "chamfer_bwd: bad directions %d", directions);
+  TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "chamfer_bwd: B > 65535");
+  if (B == 0) return TPG_OK;
+  TPG_REQUIRE(workspace && workspace_bytes >= tpg_chamfer_bwd_workspace_bytes(B, P1, P2), TPG_EWORKSPACE,
+              "chamfer_bwd: workspace too small");
+  const bool fwd = directions & TPG_CHAMFER_FWD, rev = directions & TPG_CHAMFER_REV;
+  TPG_REQUIRE(!fwd || (i_src && g_src), TPG_EINVAL, "chamfer_bwd: forward direction needs i_src and g_src");
+  TPG_REQUIRE(!rev || (i_tgt && g_tgt), TPG_EINVAL, "chamfer_bwd: reverse direction needs i_tgt and g_tgt");
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  // CSR "A": keys = src points, items = tgt points whose nearest is that src point (from i_tgt)
+  int32_t* offA = reinterpret_cast<int32_t*>(ws);
+  int32_t* itemsA = reinterpret_cast<int32_t*>(ws + align_up(sizeof(int32_t) * (size_t)B * (P1 + 1), 256));
+  ws += chamfer_csr_bytes(B, P1, P2);
+  // CSR "B": keys = tgt points, items = src points whose nearest is that tgt point (from i_src)
+  int32_t* offB = reinterpret_cast<int32_t*>(ws);
+  int32_t* itemsB = reinterpret_cast<int32_t*>(ws + align_up(sizeof(int32_t) * (size_t)B * (P2 + 1), 256));
+  ws += chamfer_csr_bytes(B, P2, P1);
+  const size_t build_bytes = csr_workspace_bytes(B, P1 > P2 ? P1 : P2, P1 > P2 ? P1 : P2);
+
+  if (grad_src && P1 > 0) {
+    const bool scat = rev && P2 > 0;
+    if (scat) {
+      int rc = build_csr(i_tgt, lengths_tgt, B, P1, P2, offA, itemsA, ws, build_bytes, st);
+      if (rc) return rc;
+    }
+    ChamferBwdArgs a{src, tgt, lengths_src, (fwd && P2 > 0) ? i_src : nullptr, g_src, scat ? offA : nullptr,
+                     itemsA, g_tgt, P1, P2, D, /*scattered_first=*/0, grad_src};
+    dim3 grid(ceil_div(P1, 256), B);
+    chamfer_bwd_kernel<<<grid, 256, 0, st>>>(a);
+    TPG_CHECK_LAUNCH("chamfer_bwd_kernel");
+  }
+  if (grad_tgt && P2 > 0) {
+    const bool scat = fwd && P1 > 0;
+    if (scat) {
+      int rc = build_csr(i_src, lengths_src, B, P2, P1, offB, itemsB, ws, build_bytes, st);
+      if (rc) return rc;
+    }
+    ChamferBwdArgs a{tgt, src, lengths_tgt, (rev && P1 > 0) ? i_tgt : nullptr, g_tgt, scat ? offB : nullptr,
+                     itemsB, g_src, P2, P1, D, /*scattered_first=*/1, grad_tgt};
+    dim3 grid(ceil_div(P2, 256), B);
+    chamfer_bwd_kernel<<<grid, 256, 0, st>>>(a);
+    TPG_CHECK_LAUNCH("chamfer_bwd_kernel");
+  }
+  return TPG_OK;
+}

@@ -1,0 +1,463 @@
+// group.cu — K6/K7/K8b: grouping / gather forward, atomic-free backward through an
+// inverse index, fused gather+reduce, three_interpolate.
+//
+// Replaces pointnet2_ops grouping_operation (gcn_lib/pointnet/gcn.py:207,261;
+// discriminator.py:270,273), gather_operation (discriminator.py:132), the
+// grouping+max pair of gcn.py:261-263, and three_interpolate.
+//
+// Forward design (HBM-bound: the [B,C,M,k] output dominates the traffic):
+//   a CTA owns (cloud b, a tile of TC channels, a range of flat (m,j) positions).
+//   The TC feature rows f[b,c,:] are staged in shared memory once (coalesced), then
+//   every thread turns one int4 of indices into TC float4 stores: the random
+//   accesses hit shared memory (4-byte bank-granular) instead of pulling a 32-byte
+//   sector per 4 useful bytes through L1/L2, and the output is written with fully
+//   coalesced 16-byte stores.  Rows that do not fit in shared memory fall back to
+//   read-only global gathers.
+// Backward design: scatter-add is inverted into a gather.  tpg_inverse_index_build
+//   turns idx into a CSR (for every source point n: the ascending list of flat
+//   positions that read it); grad_f[b,c,n] is then a private sequential sum —
+//   no atomics, deterministic, and the CSR is reused by every op sharing the idx.
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace tpg {
+
+constexpr int GRP_THREADS = 256;
+constexpr size_t GRP_SMEM_MAX = 96 * 1024;
+
+struct GroupFwdArgs {
+  const float* f;        // [B,C,N]
+  const int32_t* idx;    // [B,L]
+  const float* center;   // [B,C,M] or null
+  int B, C, N, M, k, L;
+  int TC, LT, rows_vec;
+  float* out;            // [B,C,L]
+};
+
+template <bool SMEM, bool VEC4>
+__global__ void __launch_bounds__(GRP_THREADS) group_fwd_kernel(GroupFwdArgs a) {
+  extern __shared__ float rows_s[];
+  const int b = blockIdx.z, c0 = blockIdx.y * a.TC, tid = threadIdx.x;
+  const int tc = min(a.TC, a.C - c0);
+  const float* fb = a.f + ((size_t)b * a.C + c0) * a.N;
+  if (SMEM) {
+    const int total = tc * a.N;
+    if (a.rows_vec) {
+      const float4* src = reinterpret_cast<const float4*>(fb);
+      float4* dst = reinterpret_cast<float4*>(rows_s);
+      for (int e = tid; e < (total >> 2); e += GRP_THREADS) dst[e] = __ldg(src + e);
+    } else {
+      for (int e = tid; e < total; e += GRP_THREADS) rows_s[e] = __ldg(fb + e);
+    }
+    __syncthreads();
+  }
+  const float* rows = SMEM ? rows_s : fb;
+  const int l0 = blockIdx.x * a.LT;
+  const int l1 = min(a.L, l0 + a.LT);
+  const int32_t* ib = a.idx + (size_t)b * a.L;
+  float* ob = a.out + ((size_t)b * a.C + c0) * a.L;
+  const float* cb = a.center ? a.center + ((size_t)b * a.C + c0) * a.M : nullptr;
+  if (VEC4) {
+    const int4* ib4 = reinterpret_cast<const int4*>(ib);
+    for (int g = (l0 >> 2) + tid; g < (l1 >> 2); g += GRP_THREADS) {
+      const int4 ii = __ldg(ib4 + g);
+      int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+      if (cb) { const int l = g << 2; m0 = l / a.k; m1 = (l + 1) / a.k; m2 = (l + 2) / a.k; m3 = (l + 3) / a.k; }
+#pragma unroll 4
+      for (int c = 0; c < tc; ++c) {
+        const float* r = rows + (size_t)c * a.N;
+        float4 v;
+        if (SMEM) { v.x = r[ii.x]; v.y = r[ii.y]; v.z = r[ii.z]; v.w = r[ii.w]; }
+        else { v.x = __ldg(r + ii.x); v.y = __ldg(r + ii.y); v.z = __ldg(r + ii.z); v.w = __ldg(r + ii.w); }
+        if (cb) {
+          const float* cc = cb + (size_t)c * a.M;
+          v.x = __fsub_rn(v.x, __ldg(cc + m0)); v.y = __fsub_rn(v.y, __ldg(cc + m1));
+          v.z = __fsub_rn(v.z, __ldg(cc + m2)); v.w = __fsub_rn(v.w, __ldg(cc + m3));
+        }
+        reinterpret_cast<float4*>(ob + (size_t)c * a.L)[g] = v;
+      }
+    }
+  } else {
+    for (int l = l0 + tid; l < l1; l += GRP_THREADS) {
+      const int i = __ldg(ib + l);
+      const int m = cb ? l / a.k : 0;
+      for (int c = 0; c < tc; ++c) {
+        float v = SMEM ? rows[(size_t)c * a.N + i] : __ldg(rows + (size_t)c * a.N + i);
+        if (cb) v = __fsub_rn(v, __ldg(cb + (size_t)c * a.M + m));
+        ob[(size_t)c * a.L + l] = v;
+      }
+    }
+  }
+}
+
+// ---- fused gather + reduce over k (also three_interpolate when w != null) --------
+struct ReduceFwdArgs {
+  const float* f;      // [B,C,N]
+  const int32_t* idx;  // [B,M,k]
+  const float* w;      // [B,M,k] or null (weighted sum)
+  int B, C, N, M, k, op, TC, MT;
+  float* out;          // [B,C,M]
+  int32_t* arg;        // [B,C,M] or null
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(GRP_THREADS) group_reduce_fwd_kernel(ReduceFwdArgs a) {
+  extern __shared__ float rows_s[];
+  const int b = blockIdx.z, c0 = blockIdx.y * a.TC, tid = threadIdx.x;
+  const int tc = min(a.TC, a.C - c0);
+  const float* fb = a.f + ((size_t)b * a.C + c0) * a.N;
+  if (SMEM) {
+    const int total = tc * a.N;
+    for (int e = tid; e < total; e += GRP_THREADS) rows_s[e] = __ldg(fb + e);
+    __syncthreads();
+  }
+  const float* rows = SMEM ? rows_s : fb;
+  const int m0 = blockIdx.x * a.MT, m1 = min(a.M, m0 + a.MT);
+  for (int m = m0 + tid; m < m1; m += GRP_THREADS) {
+    const int32_t* im = a.idx + ((size_t)b * a.M + m) * a.k;
+    const float* wm = a.w ? a.w + ((size_t)b * a.M + m) * a.k : nullptr;
+    for (int c = 0; c < tc; ++c) {
+      const float* r = rows + (size_t)c * a.N;
+      float acc = SMEM ? r[im[0]] : __ldg(r + im[0]);
+      if (wm) acc = __fmul_rn(wm[0], acc);
+      int best = 0;
+      for (int j = 1; j < a.k; ++j) {
+        float v = SMEM ? r[im[j]] : __ldg(r + im[j]);
+        if (wm) acc = __fadd_rn(acc, __fmul_rn(wm[j], v));
+        else if (a.op == TPG_REDUCE_MAX) { if (v > acc) { acc = v; best = j; } }
+        else if (a.op == TPG_REDUCE_MIN) { if (v < acc) { acc = v; best = j; } }
+        else acc = __fadd_rn(acc, v);
+      }
+      const size_t o = ((size_t)b * a.C + c0 + c) * a.M + m;
+      a.out[o] = acc;
+      if (a.arg) a.arg[o] = best;
+    }
+  }
+}
+
+// ---- inverse index (CSR) ------------------------------------------------------------
+__global__ void csr_count_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ item_len,
+                                 int B, int N, int L, int32_t* off) {
+  const long long total = (long long)B * L;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / L);
+    if (item_len && (e - (long long)b * L) >= item_len[b]) continue;
+    const int key = idx[e];
+    if (key >= 0 && key < N) atomicAdd(off + (size_t)b * (N + 1) + key + 1, 1);
+  }
+}
+
+// in-place inclusive scan of off[b][0..N] (off[b][0] == 0), one CTA per cloud; also
+// seeds the fill cursors with the segment starts.
+__global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* off, int32_t* cursor, int N) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* o = off + (size_t)b * (N + 1);
+  int32_t* cur = cursor + (size_t)b * N;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < N + 1; base += 1024) {
+    const int e = base + tid;
+    int v = e < N + 1 ? o[e] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(FULL, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, w, d);
+        if (lane >= d) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    v += carry + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (e < N + 1) {
+      o[e] = v;
+      if (e < N) cur[e] = v;  // start of segment e+1 ... fixed below
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = v;
+    __syncthreads();
+  }
+  // cursor[n] must be the START of segment n == off[n]; the loop stored off[n] at
+  // cur[n] already (inclusive scan value at position n is the sum of counts < n
+  // because counts live at key+1).
+}
+
+__global__ void csr_fill_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ item_len,
+                                int B, int N, int L, int32_t* cursor, int32_t* tmp_items) {
+  const long long total = (long long)B * L;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / L);
+    const int l = (int)(e - (long long)b * L);
+    if (item_len && l >= item_len[b]) continue;
+    const int key = idx[e];
+    if (key >= 0 && key < N) {
+      const int pos = atomicAdd(cursor + (size_t)b * N + key, 1);
+      tmp_items[(size_t)b * L + pos] = l;
+    }
+  }
+}
+
+// one warp per segment: rank-sort the (distinct) positions ascending, out of place.
+__global__ void csr_sort_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ tmp_items,
+                                int B, int N, int L, int32_t* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * N) return;
+  const int b = (int)(w / N), n = (int)(w - (long long)b * N);
+  const int s0 = off[(size_t)b * (N + 1) + n], s1 = off[(size_t)b * (N + 1) + n + 1];
+  const int s = s1 - s0;
+  if (s == 0) return;
+  const int32_t* src = tmp_items + (size_t)b * L + s0;
+  int32_t* dst = items + (size_t)b * L + s0;
+  if (s <= 32) {
+    const int x = lane < s ? src[lane] : 0x7fffffff;
+    int rank = 0;
+    for (int t = 0; t < s; ++t) rank += (__shfl_sync(FULL, x, t) < x) ? 1 : 0;
+    if (lane < s) dst[rank] = x;
+  } else {
+    for (int e = lane; e < s; e += 32) {
+      const int x = src[e];
+      int rank = 0;
+      for (int t = 0; t < s; ++t) rank += (__ldg(src + t) < x) ? 1 : 0;
+      dst[rank] = x;
+    }
+  }
+}
+
+// ---- backward: per-source-point sequential sums over the CSR ---------------------
+enum { BWD_GROUP = 0, BWD_ARG = 1, BWD_SUM = 2, BWD_WEIGHTED = 3 };
+
+struct BwdArgs {
+  const float* go;        // GROUP: [B,C,L]; others: [B,C,M]
+  const int32_t* arg;     // BWD_ARG: [B,C,M]
+  const float* w;         // BWD_WEIGHTED: [B,L]
+  const int32_t* off;     // [B,N+1]
+  const int32_t* items;   // [B,L]
+  int B, C, N, M, k, L, mode;
+  float* gf;              // [B,C,N]
+};
+
+__global__ void __launch_bounds__(GRP_THREADS) group_bwd_kernel(BwdArgs a) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int n = blockIdx.x * GRP_THREADS + threadIdx.x;
+  if (n >= a.N) return;
+  const int s0 = a.off[(size_t)b * (a.N + 1) + n], s1 = a.off[(size_t)b * (a.N + 1) + n + 1];
+  const int32_t* it = a.items + (size_t)b * a.L;
+  float acc = 0.0f;
+  if (a.mode == BWD_GROUP) {
+    const float* go = a.go + ((size_t)b * a.C + c) * a.L;
+    for (int p = s0; p < s1; ++p) acc = __fadd_rn(acc, __ldg(go + it[p]));
+  } else {
+    const float* go = a.go + ((size_t)b * a.C + c) * a.M;
+    for (int p = s0; p < s1; ++p) {
+      const int l = it[p];
+      const int m = l / a.k;
+      if (a.mode == BWD_ARG) {
+        if (a.arg[((size_t)b * a.C + c) * a.M + m] == l - m * a.k) acc = __fadd_rn(acc, __ldg(go + m));
+      } else if (a.mode == BWD_SUM) {
+        acc = __fadd_rn(acc, __ldg(go + m));
+      } else {
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(go + m), __ldg(a.w + (size_t)b * a.L + l)));
+      }
+    }
+  }
+  a.gf[((size_t)b * a.C + c) * a.N + n] = acc;
+}
+
+static void pick_tiles(int B, int C, int N, int L, int& TC, int& LT, bool& smem) {
+  const int target = 4 * num_sms();
+  const int max_tc = (int)(GRP_SMEM_MAX / ((size_t)N * sizeof(float)));
+  smem = max_tc >= 1;
+  TC = 1;
+  const int base_lt = max(1, L / max(1, 4 * N));  // l-tiles that keep row loads <= 25% of stores
+  for (int t = 8; t >= 1; t >>= 1) {
+    if (t > C && t > 1) continue;
+    if (smem && t > max_tc) continue;
+    TC = t;
+    if ((long long)B * ceil_div(C, t) * base_lt >= target) break;
+  }
+  int lt = max(base_lt, ceil_div(target, B * ceil_div(C, TC)));
+  lt = min(lt, max(1, L / 1024));
+  LT = ceil_div(ceil_div(L, lt), 1024) * 1024;
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+
+TPG_API int tpg_group_fwd_f32(const float* f, const int32_t* idx, const float* center, int B, int C, int N,
+                              int M, int k, float* out, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 0 && M >= 0 && k >= 0, TPG_EINVAL, "group_fwd: negative size");
+  const long long L64 = (long long)M * k;
+  TPG_REQUIRE(L64 < (1LL << 31), TPG_EUNSUPPORTED, "group_fwd: M*k too large");
+  if (B == 0 || C == 0 || L64 == 0) return TPG_OK;
+  TPG_REQUIRE(N >= 1, TPG_EINVAL, "group_fwd: empty source cloud");
+  TPG_REQUIRE(f && idx && out, TPG_EINVAL, "group_fwd: null pointer");
+  TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "group_fwd: B > 65535");
+  GroupFwdArgs a{f, idx, center, B, C, N, M, k, (int)L64, 1, 1024, 0, out};
+  a.rows_vec = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+  bool smem;
+  pick_tiles(B, C, N, a.L, a.TC, a.LT, smem);
+  TPG_REQUIRE(ceil_div(C, a.TC) <= 65535, TPG_EUNSUPPORTED, "group_fwd: C too large");
+  const bool vec4 = (a.L & 3) == 0 && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  dim3 grid(ceil_div(a.L, a.LT), ceil_div(C, a.TC), B);
+  const size_t sm = smem ? (size_t)a.TC * N * sizeof(float) : 0;
+  cudaStream_t st = as_stream(stream);
+#define LAUNCH_GF(S, V)                                                                         \
+  do {                                                                                          \
+    auto kern = group_fwd_kernel<S, V>;                                                         \
+    if (sm > 48 * 1024)                                                                         \
+      TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    kern<<<grid, GRP_THREADS, sm, st>>>(a);                                                     \
+  } while (0)
+  if (smem) { if (vec4) LAUNCH_GF(true, true); else LAUNCH_GF(true, false); }
+  else { if (vec4) LAUNCH_GF(false, true); else LAUNCH_GF(false, false); }
+#undef LAUNCH_GF
+  TPG_CHECK_LAUNCH("group_fwd_kernel");
+  return TPG_OK;
+}
+
+static int launch_reduce_fwd(ReduceFwdArgs a, cudaStream_t st) {
+  const int max_tc = (int)(GRP_SMEM_MAX / ((size_t)a.N * sizeof(float)));
+  const bool smem = max_tc >= 1;
+  const int target = 4 * num_sms();
+  int TC = 1;
+  for (int t = 8; t >= 1; t >>= 1) {
+    if (t > a.C && t > 1) continue;
+    if (smem && t > max_tc) continue;
+    TC = t;
+    if ((long long)a.B * ceil_div(a.C, t) >= target) break;
+  }
+  a.TC = TC;
+  int mt = max(1, ceil_div(target, a.B * ceil_div(a.C, TC)));
+  mt = min(mt, max(1, a.M / GRP_THREADS));
+  a.MT = ceil_div(ceil_div(a.M, mt), GRP_THREADS) * GRP_THREADS;
+  dim3 grid(ceil_div(a.M, a.MT), ceil_div(a.C, TC), a.B);
+  const size_t sm = smem ? (size_t)TC * a.N * sizeof(float) : 0;
+  if (smem) {
+    auto kern = group_reduce_fwd_kernel<true>;
+    if (sm > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, GRP_THREADS, sm, st>>>(a);
+  } else {
+    group_reduce_fwd_kernel<false><<<grid, GRP_THREADS, 0, st>>>(a);
+  }
+  TPG_CHECK_LAUNCH("group_reduce_fwd_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_group_reduce_fwd_f32(const float* f, const int32_t* idx, int B, int C, int N, int M, int k,
+                                     int op, float* out, int32_t* arg, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 0 && M >= 0, TPG_EINVAL, "group_reduce_fwd: negative size");
+  TPG_REQUIRE(k >= 1, TPG_EINVAL, "group_reduce_fwd: k must be >= 1");
+  TPG_REQUIRE(op >= 0 && op <= 2, TPG_EINVAL, "group_reduce_fwd: bad op %d", op);
+  if (B == 0 || C == 0 || M == 0) return TPG_OK;
+  TPG_REQUIRE(N >= 1 && f && idx && out, TPG_EINVAL, "group_reduce_fwd: null pointer / empty cloud");
+  TPG_REQUIRE(B <= 65535 && C <= 65535 * 8, TPG_EUNSUPPORTED, "group_reduce_fwd: B or C too large");
+  ReduceFwdArgs a{f, idx, nullptr, B, C, N, M, k, op, 1, GRP_THREADS, out, op == TPG_REDUCE_SUM ? nullptr : arg};
+  return launch_reduce_fwd(a, as_stream(stream));
+}
+
+TPG_API int tpg_three_interpolate_fwd_f32(const float* f, const int32_t* idx, const float* w, int B, int c,
+                                          int m, int n, float* out, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && c >= 0 && m >= 0 && n >= 0, TPG_EINVAL, "three_interpolate_fwd: negative size");
+  if (B == 0 || c == 0 || n == 0) return TPG_OK;
+  TPG_REQUIRE(m >= 1 && f && idx && w && out, TPG_EINVAL, "three_interpolate_fwd: null pointer / empty cloud");
+  TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "three_interpolate_fwd: B too large");
+  ReduceFwdArgs a{f, idx, w, B, c, m, n, 3, TPG_REDUCE_SUM, 1, GRP_THREADS, out, nullptr};
+  return launch_reduce_fwd(a, as_stream(stream));
+}
+
+namespace tpg {
+size_t csr_workspace_bytes(int B, int N, int L) {
+  return align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256) + align_up(sizeof(int32_t) * (size_t)B * (size_t)L, 256);
+}
+
+int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, int32_t* seg_offsets,
+              int32_t* seg_items, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TPG_REQUIRE(B >= 0 && N >= 0 && L >= 0, TPG_EINVAL, "inverse_index: negative size");
+  if (B == 0) return TPG_OK;
+  TPG_REQUIRE(seg_offsets, TPG_EINVAL, "inverse_index: null seg_offsets");
+  TPG_CUDA(cudaMemsetAsync(seg_offsets, 0, sizeof(int32_t) * (size_t)B * (N + 1), st));
+  if (N == 0 || L == 0) return TPG_OK;
+  TPG_REQUIRE(idx && seg_items, TPG_EINVAL, "inverse_index: null pointer");
+  TPG_REQUIRE(workspace && workspace_bytes >= csr_workspace_bytes(B, N, L), TPG_EWORKSPACE,
+              "inverse_index: workspace too small");
+  int32_t* cursor = reinterpret_cast<int32_t*>(workspace);
+  int32_t* tmp = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) +
+                                            align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256));
+  const long long total = (long long)B * L;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)min((total + threads - 1) / threads, (long long)num_sms() * 32);
+  csr_count_kernel<<<blocks, threads, 0, st>>>(idx, item_len, B, N, L, seg_offsets);
+  TPG_CHECK_LAUNCH("csr_count_kernel");
+  csr_scan_kernel<<<B, 1024, 0, st>>>(seg_offsets, cursor, N);
+  TPG_CHECK_LAUNCH("csr_scan_kernel");
+  csr_fill_kernel<<<blocks, threads, 0, st>>>(idx, item_len, B, N, L, cursor, tmp);
+  TPG_CHECK_LAUNCH("csr_fill_kernel");
+  const long long segs = (long long)B * N;
+  csr_sort_kernel<<<(unsigned)((segs + 7) / 8), 256, 0, st>>>(seg_offsets, tmp, B, N, L, seg_items);
+  TPG_CHECK_LAUNCH("csr_sort_kernel");
+  return TPG_OK;
+}
+}  // namespace tpg
+
+TPG_API size_t tpg_inverse_index_workspace_bytes(int B, int N, int L) { return tpg::csr_workspace_bytes(B, N, L); }
+
+TPG_API int tpg_inverse_index_build(const int32_t* idx, int B, int N, int L, int32_t* seg_offsets,
+                                    int32_t* seg_items, void* workspace, size_t workspace_bytes,
+                                    tpg_stream_t stream) {
+  return tpg::build_csr(idx, nullptr, B, N, L, seg_offsets, seg_items, workspace, workspace_bytes, as_stream(stream));
+}
+
+static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+  TPG_REQUIRE(a.C <= 65535 && a.B <= 65535, TPG_EUNSUPPORTED, "group_bwd: B or C too large");
+  dim3 grid(ceil_div(a.N, GRP_THREADS), a.C, a.B);
+  group_bwd_kernel<<<grid, GRP_THREADS, 0, st>>>(a);
+  TPG_CHECK_LAUNCH("group_bwd_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_group_bwd_f32(const float* grad_out, const int32_t* seg_offsets, const int32_t* seg_items,
+                              int B, int C, int N, int L, float* grad_f, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 0 && L >= 0, TPG_EINVAL, "group_bwd: negative size");
+  if (B == 0 || C == 0 || N == 0) return TPG_OK;
+  TPG_REQUIRE(grad_f && seg_offsets && (L == 0 || (grad_out && seg_items)), TPG_EINVAL, "group_bwd: null pointer");
+  BwdArgs a{grad_out, nullptr, nullptr, seg_offsets, seg_items, B, C, N, 0, 1, L, BWD_GROUP, grad_f};
+  return launch_bwd(a, as_stream(stream));
+}
+
+TPG_API int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg, const int32_t* seg_offsets,
+                                     const int32_t* seg_items, int B, int C, int N, int M, int k, int op,
+                                     float* grad_f, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 0 && M >= 0 && k >= 1, TPG_EINVAL, "group_reduce_bwd: bad size");
+  TPG_REQUIRE(op >= 0 && op <= 2, TPG_EINVAL, "group_reduce_bwd: bad op %d", op);
+  if (B == 0 || C == 0 || N == 0) return TPG_OK;
+  TPG_REQUIRE(grad_f && seg_offsets, TPG_EINVAL, "group_reduce_bwd: null pointer");
+  TPG_REQUIRE(op == TPG_REDUCE_SUM || arg, TPG_EINVAL, "group_reduce_bwd: max/min need arg");
+  BwdArgs a{grad_out, arg, nullptr, seg_offsets, seg_items, B, C, N, M, k, M * k,
+            op == TPG_REDUCE_SUM ? BWD_SUM : BWD_ARG, grad_f};
+  return launch_bwd(a, as_stream(stream));
+}
+
+TPG_API int tpg_three_interpolate_bwd_f32(const float* grad_out, const float* w, const int32_t* seg_offsets,
+                                          const int32_t* seg_items, int B, int c, int m, int n, float* grad_f,
+                                          tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && c >= 0 && m >= 0 && n >= 0, TPG_EINVAL, "three_interpolate_bwd: negative size");
+  if (B == 0 || c == 0 || m == 0) return TPG_OK;
+  TPG_REQUIRE(grad_f && seg_offsets && w, TPG_EINVAL, "three_interpolate_bwd: null pointer");
+  BwdArgs a{grad_out, nullptr, w, seg_offsets, seg_items, B, c, m, n, 3, n * 3, BWD_WEIGHTED, grad_f};
+  return launch_bwd(a, as_stream(stream));
+}

@@ -1,0 +1,33 @@
+// internal.cuh — cross-file internals of libtpugan_b200.so (not part of the ABI).
+#pragma once
+#include "common.cuh"
+
+namespace tpg {
+
+enum { OUT_KNN = 0, OUT_FRNN = 1, OUT_THREE = 2 };
+
+struct KnnArgs {
+  const float* p1;
+  const float* p2;
+  const int64_t* len1;
+  const int64_t* len2;
+  int B, P1, P2, D, K;
+  float r;
+  const float* r_per_cloud;
+  int use_radius;
+  float* dists;
+  void* idx;
+  int out_mode;
+};
+
+// knn.cu
+int knn_dispatch(const KnnArgs& a, cudaStream_t st);
+
+// group.cu — inverse index (CSR) of an int32 index tensor idx [B,L] with keys in
+// [0,N): seg_offsets [B,N+1], seg_items [B,L] (ascending positions per key).
+// item_len (device [B] int64 or null) limits the positions of cloud b to [0,len).
+size_t csr_workspace_bytes(int B, int N, int L);
+int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, int32_t* seg_offsets,
+              int32_t* seg_items, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+}  // namespace tpg

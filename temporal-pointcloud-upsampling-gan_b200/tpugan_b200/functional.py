@@ -1,0 +1,442 @@
+"""Tensor-level front-end of the sm_100a kernels (PyTorch is plumbing: memory + streams).
+
+Every function validates its arguments the way the upstream extension it replaces
+does, allocates outputs/workspace with the caching allocator, and launches on
+``torch.cuda.current_stream()``.  No function synchronises or reads back.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, name, dtype, ndim=None, exc=RuntimeError):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise exc(f"{name} must be a CUDA tensor (tpugan_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise exc(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise exc(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise exc(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
+
+
+def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def _lengths(lengths, B, P, device, name):
+    if lengths is None:
+        return None
+    if not isinstance(lengths, torch.Tensor):
+        lengths = torch.as_tensor(lengths)
+    if lengths.shape != (B,):
+        raise ValueError(f"{name} must have shape (N,).")
+    return lengths.to(device=device, dtype=torch.int64).contiguous()
+
+
+# --------------------------------------------------------------------------- kNN / FRNN
+def knn(p1, p2, K: int, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K nearest by squared L2, (d2, idx) ascending.  p1 [B,P1,D], p2 [B,P2,D] ->
+    dists [B,P1,K] f32, idx [B,P1,K] int64.  (pytorch3d knn_points; gcn_lib/pointnet/gcn.py:16)"""
+    _req(p1, "p1", torch.float32, 3)
+    _req(p2, "p2", torch.float32, 3)
+    if p1.shape[2] != p2.shape[2]:
+        raise ValueError("pts1 and pts2 must have the same point dimension.")
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    B, P1, D = p1.shape
+    P2 = p2.shape[1]
+    l1 = _lengths(lengths1, B, P1, p1.device, "lengths1")
+    l2 = _lengths(lengths2, B, P2, p1.device, "lengths2")
+    dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+    idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    with torch.cuda.device(p1.device):
+        _lib.call("tpg_knn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, _ptr(dists), _ptr(idx),
+                  _stream())
+    return dists, idx
+
+
+def frnn(p1, p2, K: int, r, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K nearest with d2 < r^2, -1 padded.  (frnn.frnn_grid_points; discriminator.py:27)"""
+    _req(p1, "points1", torch.float32, 3, exc=TypeError)
+    _req(p2, "points2", torch.float32, 3, exc=TypeError)
+    if p1.shape[2] != p2.shape[2]:
+        raise ValueError("pts1 and pts2 must have the same point dimension.")
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    B, P1, D = p1.shape
+    P2 = p2.shape[1]
+    l1 = _lengths(lengths1, B, P1, p1.device, "lengths1")
+    l2 = _lengths(lengths2, B, P2, p1.device, "lengths2")
+    r_dev = None
+    r_host = 0.0
+    if isinstance(r, torch.Tensor):
+        if r.numel() == 1 and not r.is_cuda:
+            r_host = float(r)
+        else:
+            r_dev = r.to(device=p1.device, dtype=torch.float32).expand(B).contiguous()
+    else:
+        r_host = float(r)
+    dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+    idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    with torch.cuda.device(p1.device):
+        nbytes = _lib.load().tpg_frnn_workspace_bytes(B, P1, P2, D, K)
+        ws = _ws(nbytes, p1.device)
+        _lib.call("tpg_frnn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, r_host, _ptr(r_dev),
+                  _ptr(dists), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    return dists, idx
+
+
+def ball_query(radius: float, nsample: int, xyz, new_xyz) -> torch.Tensor:
+    """pointnet2 ball_query: xyz [B,N,3], new_xyz [B,M,3] -> int32 [B,M,nsample]."""
+    _req(xyz, "xyz", torch.float32, 3)
+    _req(new_xyz, "new_xyz", torch.float32, 3)
+    if xyz.shape[2] != 3 or new_xyz.shape[2] != 3 or xyz.shape[0] != new_xyz.shape[0]:
+        raise RuntimeError("ball_query expects xyz (B,N,3) and new_xyz (B,M,3)")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.call("tpg_ball_query_f32", _ptr(xyz), _ptr(new_xyz), B, N, M, float(radius), int(nsample), _ptr(idx),
+                  _stream())
+    return idx
+
+
+# --------------------------------------------------------------------------- FPS
+def fps(xyz, npoint: int) -> torch.Tensor:
+    """pointnet2 furthest_point_sample: xyz [B,N,3] -> int32 [B,npoint] (discriminator.py:114)."""
+    _req(xyz, "xyz", torch.float32, 3)
+    if xyz.shape[2] != 3:
+        raise RuntimeError("furthest_point_sample expects xyz (B,N,3)")
+    B, N, _ = xyz.shape
+    out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        nbytes = _lib.load().tpg_fps_workspace_bytes(B, N)
+        ws = _ws(nbytes, xyz.device)
+        _lib.call("tpg_fps_f32", _ptr(xyz), B, N, int(npoint), _ptr(out), _ptr(ws), ws.numel() if nbytes else 0,
+                  _stream())
+    return out
+
+
+def fps_start(pts, k: int, start, return_rows: bool = False):
+    """sampling.py mode: pts [B,N,D<=3], start [B] -> int64 [B,k] (+ rows [B,k,N])."""
+    _req(pts, "pts", torch.float32, 3)
+    B, N, D = pts.shape
+    start = torch.as_tensor(start, dtype=torch.int64, device=pts.device).expand(B).contiguous()
+    out = torch.empty((B, k), dtype=torch.int64, device=pts.device)
+    rows = torch.empty((B, k, N), dtype=torch.float32, device=pts.device) if return_rows else None
+    with torch.cuda.device(pts.device):
+        nbytes = _lib.load().tpg_fps_workspace_bytes(B, N)
+        ws = _ws(nbytes, pts.device)
+        _lib.call("tpg_fps_start_f32", _ptr(pts), B, N, D, int(k), _ptr(start), _ptr(out), _ptr(rows), _ptr(ws),
+                  ws.numel() if nbytes else 0, _stream())
+    return (out, rows) if return_rows else out
+
+
+# --------------------------------------------------------------------------- grouping
+def group_fwd(f, idx, center=None) -> torch.Tensor:
+    """f [B,C,N], idx int32 [B,M,k] -> [B,C,M,k] (optionally minus center [B,C,M])."""
+    _req(f, "features", torch.float32, 3)
+    _req(idx, "idx", torch.int32, 3)
+    B, C, N = f.shape
+    if idx.shape[0] != B:
+        raise RuntimeError("grouping_operation: batch mismatch between features and idx")
+    _, M, k = idx.shape
+    if center is not None:
+        _req(center, "center", torch.float32, 3)
+        if tuple(center.shape) != (B, C, M):
+            raise RuntimeError("group_fwd: center must be [B,C,M]")
+    out = torch.empty((B, C, M, k), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.call("tpg_group_fwd_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _stream())
+    return out
+
+
+def inverse_index(idx, N: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """CSR of idx int32 [B, ...] with keys in [0,N): (seg_offsets [B,N+1], seg_items [B,L])."""
+    _req(idx, "idx", torch.int32)
+    B = idx.shape[0]
+    L = idx.numel() // max(B, 1)
+    off = torch.empty((B, N + 1), dtype=torch.int32, device=idx.device)
+    items = torch.empty((B, max(L, 1)), dtype=torch.int32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        nbytes = _lib.load().tpg_inverse_index_workspace_bytes(B, N, L)
+        ws = _ws(nbytes, idx.device)
+        _lib.call("tpg_inverse_index_build", _ptr(idx), B, N, L, _ptr(off), _ptr(items), _ptr(ws), ws.numel(),
+                  _stream())
+    return off, items
+
+
+class _CsrCache:
+    """Inverse indices keyed by the idx tensor they were built from.  Holding the idx
+    tensor keeps its storage alive, so (data_ptr, version) cannot alias a new tensor."""
+
+    def __init__(self, capacity: int = 16):
+        self.capacity = capacity
+        self.entries: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+    def get(self, idx: torch.Tensor, N: int):
+        key = (idx.data_ptr(), idx._version, tuple(idx.shape), N, idx.device.index)
+        hit = self.entries.get(key)
+        if hit is not None:
+            self.entries.move_to_end(key)
+            return hit[1], hit[2]
+        off, items = inverse_index(idx, N)
+        self.entries[key] = (idx, off, items)
+        while len(self.entries) > self.capacity:
+            self.entries.popitem(last=False)
+        return off, items
+
+    def clear(self):
+        self.entries.clear()
+
+
+csr_cache = _CsrCache()
+
+
+def group_bwd(grad_out, off, items, N: int) -> torch.Tensor:
+    """grad_out [B,C,M,k] (or [B,C,L]) -> grad_f [B,C,N] through the CSR."""
+    _req(grad_out, "grad_out", torch.float32)
+    B, C = grad_out.shape[0], grad_out.shape[1]
+    L = grad_out.numel() // max(B * C, 1)
+    gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("tpg_group_bwd_f32", _ptr(grad_out), _ptr(off), _ptr(items), B, C, N, L, _ptr(gf), _stream())
+    return gf
+
+
+def group_reduce_fwd(f, idx, op: int = _lib.REDUCE_MAX, want_arg: bool = True):
+    """Fused gather + reduce over k: f [B,C,N], idx int32 [B,M,k] -> out [B,C,M] (+ arg int32)."""
+    _req(f, "features", torch.float32, 3)
+    _req(idx, "idx", torch.int32, 3)
+    B, C, N = f.shape
+    _, M, k = idx.shape
+    out = torch.empty((B, C, M), dtype=torch.float32, device=f.device)
+    arg = torch.empty((B, C, M), dtype=torch.int32, device=f.device) if (want_arg and op != _lib.REDUCE_SUM) else None
+    with torch.cuda.device(f.device):
+        _lib.call("tpg_group_reduce_fwd_f32", _ptr(f), _ptr(idx), B, C, N, M, k, int(op), _ptr(out), _ptr(arg),
+                  _stream())
+    return out, arg
+
+
+def group_reduce_bwd(grad_out, arg, off, items, N: int, k: int, op: int) -> torch.Tensor:
+    _req(grad_out, "grad_out", torch.float32, 3)
+    B, C, M = grad_out.shape
+    gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("tpg_group_reduce_bwd_f32", _ptr(grad_out), _ptr(arg), _ptr(off), _ptr(items), B, C, N, M, k,
+                  int(op), _ptr(gf), _stream())
+    return gf
+
+
+# --------------------------------------------------------------------------- three_nn / interpolate
+def three_nn(unknown, known):
+    _req(unknown, "unknown", torch.float32, 3)
+    _req(known, "known", torch.float32, 3)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        _lib.call("tpg_three_nn_f32", _ptr(unknown), _ptr(known), B, n, m, _ptr(dist), _ptr(idx), _stream())
+    return dist, idx
+
+
+def three_interpolate_fwd(f, idx, w):
+    _req(f, "features", torch.float32, 3)
+    _req(idx, "idx", torch.int32, 3)
+    _req(w, "weight", torch.float32, 3)
+    B, c, m = f.shape
+    n = idx.shape[1]
+    out = torch.empty((B, c, n), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.call("tpg_three_interpolate_fwd_f32", _ptr(f), _ptr(idx), _ptr(w), B, c, m, n, _ptr(out), _stream())
+    return out
+
+
+def three_interpolate_bwd(grad_out, w, off, items, m: int):
+    _req(grad_out, "grad_out", torch.float32, 3)
+    B, c, n = grad_out.shape
+    gf = torch.empty((B, c, m), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("tpg_three_interpolate_bwd_f32", _ptr(grad_out), _ptr(w), _ptr(off), _ptr(items), B, c, m, n,
+                  _ptr(gf), _stream())
+    return gf
+
+
+# --------------------------------------------------------------------------- Chamfer
+def chamfer_fwd(src, tgt, directions: int, lengths_src=None, lengths_tgt=None):
+    _req(src, "source_cloud", torch.float32, 3)
+    _req(tgt, "target_cloud", torch.float32, 3)
+    B, P1, D = src.shape
+    P2 = tgt.shape[1]
+    dev = src.device
+    f, r = bool(directions & 1), bool(directions & 2)
+    d_s = torch.empty((B, P1), dtype=torch.float32, device=dev) if f else None
+    i_s = torch.empty((B, P1), dtype=torch.int32, device=dev) if f else None
+    s_s = torch.empty((B,), dtype=torch.float32, device=dev) if f else None
+    d_t = torch.empty((B, P2), dtype=torch.float32, device=dev) if r else None
+    i_t = torch.empty((B, P2), dtype=torch.int32, device=dev) if r else None
+    s_t = torch.empty((B,), dtype=torch.float32, device=dev) if r else None
+    with torch.cuda.device(dev):
+        _lib.call("tpg_chamfer_fwd_f32", _ptr(src), _ptr(tgt), _ptr(lengths_src), _ptr(lengths_tgt), B, P1, P2, D,
+                  int(directions), _ptr(d_s), _ptr(i_s), _ptr(d_t), _ptr(i_t), _ptr(s_s), _ptr(s_t), _stream())
+    return dict(d_src=d_s, i_src=i_s, sum_src=s_s, d_tgt=d_t, i_tgt=i_t, sum_tgt=s_t)
+
+
+def chamfer_bwd(src, tgt, i_src, i_tgt, g_src, g_tgt, directions: int, need_src=True, need_tgt=True,
+                lengths_src=None, lengths_tgt=None):
+    B, P1, D = src.shape
+    P2 = tgt.shape[1]
+    dev = src.device
+    gs = torch.empty_like(src) if need_src else None
+    gt = torch.empty_like(tgt) if need_tgt else None
+    with torch.cuda.device(dev):
+        nbytes = _lib.load().tpg_chamfer_bwd_workspace_bytes(B, P1, P2)
+        ws = _ws(nbytes, dev)
+        _lib.call("tpg_chamfer_bwd_f32", _ptr(src), _ptr(tgt), _ptr(lengths_src), _ptr(lengths_tgt), _ptr(i_src),
+                  _ptr(i_tgt), _ptr(g_src), _ptr(g_tgt), B, P1, P2, D, int(directions), _ptr(gs), _ptr(gt), _ptr(ws),
+                  ws.numel(), _stream())
+    return gs, gt
+
+
+# --------------------------------------------------------------------------- cubic interpolation
+def cubic_interp(query, field, pos, cutoff: float) -> torch.Tensor:
+    """Batched gcn_lib.cubic_interpolation: query [S,Q,3], field [S,P,F], pos [S,P,3] -> [S,Q,F]."""
+    _req(query, "query_pos", torch.float32, 3)
+    _req(field, "field", torch.float32, 3)
+    _req(pos, "pos", torch.float32, 3)
+    S, Q, _ = query.shape
+    P, F = field.shape[1], field.shape[2]
+    if pos.shape != (S, P, 3) or query.shape[2] != 3:
+        raise ValueError("cubic_interp: expected query [S,Q,3], field [S,P,F], pos [S,P,3]")
+    out = torch.empty((S, Q, F), dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        nbytes = _lib.load().tpg_cubic_interp_workspace_bytes(S, Q, P)
+        ws = _ws(nbytes, query.device)
+        _lib.call("tpg_cubic_interp_f32", _ptr(query), _ptr(field), _ptr(pos), S, Q, P, F, float(cutoff), _ptr(out),
+                  _ptr(ws), ws.numel(), _stream())
+    return out
+
+
+def gather_rows(x, idx) -> torch.Tensor:
+    """x [B,N,U], idx int64 [B,L] -> [B,L,U] (negative indices wrap)."""
+    _req(x, "x", torch.float32, 3)
+    _req(idx, "idx", torch.int64, 2)
+    B, N, U = x.shape
+    L = idx.shape[1]
+    out = torch.empty((B, L, U), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("tpg_gather_rows_f32", _ptr(x), _ptr(idx), B, N, U, L, _ptr(out), _stream())
+    return out
+
+
+# =========================================================================== autograd
+class GroupingOperation(torch.autograd.Function):
+    """pointnet2_utils.GroupingOperation (gcn_lib/pointnet/gcn.py:207)."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.N = features.shape[2]
+        ctx.save_for_backward(idx)
+        return group_fwd(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        off, items = csr_cache.get(idx, ctx.N)
+        return group_bwd(grad_out.contiguous(), off, items, ctx.N), None
+
+
+class GatherOperation(torch.autograd.Function):
+    """pointnet2_utils.GatherOperation (discriminator.py:132): the k == 1 grouping."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        _req(idx, "idx", torch.int32, 2)
+        ctx.N = features.shape[2]
+        ctx.save_for_backward(idx)
+        return group_fwd(features, idx.unsqueeze(-1)).squeeze(-1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        off, items = csr_cache.get(idx, ctx.N)
+        return group_bwd(grad_out.contiguous(), off, items, ctx.N), None
+
+
+class GroupReduce(torch.autograd.Function):
+    """Fused grouping + max/sum/min over the neighbour axis (gcn_lib/pointnet/gcn.py:261-263)."""
+
+    @staticmethod
+    def forward(ctx, features, idx, op):
+        out, arg = group_reduce_fwd(features, idx, op, want_arg=True)
+        ctx.N, ctx.k, ctx.op = features.shape[2], idx.shape[2], op
+        ctx.save_for_backward(idx, arg if arg is not None else idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, arg = ctx.saved_tensors
+        off, items = csr_cache.get(idx, ctx.N)
+        gf = group_reduce_bwd(grad_out.contiguous(), None if ctx.op == _lib.REDUCE_SUM else arg, off, items, ctx.N,
+                              ctx.k, ctx.op)
+        return gf, None, None
+
+
+class ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        ctx.m = features.shape[2]
+        ctx.save_for_backward(idx, weight)
+        return three_interpolate_fwd(features, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        off, items = csr_cache.get(idx, ctx.m)
+        return three_interpolate_bwd(grad_out.contiguous(), weight, off, items, ctx.m), None, None
+
+
+class ChamferSums(torch.autograd.Function):
+    """Per-cloud Chamfer sums (sum_src [B], sum_tgt [B]); reductions over the batch stay
+    in torch so every chamferdist reduction mode maps onto the same two kernels."""
+
+    @staticmethod
+    def forward(ctx, src, tgt, directions):
+        r = chamfer_fwd(src, tgt, directions)
+        ctx.directions = directions
+        z = torch.zeros((src.shape[0],), dtype=torch.float32, device=src.device)
+        i_s = r["i_src"] if r["i_src"] is not None else torch.empty(0, dtype=torch.int32, device=src.device)
+        i_t = r["i_tgt"] if r["i_tgt"] is not None else torch.empty(0, dtype=torch.int32, device=src.device)
+        ctx.save_for_backward(src, tgt, i_s, i_t)
+        return (r["sum_src"] if r["sum_src"] is not None else z), (r["sum_tgt"] if r["sum_tgt"] is not None else z)
+
+    @staticmethod
+    def backward(ctx, g_src, g_tgt):
+        src, tgt, i_s, i_t = ctx.saved_tensors
+        need_src, need_tgt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_src or need_tgt):
+            return None, None, None
+        gs, gt = chamfer_bwd(src, tgt, i_s if i_s.numel() else None, i_t if i_t.numel() else None,
+                             g_src.contiguous(), g_tgt.contiguous(), ctx.directions, need_src, need_tgt)
+        return gs, gt, None

@@ -1,0 +1,401 @@
+"""GPU parity: every kernel, through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Bar: bit-exact for indices and for values that are pure copies / single
+roundings; rtol 1e-5 for sums whose association differs (Chamfer totals, interpolation)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: "within 1e-5 relative (fp32)"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def F():
+    import tpugan_b200.functional as F_
+
+    return F_
+
+
+# ----------------------------------------------------------------------------- kNN
+KNN_CASES = [
+    # B, P1, P2, D, K, kind
+    (2, 257, 300, 3, 1, "fluid"),
+    (2, 300, 257, 3, 20, "fluid"),
+    (1, 2048, 2048, 3, 20, "fluid"),
+    (2, 512, 512, 3, 32, "dup"),
+    (2, 400, 400, 3, 16, "dummy"),
+    (1, 343, 343, 3, 9, "lattice"),
+    (2, 256, 256, 32, 9, "feat"),
+    (2, 256, 256, 32, 20, "feat"),
+    (2, 200, 333, 64, 12, "feat"),
+    (1, 128, 128, 64, 4, "featdup"),
+    (1, 100, 100, 5, 7, "feat"),
+    (1, 64, 50, 130, 8, "feat"),
+    (1, 50, 10, 3, 16, "fluid"),     # K > P2 -> zero padding
+    (1, 70, 200, 3, 40, "fluid"),    # K > 32 -> multi-pass
+    (1, 40, 300, 3, 100, "dup"),
+]
+
+
+def make_pair(rng, B, P1, P2, D, kind):
+    if kind == "lattice":
+        side = round(P1 ** (1 / 3))
+        p = synth.lattice_cloud(B, side)
+        return p, p
+    if kind in ("feat", "featdup"):
+        a = rng.standard_normal((B, P1, D)).astype(np.float32)
+        b = rng.standard_normal((B, P2, D)).astype(np.float32)
+        if kind == "featdup":
+            b = synth.with_duplicates(rng, b, 0.5)
+            a = b[:, :P1].copy()
+        return a, b
+    a = synth.fluid_cloud(rng, B, P1, D)
+    b = synth.fluid_cloud(rng, B, P2, D)
+    if kind == "dup":
+        b = synth.with_duplicates(rng, b, 0.4)
+        a = b[:, :P1].copy() if P1 <= P2 else a
+    if kind == "dummy":
+        b = synth.with_dummies(rng, b, 0.3)
+        a = b.copy() if P1 == P2 else a
+    return a, b
+
+
+@pytest.mark.parametrize("B,P1,P2,D,K,kind", KNN_CASES)
+def test_knn_bit_exact(F, oracle, B, P1, P2, D, K, kind):
+    rng = np.random.default_rng(1)
+    a, b = make_pair(rng, B, P1, P2, D, kind)
+    P1, P2 = a.shape[1], b.shape[1]
+    od, oi = oracle.knn(a, b, K)
+    gd, gi = F.knn(cu(a), cu(b), K)
+    assert gi.dtype == torch.int64 and gd.dtype == torch.float32
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_knn_ragged_lengths(F, oracle):
+    rng = np.random.default_rng(2)
+    a = synth.fluid_cloud(rng, 3, 200, 3)
+    b = synth.fluid_cloud(rng, 3, 260, 3)
+    l1 = np.array([200, 17, 0], np.int64)
+    l2 = np.array([260, 5, 100], np.int64)
+    od, oi = oracle.knn(a, b, 8, l1, l2)
+    gd, gi = F.knn(cu(a), cu(b), 8, cu(l1), cu(l2))
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_knn_empty(F):
+    d, i = F.knn(torch.zeros(2, 0, 3, device="cuda"), torch.zeros(2, 5, 3, device="cuda"), 4)
+    assert d.shape == (2, 0, 4) and i.shape == (2, 0, 4)
+    d, i = F.knn(torch.zeros(1, 6, 3, device="cuda"), torch.zeros(1, 0, 3, device="cuda"), 4)
+    assert float(d.abs().sum()) == 0 and int(i.abs().sum()) == 0
+
+
+# ----------------------------------------------------------------------------- FRNN
+FRNN_CASES = [
+    (2, 300, 400, 1, 1.9 * 0.025, "fluid"),     # masking_loss first search (loss.py:256)
+    (2, 400, 400, 16, 1.4 * 0.025, "fluid"),    # masking_loss second search (loss.py:261)
+    (2, 256, 256, 32, 2.0, "action"),           # FlowEmbedding (discriminator.py:27, r = 20 R)
+    (1, 300, 300, 32, 0.16, "fluid"),           # cubic_interpolation (interpolation.py:20)
+    (1, 343, 343, 8, 0.025 * 1.0001, "lattice"),  # points on / just inside the radius
+    (1, 343, 343, 8, 0.025, "lattice"),
+    (2, 200, 200, 8, 0.03, "dummy"),
+    (1, 100, 100, 48, 0.5, "fluid"),            # K > 32
+]
+
+
+@pytest.mark.parametrize("B,P1,P2,K,r,kind", FRNN_CASES)
+def test_frnn_bit_exact(F, oracle, B, P1, P2, K, r, kind):
+    rng = np.random.default_rng(3)
+    if kind == "action":
+        a, b = synth.action_cloud(rng, B, P1), synth.action_cloud(rng, B, P2)
+    else:
+        a, b = make_pair(rng, B, P1, P2, 3, kind)
+    od, oi = oracle.frnn(a, b, K, r)
+    gd, gi = F.frnn(cu(a), cu(b), K, r)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_frnn_per_cloud_radius_and_lengths(F, oracle):
+    rng = np.random.default_rng(4)
+    a = synth.fluid_cloud(rng, 3, 150, 3)
+    b = synth.fluid_cloud(rng, 3, 180, 3)
+    r = np.array([0.03, 0.05, 0.2], np.float32)
+    l1 = np.array([150, 100, 3], np.int64)
+    l2 = np.array([180, 0, 77], np.int64)
+    od, oi = oracle.frnn(a, b, 8, r, l1, l2)
+    gd, gi = F.frnn(cu(a), cu(b), 8, cu(r), cu(l1), cu(l2))
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+# ----------------------------------------------------------------------------- ball query / FPS
+@pytest.mark.parametrize("B,N,M,r,ns,kind", [
+    (2, 1000, 128, 0.15, 32, "fluid"), (2, 512, 512, 0.05, 16, "fluid"), (1, 300, 50, 0.01, 8, "fluid"),
+    (2, 600, 100, 0.3, 64, "action"), (1, 343, 343, 0.025, 8, "lattice"), (2, 400, 64, 0.1, 32, "dummy"),
+])
+def test_ball_query_bit_exact(F, oracle, B, N, M, r, ns, kind):
+    rng = np.random.default_rng(5)
+    if kind == "action":
+        xyz = synth.action_cloud(rng, B, N)
+    elif kind == "lattice":
+        xyz = synth.lattice_cloud(B, round(N ** (1 / 3)))
+    else:
+        xyz = synth.fluid_cloud(rng, B, N)
+        if kind == "dummy":
+            xyz = synth.with_dummies(rng, xyz)
+    new_xyz = np.ascontiguousarray(xyz[:, :: max(1, xyz.shape[1] // M)][:, :M])
+    o = oracle.ball_query(r, ns, xyz, new_xyz)
+    g = F.ball_query(r, ns, cu(xyz), cu(new_xyz))
+    assert g.dtype == torch.int32
+    np.testing.assert_array_equal(g.cpu().numpy(), o)
+
+
+@pytest.mark.parametrize("B,N,npoint,kind", [
+    (2, 1024, 128, "fluid"), (2, 2048, 512, "fluid"), (1, 8192, 1024, "fluid"), (2, 777, 100, "dup"),
+    (2, 500, 500, "dummy"), (1, 343, 64, "lattice"), (1, 5000, 64, "fluid"), (1, 9000, 40, "fluid"), (3, 33, 33, "fluid"),
+])
+def test_fps_pointnet2_bit_exact(F, oracle, B, N, npoint, kind):
+    rng = np.random.default_rng(6)
+    if kind == "lattice":
+        xyz = synth.lattice_cloud(B, round(N ** (1 / 3)))
+        xyz = xyz - xyz.mean(1, keepdims=True)  # centre: some points fall in the |p|^2 <= 1e-3 shell
+    else:
+        xyz = synth.fluid_cloud(rng, B, N)
+        if kind == "dup":
+            xyz = synth.with_duplicates(rng, xyz)
+        if kind == "dummy":
+            xyz = synth.with_dummies(rng, xyz)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    o = oracle.fps(xyz, npoint)
+    g = F.fps(cu(xyz), npoint)
+    assert g.dtype == torch.int32
+    np.testing.assert_array_equal(g.cpu().numpy(), o)
+
+
+def test_fps_origin_skip_quirk(F, oracle):
+    """Points with |p|^2 <= 1e-3 are never selected (except forced index 0)."""
+    rng = np.random.default_rng(7)
+    xyz = (rng.uniform(-0.05, 0.05, size=(2, 600, 3))).astype(np.float32)  # most points inside the shell 0.0316
+    o = oracle.fps(xyz, 64)
+    g = F.fps(cu(xyz), 64).cpu().numpy()
+    np.testing.assert_array_equal(g, o)
+
+
+@pytest.mark.parametrize("N,k,D", [(2048, 128, 3), (9216, 200, 3), (500, 500, 2), (1000, 10, 3)])
+def test_fps_sampling_py_mode_bit_exact(F, oracle, N, k, D):
+    rng = np.random.default_rng(8)
+    pts = synth.fluid_cloud(rng, 2, N, D)
+    start = np.array([5, N - 1], np.int64)
+    oi, orows = oracle.fps_start(pts, k, start, return_rows=True)
+    gi, grows = F.fps_start(cu(pts), k, cu(start), return_rows=True)
+    assert gi.dtype == torch.int64
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(grows.cpu().numpy(), orows)
+    gi2 = F.fps_start(cu(pts), k, cu(start))
+    np.testing.assert_array_equal(gi2.cpu().numpy(), oi)
+
+
+# ----------------------------------------------------------------------------- grouping
+GROUP_CASES = [
+    # B, C, N, M, k
+    (2, 64, 512, 512, 12), (2, 32, 256, 256, 9), (1, 3, 2048, 256, 32), (2, 16, 300, 77, 5), (2, 7, 129, 64, 3),
+    (1, 128, 1024, 1024, 20), (2, 3, 8192, 1024, 32), (1, 2, 30000, 100, 8), (1, 1, 10, 4, 1), (2, 5, 100, 100, 1),
+]
+
+
+def make_group(rng, B, C, N, M, k, hubs=False):
+    f = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, size=(B, M, k)).astype(np.int32)
+    if hubs:
+        idx[:, : M // 2, :] = rng.integers(0, min(N, 3), size=(B, M // 2, k))
+    return f, idx
+
+
+@pytest.mark.parametrize("B,C,N,M,k", GROUP_CASES)
+def test_group_fwd_exact(F, oracle, B, C, N, M, k):
+    rng = np.random.default_rng(9)
+    f, idx = make_group(rng, B, C, N, M, k)
+    o = oracle.group_fwd(f, idx)
+    g = F.group_fwd(cu(f), cu(idx))
+    np.testing.assert_array_equal(g.cpu().numpy(), o)
+    center = rng.standard_normal((B, C, M)).astype(np.float32)
+    o2 = oracle.group_fwd(f, idx, center)
+    g2 = F.group_fwd(cu(f), cu(idx), cu(center))
+    np.testing.assert_array_equal(g2.cpu().numpy(), o2)
+
+
+@pytest.mark.parametrize("B,C,N,M,k,hubs", [(2, 16, 512, 512, 12, False), (2, 8, 256, 300, 9, True),
+                                            (1, 3, 2048, 256, 32, False), (2, 5, 100, 100, 1, False),
+                                            (1, 4, 64, 2000, 20, True)])
+def test_group_bwd_deterministic_and_exact(F, oracle, B, C, N, M, k, hubs):
+    rng = np.random.default_rng(10)
+    f, idx = make_group(rng, B, C, N, M, k, hubs)
+    go = rng.standard_normal((B, C, M, k)).astype(np.float32)
+    o = oracle.group_bwd(go, idx, N)
+    off, items = F.inverse_index(cu(idx), N)
+    # the CSR lists, per source point, the flat positions that read it, ascending
+    offn, itn = off.cpu().numpy(), items.cpu().numpy()
+    for b in range(B):
+        flat = idx[b].ravel()
+        assert offn[b, -1] == flat.size
+        order = np.argsort(flat, kind="stable")
+        np.testing.assert_array_equal(itn[b, : flat.size], order)
+    g = F.group_bwd(cu(go), off, items, N)
+    np.testing.assert_array_equal(g.cpu().numpy(), o)  # same summation order -> bit-exact
+
+
+def test_grouping_autograd_matches_oracle(F, oracle):
+    rng = np.random.default_rng(11)
+    f, idx = make_group(rng, 2, 8, 200, 150, 6)
+    ft = cu(f).requires_grad_(True)
+    out = F.GroupingOperation.apply(ft, cu(idx))
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(cu(go))
+    np.testing.assert_array_equal(ft.grad.cpu().numpy(), oracle.group_bwd(go, idx, 200))
+    # gather_operation == k=1 grouping
+    gi = rng.integers(0, 200, size=(2, 50)).astype(np.int32)
+    ft2 = cu(f).requires_grad_(True)
+    o2 = F.GatherOperation.apply(ft2, cu(gi))
+    np.testing.assert_array_equal(o2.detach().cpu().numpy(), oracle.group_fwd(f, gi[:, :, None])[..., 0])
+    g2 = rng.standard_normal(o2.shape).astype(np.float32)
+    o2.backward(cu(g2))
+    np.testing.assert_array_equal(ft2.grad.cpu().numpy(), oracle.group_bwd(g2[..., None], gi[:, :, None], 200))
+
+
+@pytest.mark.parametrize("op", [0, 1, 2])
+@pytest.mark.parametrize("B,C,N,M,k", [(2, 32, 256, 256, 9), (1, 7, 100, 33, 4), (2, 3, 3000, 500, 16)])
+def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
+    rng = np.random.default_rng(12)
+    f, idx = make_group(rng, B, C, N, M, k)
+    f = np.round(f * 4) / 4  # ties in the max / min
+    oo, oa = oracle.group_reduce_fwd(f, idx, op)
+    go_, ga = F.group_reduce_fwd(cu(f), cu(idx), op)
+    np.testing.assert_array_equal(go_.cpu().numpy(), oo)
+    if op != 1:
+        np.testing.assert_array_equal(ga.cpu().numpy(), oa)
+    grad = rng.standard_normal((B, C, M)).astype(np.float32)
+    ob = oracle.group_reduce_bwd(grad, idx, oa, N, op)
+    off, items = F.inverse_index(cu(idx), N)
+    gb = F.group_reduce_bwd(cu(grad), ga, off, items, N, k, op)
+    np.testing.assert_array_equal(gb.cpu().numpy(), ob)
+
+
+# ----------------------------------------------------------------------------- three_nn / interpolate
+@pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2)])
+def test_three_nn_and_interpolate(F, oracle, B, n, m):
+    rng = np.random.default_rng(13)
+    unknown = synth.fluid_cloud(rng, B, n)
+    known = synth.with_duplicates(rng, synth.fluid_cloud(rng, B, m), 0.3) if m > 3 else synth.fluid_cloud(rng, B, m)
+    od, oi = oracle.three_nn(unknown, known)
+    gd, gi = F.three_nn(cu(unknown), cu(known))
+    assert gi.dtype == torch.int32
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+    c = 16
+    f = rng.standard_normal((B, c, m)).astype(np.float32)
+    w = rng.uniform(size=(B, n, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    oo = oracle.three_interpolate_fwd(f, oi, w)
+    go_ = F.three_interpolate_fwd(cu(f), cu(oi), cu(w))
+    np.testing.assert_array_equal(go_.cpu().numpy(), oo)
+    grad = rng.standard_normal((B, c, n)).astype(np.float32)
+    ob = oracle.three_interpolate_bwd(grad, oi, w, m)
+    off, items = F.inverse_index(cu(oi), m)
+    gb = F.three_interpolate_bwd(cu(grad), cu(w), off, items, m)
+    np.testing.assert_array_equal(gb.cpu().numpy(), ob)
+
+
+# ----------------------------------------------------------------------------- Chamfer
+@pytest.mark.parametrize("B,P1,P2,directions", [(2, 512, 2048, 3), (2, 2048, 512, 3), (3, 100, 100, 1),
+                                               (3, 100, 333, 2), (1, 8192, 8192, 3), (2, 300, 300, 3)])
+def test_chamfer_fwd_bwd(F, oracle, B, P1, P2, directions):
+    rng = np.random.default_rng(14)
+    tgt = synth.fluid_cloud(rng, B, P2)
+    if P1 == P2 == 300:
+        src = synth.with_duplicates(rng, tgt, 0.5)  # exact coincidences: zero distances, idx ties
+    else:
+        src = synth.fluid_cloud(rng, B, P1) + rng.normal(0, 0.003, size=(B, P1, 3)).astype(np.float32)
+    src = np.ascontiguousarray(src, np.float32)
+    o = oracle.chamfer_fwd(src, tgt, directions)
+    g = F.chamfer_fwd(cu(src), cu(tgt), directions)
+    if directions & 1:
+        np.testing.assert_array_equal(g["i_src"].cpu().numpy(), o["i_src"])
+        np.testing.assert_array_equal(g["d_src"].cpu().numpy(), o["d_src"])
+        assert rel_err(g["sum_src"].cpu().numpy(), o["sum_src"]) < RTOL
+    if directions & 2:
+        np.testing.assert_array_equal(g["i_tgt"].cpu().numpy(), o["i_tgt"])
+        np.testing.assert_array_equal(g["d_tgt"].cpu().numpy(), o["d_tgt"])
+        assert rel_err(g["sum_tgt"].cpu().numpy(), o["sum_tgt"]) < RTOL
+    gs = rng.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    gt = rng.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    ogs, ogt = oracle.chamfer_bwd(src, tgt, o["i_src"], o["i_tgt"], gs, gt, directions)
+    ggs, ggt = F.chamfer_bwd(cu(src), cu(tgt), g["i_src"], g["i_tgt"], cu(gs), cu(gt), directions)
+    assert rel_err(ggs.cpu().numpy(), ogs) < RTOL
+    assert rel_err(ggt.cpu().numpy(), ogt) < RTOL
+
+
+def test_chamfer_module_value_and_grad(oracle):
+    """chamferdist.ChamferDistance through the drop-in module, as loss.py:176-181 calls it."""
+    from chamferdist import ChamferDistance
+
+    rng = np.random.default_rng(15)
+    gt = synth.fluid_cloud(rng, 2, 1024)
+    pred = synth.fluid_cloud(rng, 2, 900)
+    pt = cu(pred).requires_grad_(True)
+    val = ChamferDistance()(cu(gt), pt, bidirectional=True)
+    ref = oracle.chamfer_distance(gt, pred, bidirectional=True)
+    assert abs(float(val) - float(ref)) <= RTOL * abs(float(ref))
+    val.backward()
+    o = oracle.chamfer_fwd(gt, pred, 3)
+    g = np.full((2,), 0.5, np.float32)  # d mean_b / d sum_b
+    _, ogt = oracle.chamfer_bwd(gt, pred, o["i_src"], o["i_tgt"], g, g, 3)
+    assert rel_err(pt.grad.cpu().numpy(), ogt) < RTOL
+    for kw in (dict(), dict(reverse=True), dict(bidirectional=True, point_reduction="mean"),
+               dict(bidirectional=True, batch_reduction="sum")):
+        v = ChamferDistance()(cu(gt), cu(pred), **kw)
+        r = oracle.chamfer_distance(gt, pred, **kw)
+        assert abs(float(v) - float(r)) <= RTOL * abs(float(r)), kw
+
+
+# ----------------------------------------------------------------------------- cubic interpolation
+@pytest.mark.parametrize("S,Q,P,F_,cutoff,far", [(2, 400, 500, 3, 0.16, False), (1, 300, 300, 3, 0.04, False),
+                                               (2, 200, 600, 3, 0.05, True), (1, 100, 50, 6, 0.03, True)])
+def test_cubic_interp(F, oracle, S, Q, P, F_, cutoff, far):
+    rng = np.random.default_rng(16)
+    pos = synth.fluid_cloud(rng, S, P)
+    query = synth.fluid_cloud(rng, S, Q)
+    if far:  # some queries far outside the fluid: no neighbour -> the kNN-padding branch (interpolation.py:44)
+        query[:, : Q // 10] += 5.0
+    field = rng.standard_normal((S, P, F_)).astype(np.float32)
+    o = oracle.cubic_interp(query, field, pos, cutoff)
+    g = F.cubic_interp(cu(query), cu(field), cu(pos), cutoff).cpu().numpy()
+    scale = np.abs(o).max()
+    assert np.abs(g - o).max() <= RTOL * max(scale, 1e-30)
+
+
+def test_gather_rows(F, oracle):
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((2, 100, 7)).astype(np.float32)
+    idx = rng.integers(-1, 100, size=(2, 333)).astype(np.int64)
+    np.testing.assert_array_equal(F.gather_rows(cu(x), cu(idx)).cpu().numpy(), oracle.gather_rows(x, idx))
+
+
+def test_library_was_used(F):
+    import tpugan_b200
+
+    assert tpugan_b200.launch_count() > 0
