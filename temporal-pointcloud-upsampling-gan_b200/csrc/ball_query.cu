@@ -71,7 +71,7 @@ TPG_API int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, in
                                int nsample, int32_t* idx, tpg_stream_t stream) {
   TPG_REQUIRE(B >= 0 && N >= 0 && M >= 0 && nsample >= 1, TPG_EINVAL, "ball_query: bad size");
   if (B == 0 || M == 0) return TPG_OK;
-  TPG_REQUIRE(xyz && new_xyz && idx, TPG_EINVAL, "ball_query: null pointer");
+  TPG_REQUIRE((xyz || N == 0) && new_xyz && idx, TPG_EINVAL, "ball_query: null pointer");
   const float r2 = radius * radius;
   const long long warps = (long long)B * M;
   const long long blocks = (warps + BQ_THREADS / 32 - 1) / (BQ_THREADS / 32);

@@ -199,7 +199,7 @@ TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths
   TPG_REQUIRE(K >= 1 && K <= 1024, TPG_EUNSUPPORTED, "knn: K=%d outside [1,1024]", K);
   TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "knn: B=%d > 65535", B);
   if (B == 0 || P1 == 0) return TPG_OK;
-  TPG_REQUIRE(p1 && p2 && dists && idx, TPG_EINVAL, "knn: null pointer");
+  TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "knn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, 0.f, nullptr, 0, dists, idx, OUT_KNN};
   return knn_dispatch(a, as_stream(stream));
 }
@@ -219,7 +219,7 @@ TPG_API int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* length
   TPG_REQUIRE(K >= 1 && K <= 1024, TPG_EUNSUPPORTED, "frnn: K=%d outside [1,1024]", K);
   TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "frnn: B=%d > 65535", B);
   if (B == 0 || P1 == 0) return TPG_OK;
-  TPG_REQUIRE(p1 && p2 && dists && idx, TPG_EINVAL, "frnn: null pointer");
+  TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "frnn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, r, r_per_cloud, 1, dists, idx, OUT_FRNN};
   return knn_dispatch(a, as_stream(stream));
 }
@@ -229,7 +229,7 @@ TPG_API int tpg_three_nn_f32(const float* unknown, const float* known, int B, in
   TPG_REQUIRE(B >= 0 && n >= 0 && m >= 0, TPG_EINVAL, "three_nn: negative size");
   TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "three_nn: B=%d > 65535", B);
   if (B == 0 || n == 0) return TPG_OK;
-  TPG_REQUIRE(unknown && known && dist && idx, TPG_EINVAL, "three_nn: null pointer");
+  TPG_REQUIRE(unknown && (known || m == 0) && dist && idx, TPG_EINVAL, "three_nn: null pointer");
   KnnArgs a{unknown, known, nullptr, nullptr, B, n, m, 3, 3, 0.f, nullptr, 0, dist, idx, OUT_THREE};
   return knn_dispatch(a, as_stream(stream));
 }
