@@ -1,0 +1,393 @@
+"""Replay of the neighbourhood-op schedule of one TPU-GAN train step on synthetic data.
+
+The schedule (``tests/golden/*_step_schedule.json``) is the list of boundary calls that the
+reference's UNMODIFIED ``tempo_gan_step`` / ``tempo_gan_step_no_mask``
+(train_step_final.py:69-320) makes into pytorch3d / frnn / pointnet2_ops / chamferdist,
+forward and backward, recorded by ``tests/golden/make_schedule.py``.  The dense layers
+between those calls (1x1 convolutions, BatchNorm, optimisers) are *not* part of the hot
+path; their outputs are replaced by seeded synthetic activations of the recorded shapes.
+Index tensors are chained exactly as in the reference (kNN -> int32 cast -> grouping;
+FPS -> gather -> ball_query -> grouping; FRNN + kNN -> fill -> grouping; every backward uses
+the index tensor of its forward call), so search and gather kernels see realistic data.
+
+The engine is backend-agnostic: it drives an ``ops`` object.  This module provides the two
+CUDA back-ends (raw C-ABI path with device-resident data; reference-facing drop-in API with
+autograd).  bench.py supplies the CPU-oracle back-end for the baseline legs — this module
+never imports ``oracle``.
+"""
+from __future__ import annotations
+
+import json
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+BASE_RADIUS = 0.025  # train_utils.py:10
+
+
+def load_schedule(path: str, batch: Optional[int] = None) -> Dict[str, Any]:
+    """Read a schedule and (optionally) rescale its batch dimension: every op on the path is
+    independent per cloud, so the call sequence does not depend on B."""
+    with open(path) as f:
+        doc = json.load(f)
+    b0 = doc["B"]
+    if batch is not None and batch != b0:
+        def fix(v):
+            if isinstance(v, dict) and "shape" in v:
+                s = list(v["shape"])
+                if s and s[0] == b0:
+                    s[0] = batch
+                return {"shape": s, "dtype": v["dtype"]}
+            return v
+        for c in doc["calls"]:
+            c["in"] = {k: fix(v) for k, v in c["in"].items()}
+            c["out"] = {k: fix(v) for k, v in c["out"].items()}
+        doc["B"] = batch
+    return doc
+
+
+def _shape(v):
+    return tuple(v["shape"])
+
+
+def count_queries(doc) -> int:
+    """Neighbourhood queries per step: every point for which a neighbour list is searched
+    (kNN / FRNN / ball query rows, Chamfer nearest-neighbour rows)."""
+    q = 0
+    for c in doc["calls"]:
+        op, i = c["op"], c["in"]
+        if op in ("knn", "frnn"):
+            q += _shape(i["p1"])[0] * _shape(i["p1"])[1]
+        elif op == "ball_query":
+            q += _shape(i["new_xyz"])[0] * _shape(i["new_xyz"])[1]
+        elif op == "chamfer":
+            s, t = _shape(i["src"]), _shape(i["tgt"])
+            q += s[0] * (s[1] + t[1])
+    return q
+
+
+def algorithmic_bytes(call) -> int:
+    """Compulsory HBM traffic of one call: every input read once, every
+    output written once."""
+    op, i, o = call["op"], call["in"], call["out"]
+    if op in ("knn", "frnn"):
+        B, P1, D = _shape(i["p1"])
+        P2 = _shape(i["p2"])[1]
+        return 4 * B * D * (P1 + P2) + 12 * B * P1 * int(i["K"])
+    if op == "ball_query":
+        B, N, _ = _shape(i["xyz"])
+        M = _shape(i["new_xyz"])[1]
+        return 12 * B * (N + M) + 4 * B * M * int(i["nsample"])
+    if op == "fps":
+        B, N, _ = _shape(i["xyz"])
+        return 12 * B * N + 4 * B * int(i["npoint"])
+    if op == "gather":
+        B, C, N = _shape(i["f"])
+        M = _shape(i["idx"])[1]
+        return 4 * B * (C * N + M + C * M)
+    if op == "group":
+        B, C, N = _shape(i["f"])
+        _, M, k = _shape(i["idx"])
+        return 4 * B * (C * N + M * k + C * M * k)
+    if op in ("group_bwd", "gather_bwd"):
+        g = _shape(i["grad_out"])
+        B, C = g[0], g[1]
+        L = int(np.prod(g[2:]))
+        return 4 * B * (C * int(i["N"]) + L + C * L)
+    if op == "chamfer":
+        B, P1, _ = _shape(i["src"])
+        P2 = _shape(i["tgt"])[1]
+        return 12 * B * (P1 + P2) + 8 * B * (P1 + P2)
+    if op == "chamfer_bwd":
+        B, P1, _ = _shape(i["src"])
+        P2 = _shape(i["tgt"])[1]
+        return 32 * B * (P1 + P2)
+    return 0
+
+
+class TraceReplay:
+    """Builds seeded inputs for a schedule once, then replays it any number of times."""
+
+    def __init__(self, doc: Dict[str, Any], ops, seed: int = 1):
+        self.doc = doc
+        self.ops = ops
+        self.calls: List[Dict[str, Any]] = doc["calls"]
+        self.domain = doc["domain"]
+        self.rng = np.random.default_rng(seed)
+        self._base_clouds: Dict[tuple, Any] = {}
+        self.frames: List[Any] = []  # external inputs of the step (position frames)
+        self.frame_keys: List[tuple] = []
+        self.inputs: List[Dict[str, Any]] = [self._make_inputs(n, c) for n, c in enumerate(self.calls)]
+        self.queries = count_queries(doc)
+        self.timers = None  # optional: dict op -> list of (start, stop) backend events
+
+    # ---- synthetic data ---------------------------------------------------------------
+    def _cloud_np(self, B, N):
+        if self.domain == "fluid":
+            L = BASE_RADIUS * (8192 ** (1.0 / 3.0))  # one physical extent for every level of a fluid frame
+            p = self.rng.uniform(0.0, L, size=(B, N, 3)).astype(np.float32)
+            p -= p.mean(axis=1, keepdims=True).astype(np.float32)
+        else:
+            lo = np.array([-0.5, -1.0, -0.25], np.float32)
+            p = self.rng.uniform(size=(B, N, 3)).astype(np.float32) * (-2 * lo) + lo
+        return np.ascontiguousarray(p, np.float32)
+
+    def base_cloud(self, B, N, slot=0):
+        """A position frame of N points ([B,N,3]); distinct `slot`s are distinct frames.
+        These are the step's EXTERNAL inputs (they come from the data loader)."""
+        key = (B, N, slot)
+        if key not in self._base_clouds:
+            self._base_clouds[key] = self.ops.array(self._cloud_np(B, N))
+            self.frames.append(self._base_clouds[key])
+            self.frame_keys.append(key)
+        return self._base_clouds[key]
+
+    def _make_inputs(self, n, c):
+        op, i = c["op"], c["in"]
+        d: Dict[str, Any] = {}
+        if op in ("knn", "frnn"):
+            B, P1, D = _shape(i["p1"])
+            P2 = _shape(i["p2"])[1]
+            if D == 3:
+                d["p2"] = self.base_cloud(B, P2, slot=n % 3)
+                d["p1"] = d["p2"] if P1 == P2 else self.base_cloud(B, P1, slot=n % 3)
+            else:
+                d["p1"] = self.ops.array(self.rng.standard_normal((B, P1, D)).astype(np.float32))
+                d["p2"] = d["p1"] if P1 == P2 else self.ops.array(
+                    self.rng.standard_normal((B, P2, D)).astype(np.float32))
+        elif op == "fps":
+            B, N, _ = _shape(i["xyz"])
+            d["xyz"] = self.base_cloud(B, N, slot=n % 3)
+        elif op == "group":
+            B, C, N = _shape(i["f"])
+            if C != 3:
+                d["f"] = self.ops.array(self.rng.standard_normal((B, C, N)).astype(np.float32))
+            d["rand_idx"] = self.ops.array(self.rng.integers(0, N, size=_shape(i["idx"])).astype(np.int32))
+        elif op in ("group_bwd", "gather_bwd"):
+            d["grad_out"] = self.ops.array(self.rng.standard_normal(_shape(i["grad_out"])).astype(np.float32))
+        elif op == "chamfer":
+            B, P1, _ = _shape(i["src"])
+            P2 = _shape(i["tgt"])[1]
+            d["src"] = self.base_cloud(B, P1, slot=0)
+            tgt = self._cloud_np(B, P2)
+            d["tgt"] = self.ops.array(tgt)
+        elif op == "chamfer_bwd":
+            B = _shape(i["g_src"])[0]
+            d["g"] = self.ops.array(np.full((B,), 1.0 / B, np.float32))
+        return d
+
+    # ---- replay -------------------------------------------------------------------------
+    def _pick_idx(self, state, want, fallback):
+        """Most recent index tensor of the wanted shape [B,M,k]; a [B,M,k*d] list is strided
+        by d (Dilated, gcn_lib/pointnet/gcn.py:71); otherwise a seeded random one."""
+        for shape, t in reversed(state["idx"]):
+            if shape == want:
+                return t
+            if len(shape) == 3 and shape[:2] == want[:2] and shape[2] > want[2] and shape[2] % want[2] == 0:
+                return self.ops.stride_last(t, shape[2] // want[2])
+        return fallback
+
+    def run_step(self):
+        ops = self.ops
+        ops.new_step()
+        state: Dict[str, Any] = {"idx": [], "fwd": {}, "cloud": {}, "chamfer": None, "last_fps": None,
+                                 "last_gather": None, "frnn": None}
+        results = []
+        for n, c in enumerate(self.calls):
+            op, i, d = c["op"], c["in"], self.inputs[n]
+            t0 = ops.tick() if self.timers is not None else None
+            if op == "knn":
+                idx = ops.knn(d["p1"], d["p2"], int(i["K"]))
+                if state["frnn"] is not None and state["frnn"][0] == _shape(c["out"]["idx"]):
+                    # ball_query_wrapper (discriminator.py:39): fill FRNN's -1 slots from kNN
+                    idx = ops.fill_negative(state["frnn"][1], idx)
+                    state["frnn"] = None
+                state["idx"].append((_shape(c["out"]["idx"]), ops.to_i32(idx)))
+            elif op == "frnn":
+                idx = ops.frnn(d["p1"], d["p2"], int(i["K"]), float(i["r"]))
+                state["frnn"] = (_shape(c["out"]["idx"]), idx)
+            elif op == "fps":
+                B, N, _ = _shape(i["xyz"])
+                xyz = state["cloud"].get((B, N), d["xyz"])
+                idx = ops.fps(xyz, int(i["npoint"]))
+                state["last_fps"] = (xyz, idx)
+            elif op == "gather":
+                xyz, idx = state["last_fps"]
+                out = ops.gather(ops.transpose12(xyz), idx)  # [B,3,M]
+                new_xyz = ops.transpose12(out)
+                state["last_gather"] = (xyz, new_xyz)
+                state["cloud"][(new_xyz.shape[0], new_xyz.shape[1])] = new_xyz
+                state["fwd"][i["id"]] = idx
+            elif op == "ball_query":
+                xyz, new_xyz = state["last_gather"]
+                idx = ops.ball_query(float(i["radius"]), int(i["nsample"]), xyz, new_xyz)
+                state["idx"].append((_shape(c["out"]["idx"]), idx))
+                state["last_xyz"] = xyz
+            elif op == "group":
+                B, C, N = _shape(i["f"])
+                idx = self._pick_idx(state, _shape(i["idx"]), d["rand_idx"])
+                if C == 3:
+                    src = state["cloud"].get((B, N))
+                    if src is None:
+                        src = self.base_cloud(B, N, slot=0)
+                    f = ops.transpose12(src)
+                else:
+                    f = d["f"]
+                results.append(ops.group(f, idx))
+                state["fwd"][i["id"]] = idx
+            elif op in ("group_bwd", "gather_bwd"):
+                idx = state["fwd"][i["fwd_id"]]
+                results.append(ops.group_bwd(d["grad_out"], idx, int(i["N"])))
+            elif op == "chamfer":
+                state["chamfer"] = ops.chamfer(d["src"], d["tgt"], int(i["directions"]))
+            elif op == "chamfer_bwd":
+                results.append(ops.chamfer_bwd(state["chamfer"], d["g"]))
+            else:
+                raise ValueError(f"unknown op in schedule: {op}")
+            if t0 is not None:
+                self.timers.setdefault(op, []).append((t0, ops.tick()))
+        return ops.finish(state["chamfer"], results)
+
+
+# ============================================================================ CUDA back-ends
+class TorchCudaOps:
+    """Device-resident replay straight through ``tpugan_b200.functional`` (the ctypes C-ABI)."""
+
+    def __init__(self, device="cuda"):
+        import torch
+
+        from . import functional as F
+
+        self.torch, self.F, self.device = torch, F, torch.device(device)
+        self._csr = {}
+
+    def array(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def new_step(self):
+        self._csr = {}
+
+    def tick(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def knn(self, p1, p2, K):
+        return self.F.knn(p1, p2, K)[1]
+
+    def frnn(self, p1, p2, K, r):
+        return self.F.frnn(p1, p2, K, r)[1]
+
+    def fill_negative(self, frnn_idx, knn_idx):
+        return self.torch.where(frnn_idx == -1, knn_idx, frnn_idx)
+
+    def to_i32(self, idx):
+        return idx.to(self.torch.int32)
+
+    def stride_last(self, idx, d):
+        return idx[:, :, ::d].contiguous()
+
+    def transpose12(self, x):
+        return x.transpose(1, 2).contiguous()
+
+    def fps(self, xyz, npoint):
+        return self.F.fps(xyz, npoint)
+
+    def gather(self, f, idx):
+        return self.F.group_fwd(f, idx.unsqueeze(-1)).squeeze(-1)
+
+    def ball_query(self, r, ns, xyz, new_xyz):
+        return self.F.ball_query(r, ns, xyz, new_xyz)
+
+    def group(self, f, idx):
+        return self.F.group_fwd(f, idx)
+
+    def group_bwd(self, grad_out, idx, N):
+        key = (idx.data_ptr(), N)
+        if key not in self._csr:  # one inverse index per idx tensor, shared by its groupings
+            self._csr[key] = (idx,) + tuple(self.F.inverse_index(idx, N))
+        _, off, items = self._csr[key]
+        return self.F.group_bwd(grad_out, off, items, N)
+
+    def chamfer(self, src, tgt, directions):
+        r = self.F.chamfer_fwd(src, tgt, directions)
+        return (src, tgt, directions, r)
+
+    def chamfer_bwd(self, handle, g):
+        src, tgt, directions, r = handle
+        return self.F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, directions, need_src=False, need_tgt=True)[1]
+
+    def finish(self, chamfer, results):
+        r = chamfer[3]
+        return (r["sum_src"] + r["sum_tgt"]).mean()
+
+
+class ShimApiOps(TorchCudaOps):
+    """Same replay through the reference-facing drop-in packages (``pytorch3d.ops``, ``frnn``,
+    ``pointnet2_ops.pointnet2_utils``, ``chamferdist``) with autograd doing the backward —
+    the call path a user of the reference takes."""
+
+    def __init__(self, device="cuda"):
+        super().__init__(device)
+        import tpugan_b200
+
+        tpugan_b200.activate()
+        import chamferdist
+        import frnn
+        import pointnet2_ops.pointnet2_utils as pu
+        import pytorch3d.ops as p3d
+
+        self.p3d, self.frnn_mod, self.pu, self.cd = p3d, frnn, pu, chamferdist.ChamferDistance()
+        self._fwd = {}
+
+    def new_step(self):
+        self._fwd = {}
+        self.F.csr_cache.clear()
+
+    def knn(self, p1, p2, K):
+        return self.p3d.knn_points(p1, p2, K=K, return_nn=False, return_sorted=True)[1]
+
+    def frnn(self, p1, p2, K, r):
+        return self.frnn_mod.frnn_grid_points(p1, p2, K=K, r=r, grid=None, return_nn=False, return_sorted=True)[1]
+
+    def to_i32(self, idx):
+        return idx.type(self.torch.int32).contiguous()
+
+    def fps(self, xyz, npoint):
+        return self.pu.furthest_point_sample(xyz, npoint)
+
+    def gather(self, f, idx):
+        f = f.detach().requires_grad_(True)
+        out = self.pu.gather_operation(f, idx)
+        self._fwd[idx.data_ptr()] = (f, out)
+        return out.detach()
+
+    def ball_query(self, r, ns, xyz, new_xyz):
+        return self.pu.ball_query(r, ns, xyz, new_xyz)
+
+    def group(self, f, idx):
+        f = f.detach().requires_grad_(True)
+        out = self.pu.grouping_operation(f, idx)
+        self._fwd.setdefault(("g", idx.data_ptr(), tuple(out.shape)), []).append((f, out))
+        return out
+
+    def group_bwd(self, grad_out, idx, N):
+        key = ("g", idx.data_ptr(), tuple(grad_out.shape))
+        if key in self._fwd and self._fwd[key]:
+            f, out = self._fwd[key].pop()
+        else:  # gather_bwd
+            f, out = self._fwd[idx.data_ptr()]
+            grad_out = grad_out.reshape(out.shape)
+        return self.torch.autograd.grad(out, f, grad_out)[0]
+
+    def chamfer(self, src, tgt, directions):
+        tgt = tgt.detach().requires_grad_(True)
+        val = self.cd(src, tgt, bidirectional=True)
+        return (tgt, val)
+
+    def chamfer_bwd(self, handle, g):
+        tgt, val = handle
+        return self.torch.autograd.grad(val, tgt)[0]
+
+    def finish(self, chamfer, results):
+        return chamfer[1].detach()
