@@ -266,6 +266,22 @@ def cubic_interp(query, field, pos, cutoff):
     return out
 
 
+def l2dist(src, dst):
+    """gcn_lib/interpolation.py:11-14 element-wise: src, dst [n,3] -> [n]."""
+    src, dst = _f32(src), _f32(dst)
+    out = np.empty((src.shape[0],), np.float32)
+    lib().orc_l2dist(_p(src), _p(dst), ctypes.c_int(src.shape[0]), _p(out))
+    return out
+
+
+def bicubic(r, cutoff):
+    """gcn_lib/interpolation.py:92-100 element-wise."""
+    r = _f32(r).reshape(-1)
+    out = np.empty_like(r)
+    lib().orc_bicubic(_p(r), ctypes.c_int(r.shape[0]), ctypes.c_float(cutoff), _p(out))
+    return out
+
+
 def gather_rows(x, idx):
     """x [B,N,U], idx [B,L] (negative wraps) -> [B,L,U]."""
     x, idx = _f32(x), _i64(idx)

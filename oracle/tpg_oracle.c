@@ -494,6 +494,17 @@ static inline float bicubic_ref(float r, float cutoff, float coeff) {
   return ker * coeff;
 }
 
+/* element-wise exports of the two helpers above, pinned against the reference's own
+ * l2dist / bicubic_kernel run live (tests/golden/interp_kernels.npz). */
+ORC_API void orc_l2dist(const float* src, const float* dst, int n, float* out) {
+  for (int i = 0; i < n; ++i) out[i] = l2dist_ref(src + (size_t)i * 3, dst + (size_t)i * 3);
+}
+ORC_API void orc_bicubic(const float* r, int n, float cutoff, float* out) {
+  const float coeff = (float)(8.0 / (3.14159265358979323846 * (double)cutoff *
+                                     (double)cutoff * (double)cutoff));
+  for (int i = 0; i < n; ++i) out[i] = bicubic_ref(r[i], cutoff, coeff);
+}
+
 ORC_API void orc_cubic_interp(const float* query, const float* field,
                               const float* pos, int S, int Q, int P, int F,
                               float cutoff, float* out) {
