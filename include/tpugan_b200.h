@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 1
+#define TPG_ABI_VERSION 2
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -67,10 +67,16 @@ uint64_t tpg_launch_count(void);
  *   gcn_lib/graph_utils.py:71.
  * p1 [B,P1,D], p2 [B,P2,D] -> dists [B,P1,K] (squared), idx [B,P1,K] int64.
  * Slots beyond min(K, lengths2[b]) and rows beyond lengths1[b] hold 0 / 0.
- * 1 <= D <= 256, 1 <= K <= 1024.                                          */
+ * 1 <= D <= 256, 1 <= K <= 1024.
+ * Feature-space searches (D a multiple of 32 up to 128, K <= 24, P2 >= 128) run on the
+ * tensor cores (tcgen05, tf32 candidate search + exact fp32 re-rank; results identical
+ * to the SIMT path) and need tpg_knn_workspace_bytes() bytes of workspace; for every
+ * other shape that function returns 0 and workspace may be NULL.            */
+size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K);
 int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                 const int64_t* lengths2, int B, int P1, int P2, int D, int K,
-                float* dists, int64_t* idx, tpg_stream_t stream);
+                float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,
+                tpg_stream_t stream);
 
 /* ---- K3: fixed-radius nearest neighbours --------------------------------
  * replaces frnn.frnn_grid_points(points1, points2, lengths1, lengths2, K, r,

@@ -23,6 +23,11 @@ struct KnnArgs {
 // knn.cu
 int knn_dispatch(const KnnArgs& a, cudaStream_t st);
 
+// knn_feat.cu — tcgen05 path for D in {32,64,96,128}, K <= 24 (exact results, tensor-core candidate search)
+bool knn_feat_eligible(const KnnArgs& a);
+size_t knn_feat_workspace_bytes(int B, int P1, int P2);
+int knn_feat_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 // group.cu — inverse index (CSR) of an int32 index tensor idx [B,L] with keys in
 // [0,N): seg_offsets [B,N+1], seg_items [B,L] (ascending positions per key).
 // item_len (device [B] int64 or null) limits the positions of cloud b to [0,len).

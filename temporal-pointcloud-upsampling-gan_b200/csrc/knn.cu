@@ -191,9 +191,16 @@ int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
 
 using namespace tpg;
 
+TPG_API size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K) {
+  KnnArgs a{reinterpret_cast<const float*>(16), reinterpret_cast<const float*>(16), nullptr, nullptr, B, P1, P2, D, K,
+            0.f, nullptr, 0, nullptr, nullptr, OUT_KNN};
+  return knn_feat_eligible(a) ? knn_feat_workspace_bytes(B, P1, P2) : 0;
+}
+
 TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                         const int64_t* lengths2, int B, int P1, int P2, int D, int K,
-                        float* dists, int64_t* idx, tpg_stream_t stream) {
+                        float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,
+                        tpg_stream_t stream) {
   TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0, TPG_EINVAL, "knn: negative size");
   TPG_REQUIRE(D >= 1 && D <= 256, TPG_EUNSUPPORTED, "knn: D=%d outside [1,256]", D);
   TPG_REQUIRE(K >= 1 && K <= 1024, TPG_EUNSUPPORTED, "knn: K=%d outside [1,1024]", K);
@@ -201,6 +208,7 @@ TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths
   if (B == 0 || P1 == 0) return TPG_OK;
   TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "knn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, 0.f, nullptr, 0, dists, idx, OUT_KNN};
+  if (P2 > 0 && knn_feat_eligible(a)) return knn_feat_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   return knn_dispatch(a, as_stream(stream));
 }
 

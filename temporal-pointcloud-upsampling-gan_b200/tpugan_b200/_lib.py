@@ -14,6 +14,7 @@ LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
+ABI_VERSION = 2
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
@@ -34,7 +35,8 @@ _PROTOS = {
     "tpg_abi_version": (_I, []),
     "tpg_last_error": (c_char_p, []),
     "tpg_launch_count": (c_uint64, []),
-    "tpg_knn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "tpg_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "tpg_knn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_frnn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "tpg_frnn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "tpg_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
@@ -78,8 +80,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError == ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.tpg_abi_version() != 1:
-        raise TpgLibraryMissing(f"{LIB_NAME}: ABI version {lib.tpg_abi_version()} != 1; rebuild")
+    if lib.tpg_abi_version() != ABI_VERSION:
+        raise TpgLibraryMissing(f"{LIB_NAME}: ABI version {lib.tpg_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
 

@@ -70,8 +70,10 @@ def knn(p1, p2, K: int, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, tor
     dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     with torch.cuda.device(p1.device):
+        nbytes = _lib.load().tpg_knn_workspace_bytes(B, P1, P2, D, K)  # > 0: tensor-core (tcgen05) path
+        ws = _ws(nbytes, p1.device) if nbytes else None
         _lib.call("tpg_knn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, _ptr(dists), _ptr(idx),
-                  _stream())
+                  _ptr(ws), nbytes, _stream())
     return dists, idx
 
 

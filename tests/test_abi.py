@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared_functions():
         assert hasattr(lib, name), name
     lib.tpg_abi_version.restype = ctypes.c_int
-    assert lib.tpg_abi_version() == 1  # host-only call
+    assert lib.tpg_abi_version() == 2  # host-only call
 
 
 def test_library_is_sm100a_only(built):
@@ -59,12 +59,12 @@ def test_host_only_entry_points_do_not_need_a_gpu(built):
 def test_argument_errors_are_reported_not_thrown(built):
     lib = built.load()
     # bad arguments are rejected before any CUDA call
-    assert lib.tpg_knn_f32(None, None, None, None, 1, 4, 4, 300, 1, None, None, None) == built.TPG_EUNSUPPORTED
+    assert lib.tpg_knn_f32(None, None, None, None, 1, 4, 4, 300, 1, None, None, None, 0, None) == built.TPG_EUNSUPPORTED
     assert b"D=300" in lib.tpg_last_error()
     assert lib.tpg_frnn_f32(None, None, None, None, 1, 4, 4, 5, 1, 0.1, None, None, None, None, 0, None) \
         == built.TPG_EUNSUPPORTED
     assert lib.tpg_group_reduce_fwd_f32(None, None, 1, 1, 1, 1, 1, 7, None, None, None) == built.TPG_EINVAL
-    assert lib.tpg_knn_f32(None, None, None, None, 1, 4, 4, 3, 1, None, None, None) == built.TPG_EINVAL  # null ptr
+    assert lib.tpg_knn_f32(None, None, None, None, 1, 4, 4, 3, 1, None, None, None, 0, None) == built.TPG_EINVAL  # null ptr
 
 
 def test_product_fails_loudly_without_cuda(built):

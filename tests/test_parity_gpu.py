@@ -85,6 +85,71 @@ def test_knn_bit_exact(F, oracle, B, P1, P2, D, K, kind):
     np.testing.assert_array_equal(gd.cpu().numpy(), od)
 
 
+# feature-space searches that take the tcgen05 path (csrc/knn_feat.cu): results must be
+# IDENTICAL to the oracle (indices and canonical distances), including the cases that
+# overflow the tf32 margin and are recomputed by the exact fallback.
+KNN_TC_CASES = [
+    (2, 2048, 2048, 32, 9, "feat"),      # IDGCN bottleneck kNN (gcn.py:258)
+    (2, 2048, 2048, 32, 20, "featself"), # EdgeConv k=20 on the same features (gcn.py:264)
+    (2, 2048, 2048, 64, 12, "feat"),     # UpsamplingModule (upsampling_network.py:57)
+    (1, 2048, 2048, 64, 4, "featself"),
+    (1, 2048, 2048, 64, 8, "feat"),
+    (2, 1000, 1500, 64, 20, "feat"),     # ragged query / candidate tiles
+    (1, 300, 700, 96, 24, "feat"),
+    (1, 256, 512, 128, 16, "feat"),
+    (1, 512, 512, 64, 12, "featdup"),    # exact duplicate rows: (d2, idx) ties
+    (1, 512, 1024, 32, 20, "featoffset"),   # |x| >> distances: margin overflow -> exact fallback
+    (1, 512, 1024, 64, 20, "featcluster"),  # tight clusters of near-duplicates
+    (1, 384, 640, 64, 16, "featrelu"),   # post-activation features (many exact zeros)
+]
+
+
+def make_feat(rng, B, P1, P2, D, kind):
+    if kind == "featself":
+        b = rng.standard_normal((B, P2, D)).astype(np.float32)
+        return b, b
+    if kind == "featoffset":
+        off = rng.standard_normal((1, 1, D)).astype(np.float32) * 50.0
+        return (rng.standard_normal((B, P1, D)).astype(np.float32) * 0.1 + off,
+                rng.standard_normal((B, P2, D)).astype(np.float32) * 0.1 + off)
+    if kind == "featcluster":
+        cen = rng.standard_normal((B, 16, D)).astype(np.float32)
+        b = cen[:, rng.integers(0, 16, size=P2)] + rng.standard_normal((B, P2, D)).astype(np.float32) * 1e-3
+        a = cen[:, rng.integers(0, 16, size=P1)] + rng.standard_normal((B, P1, D)).astype(np.float32) * 1e-3
+        return np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    if kind == "featrelu":
+        a = np.maximum(rng.standard_normal((B, P1, D)), 0).astype(np.float32)
+        b = np.maximum(rng.standard_normal((B, P2, D)), 0).astype(np.float32)
+        return a, b
+    return make_pair(rng, B, P1, P2, D, kind)
+
+
+@pytest.mark.parametrize("B,P1,P2,D,K,kind", KNN_TC_CASES)
+def test_knn_tensor_core_path_bit_exact(F, oracle, B, P1, P2, D, K, kind):
+    from tpugan_b200 import _lib
+
+    assert _lib.load().tpg_knn_workspace_bytes(B, P1, P2, D, K) > 0, "shape must select the tcgen05 path"
+    rng = np.random.default_rng(D * 1000 + K)
+    a, b = make_feat(rng, B, P1, P2, D, kind)
+    od, oi = oracle.knn(a, b, K)
+    gd, gi = F.knn(cu(a), cu(b), K)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_knn_tensor_core_path_ragged_lengths(F, oracle):
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((3, 300, 64)).astype(np.float32)
+    b = rng.standard_normal((3, 400, 64)).astype(np.float32)
+    l1 = np.array([300, 33, 0], np.int64)
+    l2 = np.array([400, 130, 7], np.int64)   # 7 < K: zero padding
+    od, oi = oracle.knn(a, b, 12, l1, l2)
+    gd, gi = F.knn(cu(a), cu(b), 12, cu(l1), cu(l2))
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
 def test_knn_ragged_lengths(F, oracle):
     rng = np.random.default_rng(2)
     a = synth.fluid_cloud(rng, 3, 200, 3)
