@@ -41,7 +41,8 @@ constexpr int FT_NQ = 32;    // queries per CTA (UMMA N)
 constexpr int FT_QW = 16;    // queries (accumulator columns) per warp
 constexpr int FT_TMEM_COLS = 64;
 constexpr int FT_MAX_K = 24; // needs slack below the 32 list slots for the margin zone
-constexpr int FT_MAXGROUPS = 256;  // group-minimum slots per query (groups beyond that fold modulo)
+constexpr int FT_MAXGROUPS = 256;  // group-value slots per query (groups beyond that fold modulo)
+constexpr int FT_CAP = 24;         // candidate slots per (quarter, query) buffer
 
 struct FeatArgs {
   const float* p1;
@@ -168,12 +169,28 @@ __global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int 
 // ---- main tcgen05 kernel -----------------------------------------------------------------------
 // 8 warps: warp w reads TMEM lane quarter (w & 3) — candidates 32(w&3)..+31 of every tile —
 // and owns the query half (w >> 2): 16 of the CTA's 32 queries (accumulator columns).
+//
+// Two passes over the e-matrix (the MMAs are simply issued twice: the tensor pipe is idle
+// otherwise, and the tiles come from L2):
+//   pass 0  per query, one element of every group of 32 candidates that is <= all the others
+//           (CREDUX.MIN on the raw bits; for a group that contains negative e the result is
+//           still an ELEMENT of the group, which is all the argument needs).  The R smallest
+//           group values are R distinct candidates, so the R-th smallest of them (tau0) is a
+//           VALID upper bound of the R-th smallest e overall — and a tight one (about the
+//           1.4 R-th smallest for 64 groups).  R = K + 8.
+//   pass 1  every candidate with e <= tau0 is APPENDED (ballot + popc, no ordering work) to
+//           the (quarter, query) buffer: ~1.4 R candidates per query in total.
+// Finalisation per query (one warp): T_K = K-th smallest buffered e; every canonical top-K
+// neighbour has e <= T_K + 2 eps, and everything with e <= tau0 is buffered, so if
+// T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset; they are
+// re-ranked with the canonical distance.  Otherwise (or on a buffer overflow) -> fallback.
 __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) {
   extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
   __shared__ __align__(8) uint64_t mbar_s[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float tau_s[4][FT_NQ];
   __shared__ float tau0_s[FT_NQ];
+  __shared__ int cnt_s[4][FT_NQ];
+  __shared__ int scratch_s[FT_THREADS / 32][32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -183,8 +200,9 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
   const int n2 = a.len2 ? min((int)a.len2[b], a.P2) : a.P2;
   const float INF = __int_as_float(0x7f800000);
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  // dynamic smem, 1024-aligned: [stage0 | stage1 | queries | group minima]
+  // dynamic smem, 1024-aligned: [stage0 | stage1 | queries | group values / candidate buffers]
   const uint32_t raw = smem_u32(ft_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* base_ptr = ft_smem_raw + (base - raw);
@@ -192,22 +210,24 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   const uint32_t atomA = 128u * 128u;                // one 32-float K-slab of a stage
   const uint32_t qtile = base + 2u * stage_bytes;
   const uint32_t atomB = 32u * 128u;
-  const int chunks_per_row = D >> 2;                 // 16-byte chunks
+  const int cpr = D >> 2;                            // 16-byte chunks per row: 8, 16 or 32
   const int T = (n2 + FT_TM - 1) / FT_TM;
 
   const float* p2b = a.p2 + (size_t)b * a.P2 * D;
   const float* p1b = a.p1 + (size_t)b * a.P1 * D;
 
+  // tile fill: thread -> (row r0 + i*rstep, chunk c) with c and (r & 7) fixed per thread, so the
+  // swizzled destination and the source advance by constants (256 % cpr == 0 for D = 32/64/128)
+  const int lt_c = tid % cpr, lt_r0 = tid / cpr, lt_rstep = FT_THREADS / cpr;
+  const uint32_t lt_dst0 = (uint32_t)(lt_c >> 3) * atomA + (uint32_t)lt_r0 * 128u + (uint32_t)(((lt_c & 7) ^ (lt_r0 & 7)) << 4);
   auto load_tile = [&](int t, int stage) {
-    const uint32_t sb = base + (uint32_t)stage * stage_bytes;
-    const int total = FT_TM * chunks_per_row;
-    for (int g = tid; g < total; g += FT_THREADS) {
-      const int r = g / chunks_per_row, c = g - r * chunks_per_row;
-      const int j = t * FT_TM + r;
-      const bool ok = j < n2;
-      const float* src = p2b + (size_t)(ok ? j : 0) * D + c * 4;
-      const uint32_t dst = sb + (uint32_t)(c >> 3) * atomA + (uint32_t)r * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
-      cp_async16(dst, src, ok ? 16 : 0);
+    const uint32_t sb = base + (uint32_t)stage * stage_bytes + lt_dst0;
+    const float* src0 = p2b + (size_t)(t * FT_TM + lt_r0) * D + lt_c * 4;
+    const int rows_left = n2 - t * FT_TM - lt_r0;  // row r valid iff i*rstep < rows_left
+#pragma unroll 4
+    for (int i = 0; i < FT_TM / lt_rstep; ++i) {
+      const bool ok = i * lt_rstep < rows_left;
+      cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, ok ? src0 + (size_t)i * lt_rstep * D : p2b, ok ? 16 : 0);
     }
   };
 
@@ -223,12 +243,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
     mbar_init(smem_u32(&mbar_s[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp < 4) tau_s[warp][lane] = INF;
-  if (warp == 4) tau0_s[lane] = INF;
   {
-    const int total = FT_NQ * chunks_per_row;
+    const int total = FT_NQ * cpr;
     for (int g = tid; g < total; g += FT_THREADS) {
-      const int r = g / chunks_per_row, c = g - r * chunks_per_row;
+      const int r = g / cpr, c = g - r * cpr;
       const int qi = q0 + r;
       const bool ok = qi < n1;
       const float* src = p1b + (size_t)(ok ? qi : 0) * D + c * 4;
@@ -236,22 +254,14 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
       cp_async16(dst, src, ok ? 16 : 0);
     }
   }
-  // Two passes over the e-matrix when there are >= 32 (quarter, tile) groups of candidates:
-  //   pass 0  per query, the minimum e of every group of 32 candidates (one REDUX each).  The
-  //           32 smallest group minima are 32 distinct candidates, so the 32nd smallest of
-  //           them (tau0) is a VALID upper bound of the 32nd smallest e overall — and a tight
-  //           one (about the 44th smallest for 64 groups);
-  //   pass 1  the list pass, admitting only e <= tau0: ~1.4 insertions per kept slot instead
-  //           of the ~15 a streaming top-32 without prior bound needs.
-  // The MMAs are simply issued twice (the tensor pipe is idle otherwise); tiles come from L2.
   const int G = 4 * T;
-  const int passes = G >= 32 ? 2 : 1;
-  const int U = passes * T;
+  const int U = 2 * T;
   const int Gs = min(G, FT_MAXGROUPS);
-  const int Gpad = (Gs + 31) & ~31;
-  int* gmin_s = reinterpret_cast<int*>(base_ptr + 2u * stage_bytes + (uint32_t)D * 128u);  // [32][Gpad] ordered keys
-  if (passes == 2)
-    for (int g = tid; g < FT_NQ * Gpad; g += FT_THREADS) gmin_s[g] = 0x7fffffff;
+  const int Gpad = max((Gs + 31) & ~31, 32);
+  unsigned char* aux = base_ptr + 2u * stage_bytes + (uint32_t)D * 128u;
+  int* gval_s = reinterpret_cast<int*>(aux);        // pass 0: [32][Gpad] raw float bits
+  float2* buf_s = reinterpret_cast<float2*>(aux);   // pass 1: [4][32][FT_CAP] (e, idx) — aliases gval_s
+  for (int g = tid; g < FT_NQ * Gpad; g += FT_THREADS) gval_s[g] = 0x7f800000;  // +inf
 
   if (U > 0) load_tile(0, 0);
   if (U > 1) load_tile(1 % T, 1);
@@ -277,82 +287,74 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   };
   if (tid == 0 && U > 0) issue_mma(0);
 
-  WarpList lst[FT_QW];
+  int cnt[FT_QW];
 #pragma unroll
-  for (int n = 0; n < FT_QW; ++n) lst[n].init();
-  float tq = INF;    // lanes 0..15: admission bound of query nq0 + lane (e-space)
-  float tau0 = INF;  // lanes 0..15: prior bound of that query (INF without pass 0)
+  for (int n = 0; n < FT_QW; ++n) cnt[n] = 0;
+  float tau0 = INF;  // lanes 0..15: admission bound of query nq0 + lane (e-space)
 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
-    const bool list_pass = (passes == 1) || (u >= T);
+    const bool list_pass = u >= T;
     if (tid == 0 && u + 1 < U) issue_mma(u + 1);
-    if (passes == 2 && u == T) {
-      // ---- tau0 = 32nd smallest group minimum (rank by counting; 4 queries per warp) ----
+    if (u == T) {
+      // ---- tau0 = R-th smallest group value: 16-bit radix select on the ordered keys, upper end of
+      //      the selected bucket (valid: >= the exact R-th smallest; < 1% looser).  4 queries per warp.
+      const int R = min(32, K + 8);
       for (int qq = 0; qq < FT_NQ / 8; ++qq) {
         const int n = warp * (FT_NQ / 8) + qq;
-        const int* row = gmin_s + n * Gpad;
-        for (int g = lane; g < Gpad; g += 32) {
-          const int v = row[g];
-          int rank = 0;
-          for (int h = 0; h < Gpad; ++h) {
-            const int o = row[h];
-            rank += (o < v || (o == v && h < g)) ? 1 : 0;
+        const int* row = gval_s + n * Gpad;
+        unsigned prefix = 0u;
+        int k = R;
+        for (int bit = 31; bit >= 16; --bit) {
+          const unsigned himask = bit == 31 ? 0u : ~((2u << bit) - 1u);
+          int c = 0;
+          for (int g = lane; g < Gpad; g += 32) {
+            const int bits = row[g];
+            const unsigned uk = (unsigned)(bits ^ ((bits >> 31) & 0x7fffffff)) ^ 0x80000000u;  // unsigned order == float order
+            c += __popc(__ballot_sync(FULL, (uk & himask) == prefix && !(uk & (1u << bit))));
           }
-          if (rank == 31) {  // admit e == tau0 too: one step up in the ordered-key domain
-            const int k1 = v == 0x7fffffff ? v : v + 1;
-            tau0_s[n] = __int_as_float(k1 ^ ((k1 >> 31) & 0x7fffffff));
-          }
+          if (k > c) { prefix |= 1u << bit; k -= c; }
+        }
+        if (lane == 0) {
+          const unsigned uk = prefix | 0xffffu;
+          const int key = (int)(uk ^ 0x80000000u);
+          int bits = key ^ ((key >> 31) & 0x7fffffff);
+          if ((bits & 0x7fffffff) > 0x7f800000) bits = 0x7f800000;  // bucket of +inf: fewer than R finite groups
+          tau0_s[n] = __int_as_float(bits);
         }
       }
-      __syncthreads();
+      __syncthreads();  // gval_s is dead from here on: buf_s may overwrite it
       tau0 = tau0_s[nq0 + (lane & (FT_QW - 1))];
-      if (half == 0) tau_s[quarter][lane] = tau0_s[lane];
-      __syncthreads();
     }
     const int j = t * FT_TM + quarter * 32 + lane;
     const float ncj = j < n2 ? __ldg(a.nrm2 + (size_t)b * a.P2 + j) : INF;
-    if (list_pass) {
-      const int n = nq0 + (lane & (FT_QW - 1));
-      tq = fminf(fminf(tau_s[0][n], tau_s[1][n]), fminf(tau_s[2][n], tau_s[3][n]));
-    }
     mbar_wait(smem_u32(&mbar_s[u & 1]), (uint32_t)((u >> 1) & 1));
     tc_fence_after();
     if (u + 2 < U) load_tile((u + 2) % T, u & 1);  // MMA(u) has released this stage
     uint32_t acc[FT_QW];
     tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u & 1) * FT_NQ + nq0), acc);
     if (!list_pass) {
-      int mine = 0x7fffffff;
+      int mine = 0x7f800000;
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) {
-        const int bits = __float_as_int(fmaf(-2.0f, __uint_as_float(acc[n]), ncj));
-        const int key = bits ^ ((bits >> 31) & 0x7fffffff);  // signed-int order == float order
-        const int r = __reduce_min_sync(FULL, key);
+        const int r = __reduce_min_sync(FULL, __float_as_int(fmaf(-2.0f, __uint_as_float(acc[n]), ncj)));
         if (lane == n) mine = r;
       }
       if (lane < FT_QW) {
-        int* slot = gmin_s + (nq0 + lane) * Gpad + ((t * 4 + quarter) % FT_MAXGROUPS);
-        *slot = min(*slot, mine);  // (slot % 4, query half) identify this warp: no other writer
+        int* slot = gval_s + (nq0 + lane) * Gpad + ((t * 4 + quarter) % FT_MAXGROUPS);
+        // (slot % 4, query half) identify this warp: no other writer.  Keep the smaller FLOAT.
+        if (__int_as_float(mine) < __int_as_float(*slot)) *slot = mine;
       }
     } else {
-      const int jbase = t * FT_TM + quarter * 32;
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) {
         const float e = fmaf(-2.0f, __uint_as_float(acc[n]), ncj);  // inf for padded candidates
-        float bound = __shfl_sync(FULL, tq, n);
-        unsigned m = __ballot_sync(FULL, e < bound);
+        const bool hit = e <= __shfl_sync(FULL, tau0, n);
+        const unsigned m = __ballot_sync(FULL, hit);
         if (m) {
-          do {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const float ec = __shfl_sync(FULL, e, l);
-            if (ec < bound) {
-              lst[n].insert_tail(ec, jbase + l, lane);
-              bound = fminf(bound, lst[n].kth(32));
-            }
-          } while (m);
-          const float mine = fminf(lst[n].kth(32), __shfl_sync(FULL, tau0, n));
-          if (lane == n) { tq = bound; tau_s[quarter][nq0 + n] = mine; }
+          const int pos = cnt[n] + __popc(m & lt_mask);
+          if (hit && pos < FT_CAP) buf_s[((size_t)quarter * FT_NQ + nq0 + n) * FT_CAP + pos] = make_float2(e, __int_as_float(j));
+          cnt[n] += __popc(m);
         }
       }
     }
@@ -362,15 +364,14 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
     __syncthreads();
     tc_fence_after();
   }
-
-  // ---- merge the four quarters' lists (stage memory is free now) ----
-  float2* mrg = reinterpret_cast<float2*>(base_ptr);  // [4][32 queries][32 slots] (e, idx bits)
 #pragma unroll
   for (int n = 0; n < FT_QW; ++n)
-    mrg[((size_t)quarter * FT_NQ + nq0 + n) * 32 + lane] = make_float2(lst[n].d, __int_as_float(lst[n].i));
+    if (lane == n) cnt_s[quarter][nq0 + n] = cnt[n];
   __syncthreads();
 
+  // ---- finalisation: 4 queries per warp ----
   const float nmax = __uint_as_float(a.nmax2[b]);
+  int* scratch = scratch_s[warp];
   for (int qq = 0; qq < FT_NQ / 8; ++qq) {
     const int n = warp * (FT_NQ / 8) + qq;
     const int qi = q0 + n;
@@ -381,68 +382,83 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
       if (lane < K) { od[lane] = 0.0f; oi[lane] = 0; }
       continue;
     }
-    WarpList L;
-    {
-      const float2 v = mrg[((size_t)0 * FT_NQ + n) * 32 + lane];
-      L.d = v.x; L.i = __float_as_int(v.y);
-    }
-    for (int w = 1; w < 4; ++w) {
-      const float2 v = mrg[((size_t)w * FT_NQ + n) * 32 + lane];
-      const float ve = v.x;
-      const int vi = __float_as_int(v.y);
-      float bound = L.kth(32);
-      int bi = __shfl_sync(FULL, L.i, 31);
-      unsigned m = __ballot_sync(FULL, vi >= 0 && (ve < bound || (ve == bound && (bi < 0 || vi < bi))));
-      while (m) {
-        const int l = __ffs(m) - 1;
-        m &= m - 1;
-        const float ec = __shfl_sync(FULL, ve, l);
-        const int ic = __shfl_sync(FULL, vi, l);
-        bound = L.kth(32);
-        bi = __shfl_sync(FULL, L.i, 31);
-        if (ec < bound || (ec == bound && (bi < 0 || ic < bi))) L.insert_key(ec, ic, lane);
+    const int c0 = cnt_s[0][n], c1 = cnt_s[1][n], c2 = cnt_s[2][n], c3 = cnt_s[3][n];
+    const int C = c0 + c1 + c2 + c3;
+    bool ok = max(max(c0, c1), max(c2, c3)) <= FT_CAP && C <= 64;
+    // logical element i of the concatenated buffers -> (quarter w, slot h)
+    float ev[2];
+    int jv[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int i = lane + 32 * s2;
+      ev[s2] = INF; jv[s2] = 0x7fffffff;
+      if (ok && i < C) {
+        const int w = (i >= c0) + (i >= c0 + c1) + (i >= c0 + c1 + c2);
+        const int h = i - (w > 0 ? c0 : 0) - (w > 1 ? c1 : 0) - (w > 2 ? c2 : 0);
+        const float2 v = buf_s[((size_t)w * FT_NQ + n) * FT_CAP + h];
+        ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
       }
     }
-    const int cnt = __popc(__ballot_sync(FULL, L.i >= 0));
-    const float nq = a.nrm1[(size_t)b * a.P1 + qi];
-    const float eps2 = 2.0f * feat_eps(nq, nmax, D);
-    const float tk = K <= cnt ? __shfl_sync(FULL, L.d, K - 1) : INF;
-    const float e_last = __shfl_sync(FULL, L.d, 31);
-    const float limit = tk + eps2;
-    // everything with e below `boundary` is in the list: the 32nd entry when it is full, else the
-    // prior bound tau0 (INF without pass 0, i.e. the list then holds every candidate)
-    const float boundary = cnt == 32 ? e_last : tau0_s[n];
-    const bool superset = limit < boundary || (boundary == INF && cnt < 32);
-    if (!superset) {
+    float limit = INF;
+    const float t0 = tau0_s[n];
+    if (ok) {
+      // K-th smallest buffered e by rank counting (ties by candidate index)
+      int rk[2] = {0, 0};
+      const int Cc = min(C, 64);
+      for (int h = 0; h < Cc; ++h) {
+        const float oe = __shfl_sync(FULL, h < 32 ? ev[0] : ev[1], h & 31);
+        const int oj = __shfl_sync(FULL, h < 32 ? jv[0] : jv[1], h & 31);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) rk[s2] += (oe < ev[s2] || (oe == ev[s2] && oj < jv[s2])) ? 1 : 0;
+      }
+      float tk = INF;
+      if (C >= K) {
+        const unsigned m0 = __ballot_sync(FULL, rk[0] == K - 1 && lane < C);
+        const unsigned m1 = __ballot_sync(FULL, rk[1] == K - 1 && lane + 32 < C);
+        tk = m0 ? __shfl_sync(FULL, ev[0], __ffs(m0) - 1) : __shfl_sync(FULL, ev[1], __ffs(m1 | 0x80000000u) - 1);
+      }
+      const float nq = a.nrm1[(size_t)b * a.P1 + qi];
+      limit = tk + 2.0f * feat_eps(nq, nmax, D);
+      // everything with e <= tau0 is buffered, so the margin zone must end below tau0
+      // (tau0 == inf: every candidate of the cloud is buffered)
+      ok = limit < t0 || t0 == INF;
+    }
+    const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
+    const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
+    const int ncand = __popc(cm0) + __popc(cm1);
+    if (!ok || ncand > 32) {
       if (lane == 0) {
         const int pos = atomicAdd(a.fb_count, 1);
         a.fb_list[pos] = b * a.P1 + qi;
       }
       continue;
     }
-    const bool cand = L.i >= 0 && L.d <= limit;
+    // one candidate per lane
+    __syncwarp();
+    if (cand0) scratch[__popc(cm0 & lt_mask)] = jv[0];
+    if (cand1) scratch[__popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
+    __syncwarp();
+    const bool cand = lane < ncand;
     float dc = INF;
     int ci = 0x7fffffff;
     if (cand) {
-      ci = L.i;
+      ci = scratch[lane];
       const float4* xr = reinterpret_cast<const float4*>(p1b + (size_t)qi * D);
       const float4* yr = reinterpret_cast<const float4*>(p2b + (size_t)ci * D);
-      float acc = 0.0f;
-      for (int c = 0; c < chunks_per_row; ++c) {
+      float acc2 = 0.0f;
+      for (int c = 0; c < cpr; ++c) {
         const float4 x = __ldg(xr + c), y = __ldg(yr + c);
-        acc = sq_acc(acc, x.x, y.x); acc = sq_acc(acc, x.y, y.y);
-        acc = sq_acc(acc, x.z, y.z); acc = sq_acc(acc, x.w, y.w);
+        acc2 = sq_acc(acc2, x.x, y.x); acc2 = sq_acc(acc2, x.y, y.y);
+        acc2 = sq_acc(acc2, x.z, y.z); acc2 = sq_acc(acc2, x.w, y.w);
       }
-      dc = acc;
+      dc = acc2;
     }
     int rank = 0;
-#pragma unroll
-    for (int m2 = 0; m2 < 32; ++m2) {
+    for (int m2 = 0; m2 < ncand; ++m2) {
       const float od2 = __shfl_sync(FULL, dc, m2);
       const int oi2 = __shfl_sync(FULL, ci, m2);
       rank += (od2 < dc || (od2 == dc && oi2 < ci)) ? 1 : 0;
     }
-    const int ncand = __popc(__ballot_sync(FULL, cand));
     if (cand && rank < K) { od[rank] = dc; oi[rank] = (int64_t)ci; }
     if (lane < K && lane >= ncand) { od[lane] = 0.0f; oi[lane] = 0; }  // fewer than K candidates in the cloud
   }
@@ -453,15 +469,14 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   }
 }
 
-// ---- exact fallback: one warp per flagged query, candidates streamed from L2 ---------------------
+// ---- exact fallback: one CTA per flagged query (8 warps x 1/8 of the candidates, then a merge) ------
 __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
+  __shared__ float2 part_s[8][32];
   const int total = *a.fb_count;
-  if (total == 0) return;
-  const int lane = threadIdx.x & 31;
-  const int wstride = gridDim.x * (blockDim.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float INF = __int_as_float(0x7f800000);
   const int chunks = a.D >> 2;
-  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += wstride) {
+  for (int e = blockIdx.x; e < total; e += gridDim.x) {
     const int flat = a.fb_list[e];
     const int b = flat / a.P1, qi = flat - b * a.P1;
     const int n2 = a.len2 ? min((int)a.len2[b], a.P2) : a.P2;
@@ -470,10 +485,12 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
     WarpList L;
     L.init();
     float tau = INF;
-    for (int j0 = 0; j0 < n2; j0 += 32) {
+    const int per = ((n2 + 7) / 8 + 31) & ~31;  // contiguous, 32-aligned slice per warp: ascending indices
+    const int jlo = warp * per, jhi = min(n2, jlo + per);
+    for (int j0 = jlo; j0 < jhi; j0 += 32) {
       const int j = j0 + lane;
       float acc = INF;
-      if (j < n2) {
+      if (j < jhi) {
         const float4* yr = reinterpret_cast<const float4*>(p2b + (size_t)j * a.D);
         acc = 0.0f;
         for (int c = 0; c < chunks; ++c) {
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
           acc = sq_acc(acc, x.z, y.z); acc = sq_acc(acc, x.w, y.w);
         }
       }
-      unsigned m = __ballot_sync(FULL, j < n2 && acc < tau);
+      unsigned m = __ballot_sync(FULL, j < jhi && acc < tau);
       while (m) {
         const int l = __ffs(m) - 1;
         m &= m - 1;
@@ -493,11 +510,33 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
         }
       }
     }
-    if (lane < a.K) {
-      const size_t o = ((size_t)b * a.P1 + qi) * a.K + lane;
-      const bool found = L.i >= 0;
-      a.dists[o] = found ? L.d : 0.0f;
-      a.idx[o] = found ? (int64_t)L.i : 0;
+    __syncthreads();  // previous query's merge has finished reading part_s
+    part_s[warp][lane] = make_float2(L.d, __int_as_float(L.i));
+    __syncthreads();
+    if (warp == 0) {
+      // slices are in ascending index order, so appending them in warp order keeps insert_tail's
+      // "equal distance -> lower index first" rule
+      for (int w = 1; w < 8; ++w) {
+        const float2 v = part_s[w][lane];
+        const int vi = __float_as_int(v.y);
+        unsigned m = __ballot_sync(FULL, vi >= 0 && v.x < tau);
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const float dcand = __shfl_sync(FULL, v.x, l);
+          const int icand = __shfl_sync(FULL, vi, l);
+          if (dcand < tau) {
+            L.insert_tail(dcand, icand, lane);
+            tau = L.kth(a.K);
+          }
+        }
+      }
+      if (lane < a.K) {
+        const size_t o = ((size_t)b * a.P1 + qi) * a.K + lane;
+        const bool found = L.i >= 0;
+        a.dists[o] = found ? L.d : 0.0f;
+        a.idx[o] = found ? (int64_t)L.i : 0;
+      }
     }
   }
 }
@@ -537,8 +576,8 @@ static bool feat_enabled() {
 bool knn_feat_eligible(const KnnArgs& a) {
   if (!feat_enabled()) return false;
   if (a.out_mode != OUT_KNN || a.use_radius) return false;
-  if (a.D < 32 || a.D > 128 || (a.D & 31)) return false;
-  if (a.K > FT_MAX_K || a.P2 < FT_TM) return false;
+  if (a.D != 32 && a.D != 64 && a.D != 128) return false;
+  if (a.K > FT_MAX_K || a.P2 < 1024) return false;  // needs >= 32 groups of 32 candidates
   if ((long long)a.B * a.P1 >= (1LL << 31)) return false;
   if ((reinterpret_cast<uintptr_t>(a.p1) | reinterpret_cast<uintptr_t>(a.p2)) & 15) return false;
   return true;
@@ -564,12 +603,13 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
              k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list};
   const int groups = 4 * ceil_div(k.P2, FT_TM);
   const int gpad = ((groups < FT_MAXGROUPS ? groups : FT_MAXGROUPS) + 31) & ~31;
-  const size_t smem = (size_t)k.D * 512 * 2 + (size_t)k.D * 128 + 1024 + (size_t)FT_NQ * gpad * sizeof(int);
+  const size_t aux = max((size_t)FT_NQ * gpad * sizeof(int), (size_t)4 * FT_NQ * FT_CAP * sizeof(float2));
+  const size_t smem = (size_t)k.D * 512 * 2 + (size_t)k.D * 128 + 1024 + aux;
   TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k.P1, FT_NQ), k.B);
   knn_feat_tc_kernel<<<grid, FT_THREADS, smem, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
-  knn_feat_fallback_kernel<<<num_sms() * 2, 256, 0, st>>>(a);
+  knn_feat_fallback_kernel<<<num_sms() * 4, 256, 0, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_fallback_kernel");
   return TPG_OK;
 }

@@ -44,6 +44,8 @@ KNN_CASES = [
     (1, 128, 128, 64, 4, "featdup"),
     (1, 100, 100, 5, 7, "feat"),
     (1, 64, 50, 130, 8, "feat"),
+    (1, 300, 700, 96, 24, "feat"),   # D = 96 / P2 < 1024: SIMT path
+    (1, 256, 512, 128, 16, "feat"),
     (1, 50, 10, 3, 16, "fluid"),     # K > P2 -> zero padding
     (1, 70, 200, 3, 40, "fluid"),    # K > 32 -> multi-pass
     (1, 40, 300, 3, 100, "dup"),
@@ -95,12 +97,13 @@ KNN_TC_CASES = [
     (1, 2048, 2048, 64, 4, "featself"),
     (1, 2048, 2048, 64, 8, "feat"),
     (2, 1000, 1500, 64, 20, "feat"),     # ragged query / candidate tiles
-    (1, 300, 700, 96, 24, "feat"),
-    (1, 256, 512, 128, 16, "feat"),
-    (1, 512, 512, 64, 12, "featdup"),    # exact duplicate rows: (d2, idx) ties
+    (1, 300, 1100, 128, 24, "feat"),
+    (1, 256, 4096, 128, 16, "feat"),
+    (1, 100, 40000, 32, 16, "feat"),     # > 256 groups: group slots fold modulo
+    (1, 1024, 1024, 64, 12, "featdup"),  # exact duplicate rows: (d2, idx) ties
     (1, 512, 1024, 32, 20, "featoffset"),   # |x| >> distances: margin overflow -> exact fallback
     (1, 512, 1024, 64, 20, "featcluster"),  # tight clusters of near-duplicates
-    (1, 384, 640, 64, 16, "featrelu"),   # post-activation features (many exact zeros)
+    (1, 384, 1280, 64, 16, "featrelu"),  # post-activation features (many exact zeros)
 ]
 
 
@@ -141,9 +144,9 @@ def test_knn_tensor_core_path_bit_exact(F, oracle, B, P1, P2, D, K, kind):
 def test_knn_tensor_core_path_ragged_lengths(F, oracle):
     rng = np.random.default_rng(21)
     a = rng.standard_normal((3, 300, 64)).astype(np.float32)
-    b = rng.standard_normal((3, 400, 64)).astype(np.float32)
+    b = rng.standard_normal((3, 1400, 64)).astype(np.float32)
     l1 = np.array([300, 33, 0], np.int64)
-    l2 = np.array([400, 130, 7], np.int64)   # 7 < K: zero padding
+    l2 = np.array([1400, 130, 7], np.int64)   # 130: too few groups for a prior bound; 7 < K: zero padding
     od, oi = oracle.knn(a, b, 12, l1, l2)
     gd, gi = F.knn(cu(a), cu(b), 12, cu(l1), cu(l2))
     np.testing.assert_array_equal(gi.cpu().numpy(), oi)
