@@ -75,14 +75,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // bounded spin: a descriptor bug must surface as a trap, never as a hung GPU
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)  // suspend up to 20 us per poll instead of spinning
         : "memory");
     if (ok) return;
   }
@@ -144,6 +144,34 @@ __device__ __forceinline__ float feat_eps(float nq, float nmax, int D) {
   const float xn = sqrtf(nq) * 1.001f, yn = sqrtf(nmax) * 1.001f;
   const float s = xn + yn;
   return 6e-3f * xn * yn + (float)(2 * D + 16) * 5.9604645e-8f * s * s;
+}
+
+// Upper end of the 16-bit radix bucket that holds the k-th smallest (1-based) of the values a
+// warp holds as `nv` ordered-unsigned keys per lane: a valid upper bound of the exact k-th
+// smallest, less than 1% (2^-7 relative) above it.  Keys of absent values must be 0xffffffff.
+template <int NV>
+__device__ __forceinline__ unsigned warp_radix_bound16(const unsigned (&uk)[NV], int k) {
+  unsigned prefix = 0u, himask = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 16; --bit) {
+    const unsigned bmask = 1u << bit;
+    int c = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) c += __popc(__ballot_sync(FULL, (uk[v] & (himask | bmask)) == prefix));
+    if (k > c) { prefix |= bmask; k -= c; }
+    himask |= bmask;
+  }
+  return prefix | 0xffffu;
+}
+__device__ __forceinline__ unsigned ordered_key(float f) {  // unsigned order == float order
+  const int bits = __float_as_int(f);
+  return (unsigned)(bits ^ ((bits >> 31) & 0x7fffffff)) ^ 0x80000000u;
+}
+__device__ __forceinline__ float ordered_key_inv(unsigned uk) {
+  const int key = (int)(uk ^ 0x80000000u);
+  int bits = key ^ ((key >> 31) & 0x7fffffff);
+  if ((bits & 0x7fffffff) > 0x7f800000) bits = 0x7f800000;  // bucket of +inf
+  return __int_as_float(bits);
 }
 
 // ---- squared norms + per-cloud max ---------------------------------------------------------
@@ -223,11 +251,16 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   auto load_tile = [&](int t, int stage) {
     const uint32_t sb = base + (uint32_t)stage * stage_bytes + lt_dst0;
     const float* src0 = p2b + (size_t)(t * FT_TM + lt_r0) * D + lt_c * 4;
-    const int rows_left = n2 - t * FT_TM - lt_r0;  // row r valid iff i*rstep < rows_left
+    const size_t sstep = (size_t)lt_rstep * D;
+    if ((t + 1) * FT_TM <= n2) {  // full tile: no predicates
 #pragma unroll 4
-    for (int i = 0; i < FT_TM / lt_rstep; ++i) {
-      const bool ok = i * lt_rstep < rows_left;
-      cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, ok ? src0 + (size_t)i * lt_rstep * D : p2b, ok ? 16 : 0);
+      for (int i = 0; i < FT_TM / lt_rstep; ++i) cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, src0 + i * sstep, 16);
+    } else {
+      const int rows_left = n2 - t * FT_TM - lt_r0;  // row valid iff i*rstep < rows_left
+      for (int i = 0; i < FT_TM / lt_rstep; ++i) {
+        const bool ok = i * lt_rstep < rows_left;
+        cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, ok ? src0 + i * sstep : p2b, ok ? 16 : 0);
+      }
     }
   };
 
@@ -303,25 +336,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
       for (int qq = 0; qq < FT_NQ / 8; ++qq) {
         const int n = warp * (FT_NQ / 8) + qq;
         const int* row = gval_s + n * Gpad;
-        unsigned prefix = 0u;
-        int k = R;
-        for (int bit = 31; bit >= 16; --bit) {
-          const unsigned himask = bit == 31 ? 0u : ~((2u << bit) - 1u);
-          int c = 0;
-          for (int g = lane; g < Gpad; g += 32) {
-            const int bits = row[g];
-            const unsigned uk = (unsigned)(bits ^ ((bits >> 31) & 0x7fffffff)) ^ 0x80000000u;  // unsigned order == float order
-            c += __popc(__ballot_sync(FULL, (uk & himask) == prefix && !(uk & (1u << bit))));
-          }
-          if (k > c) { prefix |= 1u << bit; k -= c; }
-        }
-        if (lane == 0) {
-          const unsigned uk = prefix | 0xffffu;
-          const int key = (int)(uk ^ 0x80000000u);
-          int bits = key ^ ((key >> 31) & 0x7fffffff);
-          if ((bits & 0x7fffffff) > 0x7f800000) bits = 0x7f800000;  // bucket of +inf: fewer than R finite groups
-          tau0_s[n] = __int_as_float(bits);
-        }
+        unsigned uk[FT_MAXGROUPS / 32];
+#pragma unroll
+        for (int v = 0; v < FT_MAXGROUPS / 32; ++v)
+          uk[v] = lane + 32 * v < Gpad ? ordered_key(__int_as_float(row[lane + 32 * v])) : 0xffffffffu;
+        const unsigned bound = Gpad <= 64 ? warp_radix_bound16(reinterpret_cast<const unsigned(&)[2]>(uk), R)
+                                          : warp_radix_bound16(uk, R);
+        if (lane == 0) tau0_s[n] = ordered_key_inv(bound);
       }
       __syncthreads();  // gval_s is dead from here on: buf_s may overwrite it
       tau0 = tau0_s[nq0 + (lane & (FT_QW - 1))];
@@ -402,20 +423,11 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
     float limit = INF;
     const float t0 = tau0_s[n];
     if (ok) {
-      // K-th smallest buffered e by rank counting (ties by candidate index)
-      int rk[2] = {0, 0};
-      const int Cc = min(C, 64);
-      for (int h = 0; h < Cc; ++h) {
-        const float oe = __shfl_sync(FULL, h < 32 ? ev[0] : ev[1], h & 31);
-        const int oj = __shfl_sync(FULL, h < 32 ? jv[0] : jv[1], h & 31);
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) rk[s2] += (oe < ev[s2] || (oe == ev[s2] && oj < jv[s2])) ? 1 : 0;
-      }
+      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
       float tk = INF;
       if (C >= K) {
-        const unsigned m0 = __ballot_sync(FULL, rk[0] == K - 1 && lane < C);
-        const unsigned m1 = __ballot_sync(FULL, rk[1] == K - 1 && lane + 32 < C);
-        tk = m0 ? __shfl_sync(FULL, ev[0], __ffs(m0) - 1) : __shfl_sync(FULL, ev[1], __ffs(m1 | 0x80000000u) - 1);
+        const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
+        tk = ordered_key_inv(warp_radix_bound16(uk2, K));
       }
       const float nq = a.nrm1[(size_t)b * a.P1 + qi];
       limit = tk + 2.0f * feat_eps(nq, nmax, D);
