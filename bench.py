@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--per-op", action="store_true", help="print the per-op time table to stderr")
+    ap.add_argument("--per-call", action="store_true", help="print every call of the schedule with its mean device time")
     return ap.parse_args()
 
 
@@ -303,11 +304,13 @@ def run_ours(args):
         pass
     op_ms, op_bytes, op_calls = {}, {}, {}
     cursor = {k: 0 for k in timers}
+    call_ms = [0.0] * len(doc["calls"])
     for step in range(args.steps):
-        for c in doc["calls"]:
+        for ci, c in enumerate(doc["calls"]):
             op = c["op"]
             a, b = timers[op][cursor[op]]
             cursor[op] += 1
+            call_ms[ci] += a.elapsed_time(b)
             op_ms[op] = op_ms.get(op, 0.0) + a.elapsed_time(b)
             op_bytes[op] = op_bytes.get(op, 0) + ht.algorithmic_bytes(c)
             op_calls[op] = op_calls.get(op, 0) + 1
@@ -332,6 +335,16 @@ def run_ours(args):
         "per_op_ms_per_step": {k: v / args.steps for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])},
         "per_op_gbs": {k: op_bytes[k] / (op_ms[k] * 1e-3) / 1e9 for k in op_ms},
     }
+    if args.per_call and rank == 0:
+        agg = {}
+        for ci, c in enumerate(doc["calls"]):
+            sig = c["op"] + " " + " ".join(f"{k}={tuple(v['shape']) if isinstance(v, dict) else v}" for k, v in c["in"].items()
+                                          if k not in ("id", "fwd_id"))
+            e = agg.setdefault(sig, [0, 0.0])
+            e[0] += 1
+            e[1] += call_ms[ci] / args.steps
+        for sig, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {ms * 1e3:9.1f} us/step  {n:3d} x {ms * 1e3 / n:8.1f} us  {sig}", file=sys.stderr)
     if args.per_op and rank == 0:
         for k, v in roofline["per_op_ms_per_step"].items():
             print(f"  {k:12s} {v:9.3f} ms/step  {op_calls[k] // args.steps:4d} calls  "

@@ -112,7 +112,7 @@ int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N,
  *     sampling.py:50-106 (numba loop sampling.py:36-44).  pts [B,N,D] (D<=3),
  *     start [B] int64 -> idx [B,k] int64 and, when dist_rows != NULL, the
  *     [B,k,N] rows of squared distances the reference returns.             */
-size_t tpg_fps_workspace_bytes(int B, int N); /* 0 for N <= 8192 */
+size_t tpg_fps_workspace_bytes(int B, int N); /* 0 for N <= 65536 */
 int tpg_fps_f32(const float* xyz, int B, int N, int npoint, int32_t* idx,
                 void* workspace, size_t workspace_bytes, tpg_stream_t stream);
 int tpg_fps_start_f32(const float* pts, int B, int N, int D, int k,

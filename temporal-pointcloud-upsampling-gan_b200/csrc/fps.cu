@@ -15,9 +15,12 @@
 // shared-memory exchange with a single __syncthreads (double-buffered) -> two more
 // REDUX -> the winner's coordinates come back through L1 (the cloud was loaded
 // through L1 by this CTA and stays resident).
-// Clouds larger than 8192 points use the same round structure with the running
-// min-dist in a caller-provided global workspace.
+// Clouds of more than 2048 points are split over a thread-block cluster of 8 CTAs (DSMEM
+// exchange of the local winners, one cluster barrier per round); beyond 65536 points the
+// running min-dist moves to a caller-provided global workspace.
 #include "common.cuh"
+
+#include <cooperative_groups.h>
 
 namespace tpg {
 
@@ -28,6 +31,7 @@ struct FpsArgs {
   void* out;             // int32 [B,npoint] (A) or int64 (B)
   float* rows;           // mode B optional [B,npoint,N]
   float* temp_ws;        // [B,N] for the large-cloud kernel
+  int flags;             // tuning hook (tools/bench_fps.py), unused by the shipped kernels
 };
 
 __device__ __forceinline__ void load_point(const float* p, int D, float& x, float& y, float& z) {
@@ -55,21 +59,47 @@ __device__ __forceinline__ int block_argmax(unsigned bits, unsigned j, bool has,
   return j2 == 0xffffffffu ? 0 : (int)j2;
 }
 
-template <int PPT, bool MODEB>
+// Register-resident FPS.  One CTA (CL == 1) or one thread-block cluster of CL CTAs (CL == 8,
+// one SM each) owns a cloud; a CTA keeps its slice of the cloud in registers, PPT points per
+// thread, and uses as FEW warps as the slice allows: the per-round cost of a warp is
+// ~14 instructions per point plus ~30 of fixed reduction work, so 8 points per thread keeps
+// the round latency-bound (~300 cycles) instead of issue-bound.
+// Cluster rounds: CTA-local arg-max as above, then warp 0 pushes {key, index, xyz} of the local
+// winner into every peer's shared memory (DSMEM), one cluster barrier, and every thread reduces
+// the CL slots — the winner's coordinates arrive with the key, so no global access is on the
+// critical path (cluster.sync invalidates L1D anyway).
+struct __align__(16) FpsSlot {
+  unsigned long long key;  // (bits(min-dist) + 1) << 32 | ~index; 0 == no candidate
+  float x, y, z;
+  unsigned pad;
+};
+
+__device__ __forceinline__ unsigned long long fps_pack(unsigned key, unsigned j) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - j);
+}
+
+template <int PPT, int CL, bool MODEB>
 __global__ void __launch_bounds__(1024) fps_reg_kernel(FpsArgs a) {
-  __shared__ unsigned s_bits[2][32];
-  __shared__ unsigned s_j[2][32];
-  const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  __shared__ unsigned long long s_key[2][32];
+  __shared__ FpsSlot xchg[2][CL];
+  extern __shared__ float pts_s[];  // this CTA's slice of the cloud, xyz interleaved (winner lookup)
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int nwarps = T >> 5;
+  const int b = blockIdx.x / CL, rank = blockIdx.x % CL;
   const float* p = a.pts + (size_t)b * a.N * a.D;
+  const int ppc = CL == 1 ? a.N : ((a.N + CL - 1) / CL + 31) & ~31;  // points per CTA
+  const int lo = rank * ppc, hi = min(a.N, lo + ppc);
   float x[PPT], y[PPT], z[PPT], t[PPT];
   bool live[PPT];
 #pragma unroll
   for (int s = 0; s < PPT; ++s) {
-    const int j = tid + s * T;
-    live[s] = j < a.N;
+    const int jl = tid + s * T, j = lo + jl;
+    live[s] = j < hi;
     x[s] = y[s] = z[s] = 0.0f;
-    if (live[s]) load_point(p + (size_t)j * a.D, a.D, x[s], y[s], z[s]);
+    if (live[s]) {
+      load_point(p + (size_t)j * a.D, a.D, x[s], y[s], z[s]);
+      pts_s[3 * jl] = x[s]; pts_s[3 * jl + 1] = y[s]; pts_s[3 * jl + 2] = z[s];
+    }
     if (MODEB) {
       t[s] = __int_as_float(0x7f800000);
     } else {
@@ -79,30 +109,78 @@ __global__ void __launch_bounds__(1024) fps_reg_kernel(FpsArgs a) {
     }
   }
   int cur = MODEB ? (int)a.start[b] : 0;
+  float cx, cy, cz;
+  load_point(p + (size_t)cur * a.D, a.D, cx, cy, cz);
+  __syncthreads();
   for (int it = 0; it < a.npoint; ++it) {
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
       if (MODEB) reinterpret_cast<int64_t*>(a.out)[(size_t)b * a.npoint + it] = cur;
       else reinterpret_cast<int32_t*>(a.out)[(size_t)b * a.npoint + it] = cur;
     }
     if (it == a.npoint - 1 && !(MODEB && a.rows)) break;
-    float cx, cy, cz;
-    load_point(p + (size_t)cur * a.D, a.D, cx, cy, cz);
+    // branch-free update (the PPT points of a thread must overlap in the pipeline: a branchy
+    // version serialises them at ~135 cycles per point).  key = bits(min-dist) + 1 for live
+    // points, 0 for skipped ones; strict '>' keeps the lower index on ties.
     unsigned bb = 0u, bj = 0xffffffffu;
-    bool has = false;
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
-      const int j = tid + s * T;
-      if (live[s]) {
-        float d = sqdist3(x[s], y[s], z[s], cx, cy, cz);
-        if (MODEB && a.rows) a.rows[((size_t)b * a.npoint + it) * a.N + j] = d;
-        float v = fminf(d, t[s]);
-        t[s] = v;
-        unsigned vb = __float_as_uint(v);
-        if (!has || vb > bb) { bb = vb; bj = (unsigned)j; has = true; }
+      const int j = lo + tid + s * T;
+      const float d = sqdist3(x[s], y[s], z[s], cx, cy, cz);
+      if (MODEB && a.rows && live[s]) a.rows[((size_t)b * a.npoint + it) * a.N + j] = d;
+      const float v = fminf(d, t[s]);
+      t[s] = v;
+      const unsigned key = live[s] ? __float_as_uint(v) + 1u : 0u;
+      const bool take = key > bb;
+      bb = take ? key : bb;
+      bj = take ? (unsigned)j : bj;
+    }
+    // warp arg-max: (max key, lowest index)
+    const int warp = tid >> 5, buf = it & 1;
+    const unsigned m = __reduce_max_sync(FULL, bb);
+    const unsigned jm = __reduce_min_sync(FULL, (bb == m && m != 0u) ? bj : 0xffffffffu);
+    if (lane == 0) s_key[buf][warp] = m == 0u ? 0ull : fps_pack(m, jm);
+    __syncthreads();
+    // CTA arg-max over the warp entries: REDUX on the two halves of the packed key (measured faster
+    // than a linear scan of broadcast LDS.64 even for 4 warps)
+    unsigned long long best;
+    {
+      const unsigned long long e = lane < nwarps ? s_key[buf][lane] : 0ull;
+      const unsigned hi32 = __reduce_max_sync(FULL, (unsigned)(e >> 32));
+      const unsigned lo32 = __reduce_max_sync(FULL, (unsigned)(e >> 32) == hi32 ? (unsigned)e : 0u);
+      best = ((unsigned long long)hi32 << 32) | lo32;
+    }
+    if (CL == 1) {
+      cur = best == 0ull ? 0 : (int)(0xffffffffu - (unsigned)best);  // upstream starts at (best=-1, besti=0)
+      cx = pts_s[3 * cur]; cy = pts_s[3 * cur + 1]; cz = pts_s[3 * cur + 2];
+    } else {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      if (warp == 0 && lane < CL) {
+        FpsSlot v;
+        v.key = best; v.x = v.y = v.z = 0.0f; v.pad = 0u;
+        if (best != 0ull) {
+          const int jl = (int)(0xffffffffu - (unsigned)best) - lo;
+          v.x = pts_s[3 * jl]; v.y = pts_s[3 * jl + 1]; v.z = pts_s[3 * jl + 2];
+        }
+        FpsSlot* dst = cluster.map_shared_rank(&xchg[buf][rank], lane);
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4((unsigned)v.key, (unsigned)(v.key >> 32), __float_as_uint(v.x), __float_as_uint(v.y));
+        reinterpret_cast<float*>(dst)[4] = v.z;
+      }
+      cluster.sync();
+      unsigned long long g = xchg[buf][0].key;
+      int src = 0;
+#pragma unroll
+      for (int r = 1; r < CL; ++r) { const unsigned long long o = xchg[buf][r].key; if (o > g) { g = o; src = r; } }
+      if (g == 0ull) {
+        cur = 0;
+        load_point(p, a.D, cx, cy, cz);
+      } else {
+        cur = (int)(0xffffffffu - (unsigned)g);
+        cx = xchg[buf][src].x; cy = xchg[buf][src].y; cz = xchg[buf][src].z;
       }
     }
-    cur = block_argmax(bb, bj, has, s_bits, s_j, it & 1, nwarps);
   }
+  if (CL > 1) cooperative_groups::this_cluster().sync();  // no CTA may exit while peers still write its smem
 }
 
 // large clouds: running min-dist in global memory, coordinates re-read (L2-resident)
@@ -144,26 +222,50 @@ __global__ void __launch_bounds__(1024) fps_mem_kernel(FpsArgs a) {
   }
 }
 
+template <int PPT, int CL, bool MODEB>
+static int fps_launch(const FpsArgs& a, int threads, cudaStream_t st) {
+  auto kern = fps_reg_kernel<PPT, CL, MODEB>;
+  const int ppc = CL == 1 ? a.N : (ceil_div(a.N, CL) + 31) & ~31;
+  const size_t smem = sizeof(float) * 3 * (size_t)ppc;
+  if (smem > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(a.B * CL));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  TPG_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  TPG_CHECK_LAUNCH("fps_reg_kernel");
+  return TPG_OK;
+}
+
+constexpr int FPS_CL = 8;         // CTAs (SMs) per cloud for N > FPS_SINGLE_MAX
+constexpr int FPS_SINGLE_MAX = 2048;
+constexpr int FPS_REG_MAX = 65536;  // 8 CTAs x 1024 threads x 8 points
+
 template <bool MODEB>
 static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
   if (a.B == 0 || a.npoint == 0) return TPG_OK;
   const int N = a.N;
-  if (N <= 8192) {
-    int T, ppt;
-    if (N <= 1024) { T = max(32, (N + 31) / 32 * 32); ppt = 1; }
-    else { T = 1024; ppt = N <= 2048 ? 2 : (N <= 4096 ? 4 : 8); }
-    switch (ppt) {
-      case 1: fps_reg_kernel<1, MODEB><<<a.B, T, 0, st>>>(a); break;
-      case 2: fps_reg_kernel<2, MODEB><<<a.B, T, 0, st>>>(a); break;
-      case 4: fps_reg_kernel<4, MODEB><<<a.B, T, 0, st>>>(a); break;
-      default: fps_reg_kernel<8, MODEB><<<a.B, T, 0, st>>>(a); break;
-    }
-    TPG_CHECK_LAUNCH("fps_reg_kernel");
-  } else {
-    TPG_REQUIRE(a.temp_ws != nullptr, TPG_EWORKSPACE, "fps: N=%d > 8192 needs a [B,N] float workspace", N);
-    fps_mem_kernel<MODEB><<<a.B, 1024, 0, st>>>(a);
-    TPG_CHECK_LAUNCH("fps_mem_kernel");
+  if (N <= FPS_SINGLE_MAX) {
+    // one CTA; measured on B200: 2 points per thread up to 1024 points, 4 up to 2048
+    if (N <= 1024) return fps_launch<2, 1, MODEB>(a, max(32, (ceil_div(N, 2) + 31) & ~31), st);
+    return fps_launch<4, 1, MODEB>(a, (ceil_div(N, 4) + 31) & ~31, st);
   }
+  if (N <= FPS_REG_MAX) {
+    const int ppc = (ceil_div(N, FPS_CL) + 31) & ~31;
+    if (ppc <= 4096) return fps_launch<4, FPS_CL, MODEB>(a, (ceil_div(ppc, 4) + 31) & ~31, st);
+    return fps_launch<8, FPS_CL, MODEB>(a, (ceil_div(ppc, 8) + 31) & ~31, st);
+  }
+  TPG_REQUIRE(a.temp_ws != nullptr, TPG_EWORKSPACE, "fps: N=%d > %d needs a [B,N] float workspace", N, FPS_REG_MAX);
+  fps_mem_kernel<MODEB><<<a.B, 1024, 0, st>>>(a);
+  TPG_CHECK_LAUNCH("fps_mem_kernel");
   return TPG_OK;
 }
 
@@ -172,7 +274,7 @@ static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
 using namespace tpg;
 
 TPG_API size_t tpg_fps_workspace_bytes(int B, int N) {
-  return N > 8192 ? sizeof(float) * (size_t)B * (size_t)N : 0;
+  return N > tpg::FPS_REG_MAX ? sizeof(float) * (size_t)B * (size_t)N : 0;
 }
 
 TPG_API int tpg_fps_f32(const float* xyz, int B, int N, int npoint, int32_t* idx, void* workspace,
@@ -181,8 +283,22 @@ TPG_API int tpg_fps_f32(const float* xyz, int B, int N, int npoint, int32_t* idx
   if (B == 0 || npoint == 0) return TPG_OK;
   TPG_REQUIRE(xyz && idx, TPG_EINVAL, "fps: null pointer");
   TPG_REQUIRE(workspace_bytes >= tpg_fps_workspace_bytes(B, N), TPG_EWORKSPACE, "fps: workspace too small");
-  FpsArgs a{xyz, B, N, 3, npoint, nullptr, idx, nullptr, reinterpret_cast<float*>(workspace)};
+  FpsArgs a{xyz, B, N, 3, npoint, nullptr, idx, nullptr, reinterpret_cast<float*>(workspace), 0};
   return fps_dispatch<false>(a, as_stream(stream));
+}
+
+// tuning hook (tools/bench_fps.py; not part of the ABI): pointnet2 mode with an explicit variant
+TPG_API int tpg_debug_fps_variant(const float* xyz, int B, int N, int npoint, int32_t* idx, int ppt, int cl,
+                                  int threads, int flags, tpg_stream_t stream) {
+  FpsArgs a{xyz, B, N, 3, npoint, nullptr, idx, nullptr, nullptr, flags};
+  cudaStream_t st = as_stream(stream);
+#define V(P, C) if (ppt == P && cl == C) return fps_launch<P, C, false>(a, threads, st)
+  V(1, 1); V(2, 1); V(4, 1); V(8, 1); V(16, 1);
+  V(1, 8); V(2, 8); V(4, 8); V(8, 8);
+  V(2, 4); V(4, 4); V(8, 4); V(4, 2); V(8, 2); V(16, 2);
+#undef V
+  set_error("fps variant ppt=%d cl=%d not built", ppt, cl);
+  return TPG_EUNSUPPORTED;
 }
 
 TPG_API int tpg_fps_start_f32(const float* pts, int B, int N, int D, int k, const int64_t* start,
@@ -193,6 +309,6 @@ TPG_API int tpg_fps_start_f32(const float* pts, int B, int N, int D, int k, cons
   if (B == 0 || k == 0) return TPG_OK;
   TPG_REQUIRE(pts && start && idx, TPG_EINVAL, "fps_start: null pointer");
   TPG_REQUIRE(workspace_bytes >= tpg_fps_workspace_bytes(B, N), TPG_EWORKSPACE, "fps_start: workspace too small");
-  FpsArgs a{pts, B, N, D, k, start, idx, dist_rows, reinterpret_cast<float*>(workspace)};
+  FpsArgs a{pts, B, N, D, k, start, idx, dist_rows, reinterpret_cast<float*>(workspace), 0};
   return fps_dispatch<true>(a, as_stream(stream));
 }

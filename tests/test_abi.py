@@ -48,8 +48,8 @@ def test_library_is_sm100a_only(built):
 
 def test_host_only_entry_points_do_not_need_a_gpu(built):
     lib = built.load()
-    assert lib.tpg_fps_workspace_bytes(4, 8192) == 0
-    assert lib.tpg_fps_workspace_bytes(4, 8193) == 4 * 8193 * 4
+    assert lib.tpg_fps_workspace_bytes(4, 65536) == 0
+    assert lib.tpg_fps_workspace_bytes(4, 65537) == 4 * 65537 * 4
     assert lib.tpg_inverse_index_workspace_bytes(2, 100, 1000) > 0
     assert lib.tpg_chamfer_bwd_workspace_bytes(2, 100, 200) > 0
     assert lib.tpg_cubic_interp_workspace_bytes(1, 100, 100) > 0

@@ -236,6 +236,10 @@ def test_ball_query_bit_exact(F, oracle, B, N, M, r, ns, kind):
 @pytest.mark.parametrize("B,N,npoint,kind", [
     (2, 1024, 128, "fluid"), (2, 2048, 512, "fluid"), (1, 8192, 1024, "fluid"), (2, 777, 100, "dup"),
     (2, 500, 500, "dummy"), (1, 343, 64, "lattice"), (1, 5000, 64, "fluid"), (1, 9000, 40, "fluid"), (3, 33, 33, "fluid"),
+    (8, 8192, 1024, "fluid"),   # BASELINE config 2: one 8-CTA cluster per cloud
+    (1, 2049, 64, "fluid"), (2, 4096, 256, "dup"), (1, 3000, 300, "dummy"), (1, 4913, 200, "lattice"),
+    (1, 65536, 24, "fluid"), (1, 70000, 12, "fluid"),   # largest cluster case / global-memory kernel
+    (2, 200, 64, "fluid"), (1, 40, 40, "dup"),
 ])
 def test_fps_pointnet2_bit_exact(F, oracle, B, N, npoint, kind):
     rng = np.random.default_rng(6)
