@@ -236,6 +236,140 @@ __global__ void csr_sort_kernel(const int32_t* __restrict__ off, const int32_t* 
   }
 }
 
+// ---- inverse index, stable single-kernel build (one CTA per cloud) ---------------------------
+// Positions are split into W contiguous chunks, one per warp.  A warp walks its chunk 32
+// positions at a time; MATCH.ANY groups the lanes that hold the same key, so one lane per key
+// updates the warp-private counter cnt[w][key] — no atomics anywhere.  After an exclusive scan
+// over (key, chunk) the second walk hands out slots in ascending position order directly
+// (rank inside a MATCH group = lanes below with the same key), so no sort pass is needed and
+// the result is deterministic.  CT = uint16 when a chunk cannot overflow it, else uint32.
+// lanes of the warp that hold the same key.  MATCH.ANY costs ~10 cycles per distinct value, so it
+// only runs when a duplicate exists among the 32 keys; duplicates are detected through a per-warp
+// tag array: every lane writes its id to tag[key] and a lane that reads back another id lost.
+__device__ __forceinline__ unsigned same_key_mask(unsigned char* tag, int key, bool valid, int lane, int N) {
+  if (valid) tag[key] = (unsigned char)lane;
+  __syncwarp();
+  const bool lost = valid && tag[key] != (unsigned char)lane;
+  if (__ballot_sync(FULL, lost) == 0u) return 1u << lane;
+  return __match_any_sync(FULL, valid ? key : N + lane);
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(1024) csr_stable_kernel(const int32_t* __restrict__ idx,
+                                                          const int64_t* __restrict__ item_len, int N, int L,
+                                                          int32_t* __restrict__ off_g, int32_t* __restrict__ items_g) {
+  extern __shared__ __align__(16) unsigned char csr_smem[];
+  __shared__ int warp_tot[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, W = T >> 5;
+  int32_t* off_s = reinterpret_cast<int32_t*>(csr_smem);                 // [N + 1]
+  CT* cnt = reinterpret_cast<CT*>(csr_smem + sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3));  // [W][N]
+  const int Lb = item_len ? (int)min((long long)item_len[b], (long long)L) : L;
+  const int32_t* ib = idx + (size_t)b * L;
+  int32_t* itb = items_g + (size_t)b * L;
+  int32_t* ob = off_g + (size_t)b * (N + 1);
+  for (int e = tid; e < W * N; e += T) cnt[e] = 0;
+  __syncthreads();
+  const int CL = ((Lb + W - 1) / W + 127) & ~127;
+  const int l_lo = warp * CL, l_hi = min(Lb, l_lo + CL);
+  CT* mycnt = cnt + (size_t)warp * N;
+  unsigned char* mytag = reinterpret_cast<unsigned char*>(cnt + (size_t)W * N) + (size_t)warp * N;  // [W][N]
+  const unsigned lt = (1u << lane) - 1u;
+  for (int l0 = l_lo; l0 < l_hi; l0 += 128) {  // 4 independent loads in flight per lane
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * 32 + lane;
+      keys[u] = l < l_hi ? __ldg(ib + l) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = keys[u];
+      const bool valid = key >= 0 && key < N;
+      const unsigned m = same_key_mask(mytag, key, valid, lane, N);
+      if (valid && (m & lt) == 0) mycnt[key] = (CT)(mycnt[key] + __popc(m));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // exclusive scan over keys of the per-key totals; cnt[w][key] becomes the prefix over chunks
+  const int KPT = (N + T - 1) / T;
+  const int k0 = tid * KPT, k1 = min(N, k0 + KPT);
+  int mine = 0;
+  for (int key = k0; key < k1; ++key) {
+    int tot = 0;
+    for (int w = 0; w < W; ++w) {
+      const int c = cnt[(size_t)w * N + key];
+      cnt[(size_t)w * N + key] = (CT)tot;
+      tot += c;
+    }
+    off_s[key] = tot;  // per-key total for now
+    mine += tot;
+  }
+  int v = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += t;
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < W ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  int run = v - mine + (warp > 0 ? warp_tot[warp - 1] : 0);  // exclusive prefix of this thread's first key
+  for (int key = k0; key < k1; ++key) {
+    const int tot = off_s[key];
+    off_s[key] = run;
+    ob[key] = run;
+    run += tot;
+  }
+  if (k1 == N && k0 < N) ob[N] = run;
+  if (N == 0 && tid == 0) ob[0] = 0;
+  __syncthreads();
+  for (int l0 = l_lo; l0 < l_hi; l0 += 128) {
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * 32 + lane;
+      keys[u] = l < l_hi ? __ldg(ib + l) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = keys[u];
+      const int l = l0 + u * 32 + lane;
+      const bool valid = key >= 0 && key < N;
+      const unsigned m = same_key_mask(mytag, key, valid, lane, N);
+      int base = 0;
+      if (valid) base = off_s[key] + (int)mycnt[key];
+      __syncwarp();
+      if (valid) {
+        itb[base + __popc(m & lt)] = l;
+        if ((m & lt) == 0) mycnt[key] = (CT)(mycnt[key] + __popc(m));
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// warps per cloud for the stable build (0 = does not fit: use the count/scan/fill/sort path)
+static int csr_stable_warps(int N, int L, bool* wide) {
+  *wide = false;
+  for (int W = 32; W >= 4; W >>= 1) {
+    const long long chunk = ((long long)(L + W - 1) / W + 127) & ~127LL;
+    const bool w32 = chunk > 65535;
+    const size_t bytes = sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3) + (size_t)W * N * (w32 ? 5 : 3);
+    if (bytes <= 220 * 1024) { *wide = w32; return W; }
+  }
+  return 0;
+}
+
 // ---- backward: per-source-point sequential sums over the CSR ---------------------
 enum { BWD_GROUP = 0, BWD_ARG = 1, BWD_SUM = 2, BWD_WEIGHTED = 3 };
 
@@ -390,11 +524,32 @@ int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, 
   TPG_REQUIRE(B >= 0 && N >= 0 && L >= 0, TPG_EINVAL, "inverse_index: negative size");
   if (B == 0) return TPG_OK;
   TPG_REQUIRE(seg_offsets, TPG_EINVAL, "inverse_index: null seg_offsets");
-  TPG_CUDA(cudaMemsetAsync(seg_offsets, 0, sizeof(int32_t) * (size_t)B * (N + 1), st));
-  if (N == 0 || L == 0) return TPG_OK;
+  if (N == 0 || L == 0) {
+    TPG_CUDA(cudaMemsetAsync(seg_offsets, 0, sizeof(int32_t) * (size_t)B * (N + 1), st));
+    return TPG_OK;
+  }
   TPG_REQUIRE(idx && seg_items, TPG_EINVAL, "inverse_index: null pointer");
   TPG_REQUIRE(workspace && workspace_bytes >= csr_workspace_bytes(B, N, L), TPG_EWORKSPACE,
               "inverse_index: workspace too small");
+  {
+    bool wide = false;
+    const int W = csr_stable_warps(N, L, &wide);
+    if (W > 0) {
+      const size_t sm = sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3) + (size_t)W * N * (wide ? 5 : 3);
+      if (wide) {
+        auto kern = csr_stable_kernel<uint32_t>;
+        if (sm > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<B, 32 * W, sm, st>>>(idx, item_len, N, L, seg_offsets, seg_items);
+      } else {
+        auto kern = csr_stable_kernel<uint16_t>;
+        if (sm > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        kern<<<B, 32 * W, sm, st>>>(idx, item_len, N, L, seg_offsets, seg_items);
+      }
+      TPG_CHECK_LAUNCH("csr_stable_kernel");
+      return TPG_OK;
+    }
+  }
+  TPG_CUDA(cudaMemsetAsync(seg_offsets, 0, sizeof(int32_t) * (size_t)B * (N + 1), st));
   int32_t* cursor = reinterpret_cast<int32_t*>(workspace);
   int32_t* tmp = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) +
                                             align_up(sizeof(int32_t) * (size_t)B * (size_t)N, 256));

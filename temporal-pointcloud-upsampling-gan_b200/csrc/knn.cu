@@ -183,8 +183,19 @@ static int launch_knn(const KnnArgs& a, cudaStream_t st) {
 int knn_dispatch(const KnnArgs& a, cudaStream_t st) {
   if (a.B == 0 || a.P1 == 0 || a.K == 0) return TPG_OK;
   const int dv = (a.D + 3) / 4;
-  if (dv == 1) return launch_knn<1, 4, 2>(a, st);
-  return launch_knn<0, 4, 2>(a, st);
+  // queries per warp: 4 amortises the candidate loads best, but the insertions of a warp's
+  // queries are serial, so small problems (few CTAs) spread over more warps instead
+  const long long queries = (long long)a.B * a.P1;
+  const int two_waves = 2 * num_sms();
+  const int qpw = queries / (KNN_WARPS * 4) >= two_waves ? 4 : (queries / (KNN_WARPS * 2) >= two_waves ? 2 : 1);
+  if (dv == 1) {
+    if (qpw == 4) return launch_knn<1, 4, 2>(a, st);
+    if (qpw == 2) return launch_knn<1, 2, 2>(a, st);
+    return launch_knn<1, 1, 2>(a, st);
+  }
+  if (qpw == 4) return launch_knn<0, 4, 2>(a, st);
+  if (qpw == 2) return launch_knn<0, 2, 2>(a, st);
+  return launch_knn<0, 1, 2>(a, st);
 }
 
 }  // namespace tpg
