@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 2
+#define TPG_ABI_VERSION 3
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -68,9 +68,10 @@ uint64_t tpg_launch_count(void);
  * p1 [B,P1,D], p2 [B,P2,D] -> dists [B,P1,K] (squared), idx [B,P1,K] int64.
  * Slots beyond min(K, lengths2[b]) and rows beyond lengths1[b] hold 0 / 0.
  * 1 <= D <= 256, 1 <= K <= 1024.
- * Feature-space searches (D a multiple of 32 up to 128, K <= 24, P2 >= 128) run on the
- * tensor cores (tcgen05, tf32 candidate search + exact fp32 re-rank; results identical
- * to the SIMT path) and need tpg_knn_workspace_bytes() bytes of workspace; for every
+ * Feature-space searches (D = 32/64/128, K <= 24, P2 >= 1024) run on the tensor cores
+ * (tcgen05, tf32 candidate search + exact fp32 re-rank) and 3-D searches over clouds of
+ * >= 2048 points (K <= 32) walk a uniform grid; both return results identical to the
+ * brute-force path and need tpg_knn_workspace_bytes() bytes of workspace; for every
  * other shape that function returns 0 and workspace may be NULL.            */
 size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K);
 int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
@@ -86,7 +87,8 @@ int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
  * The K nearest points with d2 < r*r (strict), ordered by (d2, idx); unused
  * slots hold dist -1 / idx -1.  D = 3 (2 also accepted).
  * r_per_cloud: device [B] or NULL, in which case the host scalar `r` is used.
- * workspace: tpg_frnn_workspace_bytes() bytes.                             */
+ * workspace: tpg_frnn_workspace_bytes() bytes (uniform grid: bounding box, cell
+ * size and counting sort are computed on the device, no host synchronisation). */
 size_t tpg_frnn_workspace_bytes(int B, int P1, int P2, int D, int K);
 int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                  const int64_t* lengths2, int B, int P1, int P2, int D, int K,
@@ -187,12 +189,15 @@ int tpg_three_interpolate_bwd_f32(const float* grad_out, const float* w,
  * gradients g_src [B], g_tgt [B] (d loss / d sum_src[b], d sum_tgt[b]):
  *   grad_src[i] = 2 g_src (s_i - t_nn(i)) + sum_{j: nn(j)=i} 2 g_tgt (s_i - t_j)
  * the scattered part summed in ascending j through a CSR over i_tgt.
- * workspace: tpg_chamfer_bwd_workspace_bytes().                             */
+ * workspace: tpg_chamfer_fwd_workspace_bytes() (uniform-grid search for 3-D clouds
+ * of >= 2048 points; 0 otherwise) / tpg_chamfer_bwd_workspace_bytes().       */
+size_t tpg_chamfer_fwd_workspace_bytes(int B, int P1, int P2, int D);
 int tpg_chamfer_fwd_f32(const float* src, const float* tgt,
                         const int64_t* lengths_src, const int64_t* lengths_tgt,
                         int B, int P1, int P2, int D, int directions,
                         float* d_src, int32_t* i_src, float* d_tgt,
                         int32_t* i_tgt, float* sum_src, float* sum_tgt,
+                        void* workspace, size_t workspace_bytes,
                         tpg_stream_t stream);
 size_t tpg_chamfer_bwd_workspace_bytes(int B, int P1, int P2);
 int tpg_chamfer_bwd_f32(const float* src, const float* tgt,

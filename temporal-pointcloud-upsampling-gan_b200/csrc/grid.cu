@@ -1,0 +1,470 @@
+// grid.cu — K3: uniform-grid neighbour search for 3-D clouds (kNN, fixed-radius, Chamfer NN).
+//
+// Replaces the search inside frnn.frnn_grid_points (discriminator.py:27; loss.py:256,261;
+// gcn_lib/interpolation.py:20,33), pytorch3d knn_points on positions (gcn_lib/pointnet/gcn.py:16)
+// and the two K=1 searches of chamferdist (loss.py:176-181) for clouds of >= 2048 points, where
+// brute force is bound by the fp32 pipe (67 M pairs per 8192-point cloud) and a grid makes the
+// search proportional to the neighbourhood size.  Results are IDENTICAL to the brute-force
+// kernels: the same canonical distance expression is evaluated for every visited candidate and
+// candidates are ranked by the full (d2, index) key, which is independent of traversal order.
+//
+// Build (per call, no host synchronisation, grid parameters computed on the device):
+//   setup  one CTA per cloud: bounding box -> origin / cell size / dims (<= 32 per axis), zeroes
+//          the cell counters.  Radius searches use cell = r (27-cell block covers the ball);
+//          kNN / NN use ~4 points per cell and grow the block until the K-th distance is
+//          provably covered.
+//   count  cell histogram (integer atomics: deterministic counts), scan, fill: counting sort of
+//          (x, y, z, original index) into float4 records — one coalesced 16-byte load per
+//          candidate in the search.
+// Search:
+//   K >= 2  one warp per query: the rows of the cell block are contiguous record ranges; the
+//           ranges are flattened with a warp prefix sum so all 32 lanes evaluate candidates,
+//           admission by ballot, insertion into the register-resident sorted list by key.
+//   K == 1  one thread per query (no list), used by Chamfer and K=1 radius searches.
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace tpg {
+
+constexpr int GRID_AXIS = 32;
+constexpr int GRID_CELLS = GRID_AXIS * GRID_AXIS * GRID_AXIS;  // counters allocated per cloud
+constexpr float GRID_TARGET = 4.0f;                            // points per cell for kNN / NN
+
+struct GridParams {
+  float ox, oy, oz, h, inv_h, slack;
+  int gx, gy, gz, n;
+};
+
+struct GridRef {
+  const GridParams* prm;   // [B]
+  const int* cell_start;   // [B][GRID_CELLS + 1]
+  const float4* rec;       // [B][P] (x, y, z, bits(index)) sorted by cell
+  int P;
+};
+
+__device__ __forceinline__ int cell_of(float v, float o, float inv_h, int g) {
+  const int c = (int)floorf(__fmul_rn(__fsub_rn(v, o), inv_h));
+  return min(max(c, 0), g - 1);
+}
+
+// ---- build --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) grid_setup_kernel(const float* __restrict__ p, const int64_t* __restrict__ len,
+                                                          int P, int use_radius, float r,
+                                                          const float* __restrict__ r_per_cloud,
+                                                          GridParams* __restrict__ prm, int* __restrict__ counts) {
+  __shared__ float red[6][32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = len ? min((int)len[b], P) : P;
+  const float* pb = p + (size_t)b * P * 3;
+  const float INF = __int_as_float(0x7f800000);
+  float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+  for (int i = tid; i < n; i += 1024) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = pb[(size_t)i * 3 + c];
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(FULL, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(FULL, hi[c], o));
+    }
+    if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      lo[c] = red[c][lane];
+      hi[c] = red[3 + c][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[c] = fminf(lo[c], __shfl_xor_sync(FULL, lo[c], o));
+        hi[c] = fmaxf(hi[c], __shfl_xor_sync(FULL, hi[c], o));
+      }
+    }
+    if (lane == 0) {
+      GridParams g;
+      if (n == 0) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 0.f; }
+      const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+      const float emax = fmaxf(ex, fmaxf(ey, ez));
+      const float amax = fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])),
+                               fmaxf(fmaxf(fabsf(lo[1]), fabsf(hi[1])), fmaxf(fabsf(lo[2]), fabsf(hi[2]))));
+      float h;
+      if (use_radius) {
+        const float rr = r_per_cloud ? r_per_cloud[b] : r;
+        h = rr * 1.0001f;
+      } else {
+        const float e0 = fmaxf(emax * 1e-3f, 1e-20f);
+        const float vol = fmaxf(ex, e0) * fmaxf(ey, e0) * fmaxf(ez, e0);
+        h = cbrtf(vol * GRID_TARGET / (float)max(n, 1));
+      }
+      h = fmaxf(h, emax / (float)GRID_AXIS * 1.0001f);
+      if (!(h > 0.f) || !(h < INF)) h = 1.0f;
+      g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+      g.h = h;
+      g.inv_h = 1.0f / h;
+      g.gx = min(GRID_AXIS, (int)floorf(ex * g.inv_h) + 1);
+      g.gy = min(GRID_AXIS, (int)floorf(ey * g.inv_h) + 1);
+      g.gz = min(GRID_AXIS, (int)floorf(ez * g.inv_h) + 1);
+      g.n = n;
+      // slack of every coverage bound: rounding of (v - o) * inv_h at a cell face
+      g.slack = 4e-6f * (amax + emax + h) + 1e-5f * h;
+      prm[b] = g;
+    }
+  }
+  int* cb = counts + (size_t)b * GRID_CELLS;
+  for (int i = tid; i < GRID_CELLS; i += 1024) cb[i] = 0;
+}
+
+__global__ void grid_count_kernel(const float* __restrict__ p, int B, int P, const GridParams* __restrict__ prm,
+                                  int* __restrict__ counts, int* __restrict__ cellid) {
+  const long long total = (long long)B * P;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / P), i = (int)(e - (long long)b * P);
+    const GridParams g = prm[b];
+    if (i >= g.n) continue;
+    const float* q = p + (size_t)e * 3;
+    const int c = (cell_of(q[2], g.oz, g.inv_h, g.gz) * g.gy + cell_of(q[1], g.oy, g.inv_h, g.gy)) * g.gx +
+                  cell_of(q[0], g.ox, g.inv_h, g.gx);
+    cellid[e] = c;
+    atomicAdd(counts + (size_t)b * GRID_CELLS + c, 1);
+  }
+}
+
+// exclusive scan of the GRID_CELLS counters of a cloud -> cell_start[0..GRID_CELLS]; counters become cursors
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int* __restrict__ counts, int* __restrict__ cell_start) {
+  __shared__ int wsum[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = GRID_CELLS / 1024;
+  int* cb = counts + (size_t)b * GRID_CELLS;
+  int* cs = cell_start + (size_t)b * (GRID_CELLS + 1);
+  int v[PER], s = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { v[i] = cb[tid * PER + i]; s += v[i]; }
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, w, d);
+      if (lane >= d) w += t;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    cs[tid * PER + i] = run;
+    cb[tid * PER + i] = run;
+    run += v[i];
+  }
+  if (tid == 1023) cs[GRID_CELLS] = run;
+}
+
+__global__ void grid_fill_kernel(const float* __restrict__ p, int B, int P, const GridParams* __restrict__ prm,
+                                 int* __restrict__ cursor, const int* __restrict__ cellid, float4* __restrict__ rec) {
+  const long long total = (long long)B * P;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / P), i = (int)(e - (long long)b * P);
+    if (i >= prm[b].n) continue;
+    const float* q = p + (size_t)e * 3;
+    const int pos = atomicAdd(cursor + (size_t)b * GRID_CELLS + cellid[e], 1);
+    rec[(size_t)b * P + pos] = make_float4(q[0], q[1], q[2], __int_as_float(i));
+  }
+}
+
+// ---- block of cells around a query + the distance it provably covers -----------------------------
+struct Block {
+  int x0, x1, y0, y1, z0, z1;
+  float cover;  // every point outside the block is farther than this (inf: block == grid)
+};
+
+__device__ __forceinline__ Block make_block(const GridParams& g, float qx, float qy, float qz, int R) {
+  const float INF = __int_as_float(0x7f800000);
+  const int cx = cell_of(qx, g.ox, g.inv_h, g.gx), cy = cell_of(qy, g.oy, g.inv_h, g.gy),
+            cz = cell_of(qz, g.oz, g.inv_h, g.gz);
+  Block k;
+  k.x0 = max(cx - R, 0); k.x1 = min(cx + R, g.gx - 1);
+  k.y0 = max(cy - R, 0); k.y1 = min(cy + R, g.gy - 1);
+  k.z0 = max(cz - R, 0); k.z1 = min(cz + R, g.gz - 1);
+  float c = INF;
+  // a face that is not on the grid boundary limits the covered distance
+  if (k.x0 > 0) c = fminf(c, qx - (g.ox + (float)k.x0 * g.h));
+  if (k.x1 < g.gx - 1) c = fminf(c, (g.ox + (float)(k.x1 + 1) * g.h) - qx);
+  if (k.y0 > 0) c = fminf(c, qy - (g.oy + (float)k.y0 * g.h));
+  if (k.y1 < g.gy - 1) c = fminf(c, (g.oy + (float)(k.y1 + 1) * g.h) - qy);
+  if (k.z0 > 0) c = fminf(c, qz - (g.oz + (float)k.z0 * g.h));
+  if (k.z1 < g.gz - 1) c = fminf(c, (g.oz + (float)(k.z1 + 1) * g.h) - qz);
+  k.cover = c == INF ? INF : fmaxf(c - g.slack, 0.0f) * 0.99999f;
+  return k;
+}
+
+// ---- K >= 2: one warp per query --------------------------------------------------------------------
+struct GridKnnArgs {
+  const float* p1;
+  const int64_t* len1;
+  int B, P1, K, use_radius;
+  float r;
+  const float* r_per_cloud;
+  GridRef g;
+  float* dists;
+  void* idx;
+  int out_mode;
+};
+
+__global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wq >= (long long)a.B * a.P1) return;
+  const int b = (int)(wq / a.P1), qi = (int)(wq - (long long)b * a.P1);
+  const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
+  const float INF = __int_as_float(0x7f800000);
+  const int K = a.K;
+  WarpList L;
+  L.init();
+  if (qi < n1) {
+    const GridParams g = a.g.prm[b];
+    const float* q = a.p1 + (size_t)wq * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const int* cs = a.g.cell_start + (size_t)b * (GRID_CELLS + 1);
+    const float4* rec = a.g.rec + (size_t)b * a.g.P;
+    float r2 = INF;
+    if (a.use_radius) {
+      const float rr = a.r_per_cloud ? a.r_per_cloud[b] : a.r;
+      r2 = __fmul_rn(rr, rr);
+    }
+    for (int R = 1;; R *= 2) {
+      const Block k = make_block(g, qx, qy, qz, R);
+      L.init();
+      float tau_d = INF;
+      int tau_i = 0x7fffffff;
+      const int ny = k.y1 - k.y0 + 1, nrows = ny * (k.z1 - k.z0 + 1);
+      for (int row0 = 0; row0 < nrows; row0 += 32) {
+        // rows of the block: contiguous record ranges; flatten them with a prefix sum
+        const int row = row0 + lane;
+        int start = 0, cnt = 0;
+        if (row < nrows) {
+          const int z = k.z0 + row / ny, y = k.y0 + row % ny;
+          const int c0 = (z * g.gy + y) * g.gx;
+          start = cs[c0 + k.x0];
+          cnt = cs[c0 + k.x1 + 1] - start;
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d) inc += t;
+        }
+        const int total = __shfl_sync(FULL, inc, 31);
+        const int nr = min(32, nrows - row0);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const int t = t0 + lane;
+          int rsel = 0;
+          for (int rr = 0; rr < nr - 1; ++rr) rsel += (t >= __shfl_sync(FULL, inc, rr)) ? 1 : 0;
+          const int rstart = __shfl_sync(FULL, start, rsel);
+          const int rinc = __shfl_sync(FULL, inc, rsel);
+          const int rcnt = __shfl_sync(FULL, cnt, rsel);
+          float d = INF;
+          int ci = 0x7fffffff;
+          if (t < total) {
+            const float4 v = __ldg(rec + rstart + (t - (rinc - rcnt)));
+            d = sqdist3(qx, qy, qz, v.x, v.y, v.z);
+            ci = __float_as_int(v.w);
+          }
+          unsigned m = __ballot_sync(FULL, t < total && d < r2 && (d < tau_d || (d == tau_d && ci < tau_i)));
+          while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const float dc = __shfl_sync(FULL, d, l);
+            const int ic = __shfl_sync(FULL, ci, l);
+            if (dc < tau_d || (dc == tau_d && ic < tau_i)) {
+              L.insert_key(dc, ic, lane);
+              tau_d = __shfl_sync(FULL, L.d, K - 1);
+              tau_i = __shfl_sync(FULL, L.i, K - 1);
+              if (tau_i < 0) tau_i = 0x7fffffff;
+            }
+          }
+        }
+      }
+      // radius search: the 27-cell block (cell >= r) covers the ball; kNN: stop once the K-th
+      // distance is provably inside the covered region
+      if (a.use_radius || k.cover == INF) break;
+      if (tau_d < INF && tau_d < __fmul_rn(k.cover, k.cover)) break;
+    }
+  }
+  if (qi < a.P1 && lane < K) {
+    const size_t o = (size_t)wq * K + lane;
+    const bool found = qi < n1 && L.i >= 0;
+    if (a.out_mode == OUT_THREE) {
+      a.dists[o] = found ? sqrtf(L.d) : 0.0f;
+      reinterpret_cast<int32_t*>(a.idx)[o] = found ? L.i : 0;
+    } else {
+      const float padd = a.out_mode == OUT_FRNN ? -1.0f : 0.0f;
+      const int64_t padi = a.out_mode == OUT_FRNN ? -1 : 0;
+      a.dists[o] = found ? L.d : padd;
+      reinterpret_cast<int64_t*>(a.idx)[o] = found ? (int64_t)L.i : padi;
+    }
+  }
+}
+
+// ---- K == 1: one thread per query --------------------------------------------------------------------
+struct GridNn1Args {
+  const float* q;          // [B,Pq,3]
+  const int64_t* qlen;
+  int B, Pq, use_radius;
+  float r;
+  const float* r_per_cloud;
+  GridRef g;
+  float* d_out;            // [B,Pq]
+  int32_t* i32_out;        // chamfer mode: int32 [B,Pq]
+  int64_t* i64_out;        // knn / frnn mode: int64 [B,Pq]
+  int out_mode;            // OUT_KNN / OUT_FRNN pads; i32_out != null -> chamfer (0 / 0)
+};
+
+__global__ void __launch_bounds__(128) grid_nn1_kernel(GridNn1Args a) {
+  const long long e = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (e >= (long long)a.B * a.Pq) return;
+  const int b = (int)(e / a.Pq), qi = (int)(e - (long long)b * a.Pq);
+  const int nq = a.qlen ? min((int)a.qlen[b], a.Pq) : a.Pq;
+  const float INF = __int_as_float(0x7f800000);
+  float best = INF;
+  int bi = -1;
+  if (qi < nq) {
+    const GridParams g = a.g.prm[b];
+    const float* q = a.q + (size_t)e * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const int* cs = a.g.cell_start + (size_t)b * (GRID_CELLS + 1);
+    const float4* rec = a.g.rec + (size_t)b * a.g.P;
+    float r2 = INF;
+    if (a.use_radius) {
+      const float rr = a.r_per_cloud ? a.r_per_cloud[b] : a.r;
+      r2 = __fmul_rn(rr, rr);
+    }
+    for (int R = 1;; R *= 2) {
+      const Block k = make_block(g, qx, qy, qz, R);
+      best = INF;
+      bi = -1;
+      for (int z = k.z0; z <= k.z1; ++z)
+        for (int y = k.y0; y <= k.y1; ++y) {
+          const int c0 = (z * g.gy + y) * g.gx;
+          const int s0 = cs[c0 + k.x0], s1 = cs[c0 + k.x1 + 1];
+          for (int s = s0; s < s1; ++s) {
+            const float4 v = __ldg(rec + s);
+            const float d = sqdist3(qx, qy, qz, v.x, v.y, v.z);
+            const int ci = __float_as_int(v.w);
+            if (d < r2 && (d < best || (d == best && ci < bi))) { best = d; bi = ci; }
+          }
+        }
+      if (a.use_radius || k.cover == INF) break;
+      if (bi >= 0 && best < __fmul_rn(k.cover, k.cover)) break;
+    }
+  }
+  const bool found = qi < nq && bi >= 0;
+  if (a.i32_out) {
+    a.d_out[e] = found ? best : 0.0f;
+    a.i32_out[e] = found ? bi : 0;
+  } else {
+    const float padd = a.out_mode == OUT_FRNN ? -1.0f : 0.0f;
+    const int64_t padi = a.out_mode == OUT_FRNN ? -1 : 0;
+    a.d_out[e] = found ? best : padd;
+    a.i64_out[e] = found ? (int64_t)bi : padi;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+struct GridWs {
+  GridParams* prm;
+  int* counts;
+  int* cell_start;
+  int* cellid;
+  float4* rec;
+  size_t total;
+};
+
+static GridWs grid_carve(void* base, int B, int P) {
+  GridWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t o = 0;
+  w.prm = reinterpret_cast<GridParams*>(p + o);  o += align_up(sizeof(GridParams) * (size_t)B, 256);
+  w.counts = reinterpret_cast<int*>(p + o);      o += align_up(sizeof(int) * (size_t)B * GRID_CELLS, 256);
+  w.cell_start = reinterpret_cast<int*>(p + o);  o += align_up(sizeof(int) * (size_t)B * (GRID_CELLS + 1), 256);
+  w.cellid = reinterpret_cast<int*>(p + o);      o += align_up(sizeof(int) * (size_t)B * P, 256);
+  w.rec = reinterpret_cast<float4*>(p + o);      o += align_up(sizeof(float4) * (size_t)B * P, 256);
+  w.total = o;
+  return w;
+}
+
+size_t grid_workspace_bytes(int B, int P) { return grid_carve(nullptr, B, P).total; }
+
+bool grid_eligible(int D, int P2, int K) { return D == 3 && P2 >= 2048 && K >= 1 && K <= 32; }
+
+// builds the grid of cloud set p [B,P,3] inside `workspace` and returns a reference to it
+static int grid_build(const float* p, const int64_t* len, int B, int P, int use_radius, float r,
+                      const float* r_per_cloud, void* workspace, GridRef* out, cudaStream_t st) {
+  GridWs w = grid_carve(workspace, B, P);
+  grid_setup_kernel<<<B, 1024, 0, st>>>(p, len, P, use_radius, r, r_per_cloud, w.prm, w.counts);
+  TPG_CHECK_LAUNCH("grid_setup_kernel");
+  const long long total = (long long)B * P;
+  const unsigned blocks = (unsigned)min((total + 255) / 256, (long long)num_sms() * 16);
+  grid_count_kernel<<<blocks, 256, 0, st>>>(p, B, P, w.prm, w.counts, w.cellid);
+  TPG_CHECK_LAUNCH("grid_count_kernel");
+  grid_scan_kernel<<<B, 1024, 0, st>>>(w.counts, w.cell_start);
+  TPG_CHECK_LAUNCH("grid_scan_kernel");
+  grid_fill_kernel<<<blocks, 256, 0, st>>>(p, B, P, w.prm, w.counts, w.cellid, w.rec);
+  TPG_CHECK_LAUNCH("grid_fill_kernel");
+  out->prm = w.prm;
+  out->cell_start = w.cell_start;
+  out->rec = w.rec;
+  out->P = P;
+  return TPG_OK;
+}
+
+int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TPG_REQUIRE(workspace && workspace_bytes >= grid_workspace_bytes(a.B, a.P2), TPG_EWORKSPACE,
+              "grid search: workspace too small (need %zu bytes)", grid_workspace_bytes(a.B, a.P2));
+  TPG_REQUIRE(a.B <= 65535, TPG_EUNSUPPORTED, "grid search: B > 65535");
+  GridRef g;
+  int rc = grid_build(a.p2, a.len2, a.B, a.P2, a.use_radius, a.r, a.r_per_cloud, workspace, &g, st);
+  if (rc) return rc;
+  const long long queries = (long long)a.B * a.P1;
+  if (a.K == 1 && a.out_mode != OUT_THREE) {
+    GridNn1Args n{a.p1, a.len1, a.B, a.P1, a.use_radius, a.r, a.r_per_cloud, g, a.dists, nullptr,
+                  reinterpret_cast<int64_t*>(a.idx), a.out_mode};
+    grid_nn1_kernel<<<(unsigned)((queries + 127) / 128), 128, 0, st>>>(n);
+    TPG_CHECK_LAUNCH("grid_nn1_kernel");
+    return TPG_OK;
+  }
+  GridKnnArgs k{a.p1, a.len1, a.B, a.P1, a.K, a.use_radius, a.r, a.r_per_cloud, g, a.dists, a.idx, a.out_mode};
+  grid_knn_kernel<<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
+  TPG_CHECK_LAUNCH("grid_knn_kernel");
+  return TPG_OK;
+}
+
+int grid_nn1_chamfer(const float* q, const float* c, const int64_t* ql, const int64_t* cl, int B, int Pq, int Pc,
+                     float* d_out, int32_t* i_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TPG_REQUIRE(workspace && workspace_bytes >= grid_workspace_bytes(B, Pc), TPG_EWORKSPACE,
+              "chamfer grid search: workspace too small");
+  GridRef g;
+  int rc = grid_build(c, cl, B, Pc, 0, 0.f, nullptr, workspace, &g, st);
+  if (rc) return rc;
+  const long long queries = (long long)B * Pq;
+  GridNn1Args n{q, ql, B, Pq, 0, 0.f, nullptr, g, d_out, i_out, nullptr, OUT_KNN};
+  grid_nn1_kernel<<<(unsigned)((queries + 127) / 128), 128, 0, st>>>(n);
+  TPG_CHECK_LAUNCH("grid_nn1_kernel");
+  return TPG_OK;
+}
+
+}  // namespace tpg

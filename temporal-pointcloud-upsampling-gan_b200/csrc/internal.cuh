@@ -28,6 +28,13 @@ bool knn_feat_eligible(const KnnArgs& a);
 size_t knn_feat_workspace_bytes(int B, int P1, int P2);
 int knn_feat_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// grid.cu — uniform-grid search for 3-D clouds of >= 2048 points, K <= 32 (results identical to knn_dispatch)
+bool grid_eligible(int D, int P2, int K);
+size_t grid_workspace_bytes(int B, int P);
+int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int grid_nn1_chamfer(const float* q, const float* c, const int64_t* ql, const int64_t* cl, int B, int Pq, int Pc,
+                     float* d_out, int32_t* i_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 // group.cu — inverse index (CSR) of an int32 index tensor idx [B,L] with keys in
 // [0,N): seg_offsets [B,N+1], seg_items [B,L] (ascending positions per key).
 // item_len (device [B] int64 or null) limits the positions of cloud b to [0,len).

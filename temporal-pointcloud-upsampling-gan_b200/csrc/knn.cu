@@ -205,7 +205,8 @@ using namespace tpg;
 TPG_API size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K) {
   KnnArgs a{reinterpret_cast<const float*>(16), reinterpret_cast<const float*>(16), nullptr, nullptr, B, P1, P2, D, K,
             0.f, nullptr, 0, nullptr, nullptr, OUT_KNN};
-  return knn_feat_eligible(a) ? knn_feat_workspace_bytes(B, P1, P2) : 0;
+  if (knn_feat_eligible(a)) return knn_feat_workspace_bytes(B, P1, P2);
+  return grid_eligible(D, P2, K) ? grid_workspace_bytes(B, P2) : 0;
 }
 
 TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
@@ -220,19 +221,19 @@ TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths
   TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "knn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, 0.f, nullptr, 0, dists, idx, OUT_KNN};
   if (P2 > 0 && knn_feat_eligible(a)) return knn_feat_dispatch(a, workspace, workspace_bytes, as_stream(stream));
+  if (grid_eligible(D, P2, K)) return grid_knn_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   return knn_dispatch(a, as_stream(stream));
 }
 
 TPG_API size_t tpg_frnn_workspace_bytes(int B, int P1, int P2, int D, int K) {
-  (void)B; (void)P1; (void)P2; (void)D; (void)K;
-  return 256;  // brute-force path needs none; reserved for the uniform-grid path
+  (void)P1;
+  return grid_eligible(D, P2, K) ? grid_workspace_bytes(B, P2) : 256;
 }
 
 TPG_API int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                          const int64_t* lengths2, int B, int P1, int P2, int D, int K, float r,
                          const float* r_per_cloud, float* dists, int64_t* idx, void* workspace,
                          size_t workspace_bytes, tpg_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0, TPG_EINVAL, "frnn: negative size");
   TPG_REQUIRE(D == 2 || D == 3, TPG_EUNSUPPORTED, "frnn: D=%d (only 2 or 3, like upstream)", D);
   TPG_REQUIRE(K >= 1 && K <= 1024, TPG_EUNSUPPORTED, "frnn: K=%d outside [1,1024]", K);
@@ -240,6 +241,7 @@ TPG_API int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* length
   if (B == 0 || P1 == 0) return TPG_OK;
   TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "frnn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, r, r_per_cloud, 1, dists, idx, OUT_FRNN};
+  if (grid_eligible(D, P2, K)) return grid_knn_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   return knn_dispatch(a, as_stream(stream));
 }
 

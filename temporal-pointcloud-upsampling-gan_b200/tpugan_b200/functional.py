@@ -300,8 +300,11 @@ def chamfer_fwd(src, tgt, directions: int, lengths_src=None, lengths_tgt=None):
     i_t = torch.empty((B, P2), dtype=torch.int32, device=dev) if r else None
     s_t = torch.empty((B,), dtype=torch.float32, device=dev) if r else None
     with torch.cuda.device(dev):
+        nbytes = _lib.load().tpg_chamfer_fwd_workspace_bytes(B, P1, P2, D)  # > 0: uniform-grid search
+        ws = _ws(nbytes, dev) if nbytes else None
         _lib.call("tpg_chamfer_fwd_f32", _ptr(src), _ptr(tgt), _ptr(lengths_src), _ptr(lengths_tgt), B, P1, P2, D,
-                  int(directions), _ptr(d_s), _ptr(i_s), _ptr(d_t), _ptr(i_t), _ptr(s_s), _ptr(s_t), _stream())
+                  int(directions), _ptr(d_s), _ptr(i_s), _ptr(d_t), _ptr(i_t), _ptr(s_s), _ptr(s_t), _ptr(ws), nbytes,
+                  _stream())
     return dict(d_src=d_s, i_src=i_s, sum_src=s_s, d_tgt=d_t, i_tgt=i_t, sum_tgt=s_t)
 
 

@@ -87,6 +87,71 @@ def test_knn_bit_exact(F, oracle, B, P1, P2, D, K, kind):
     np.testing.assert_array_equal(gd.cpu().numpy(), od)
 
 
+# 3-D searches over >= 2048 candidates take the uniform-grid path (csrc/grid.cu): identical results
+KNN_GRID_CASES = [
+    (2, 3000, 5000, 16, "fluid"), (1, 8192, 8192, 20, "fluid"), (2, 4096, 4096, 32, "dup"), (1, 4096, 4096, 8, "dummy"),
+    (1, 4913, 4913, 9, "lattice"), (2, 500, 2048, 1, "fluid"), (1, 700, 2500, 12, "outside"), (1, 300, 2048, 5, "flat"),
+    (1, 64, 3000, 3, "same"),
+]
+
+
+def make_grid_pair(rng, B, P1, P2, kind):
+    if kind == "outside":   # queries far outside the candidates' bounding box
+        b = synth.fluid_cloud(rng, B, P2)
+        a = (synth.fluid_cloud(rng, B, P1) * 3.0 + 0.4).astype(np.float32)
+        return a, b
+    if kind == "flat":      # degenerate extent along z
+        b = synth.fluid_cloud(rng, B, P2)
+        b[..., 2] = 0.125
+        a = synth.fluid_cloud(rng, B, P1)
+        return a, b
+    if kind == "same":      # every candidate at the same place
+        b = np.full((B, P2, 3), 0.25, np.float32)
+        return synth.fluid_cloud(rng, B, P1), b
+    return make_pair(rng, B, P1, P2, 3, kind)
+
+
+@pytest.mark.parametrize("B,P1,P2,K,kind", KNN_GRID_CASES)
+def test_knn_grid_path_bit_exact(F, oracle, B, P1, P2, K, kind):
+    rng = np.random.default_rng(K * 7 + P2)
+    a, b = make_grid_pair(rng, B, P1, P2, kind)
+    P1, P2 = a.shape[1], b.shape[1]
+    from tpugan_b200 import _lib
+
+    assert _lib.load().tpg_knn_workspace_bytes(B, P1, P2, 3, K) > 0
+    od, oi = oracle.knn(a, b, K)
+    gd, gi = F.knn(cu(a), cu(b), K)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("B,P1,P2,K,r,kind", [
+    (2, 2048, 8192, 1, 1.9 * 0.025, "fluid"), (1, 8192, 8192, 16, 1.4 * 0.025, "fluid"), (1, 3000, 3000, 32, 0.16, "fluid"),
+    (1, 4913, 4913, 8, 0.025, "lattice"), (1, 4913, 4913, 8, 0.025 * 1.0001, "lattice"), (1, 2048, 2048, 8, 0.03, "dummy"),
+    (1, 600, 2500, 6, 0.05, "outside"), (1, 400, 2048, 4, 5.0, "fluid"),
+])
+def test_frnn_grid_path_bit_exact(F, oracle, B, P1, P2, K, r, kind):
+    rng = np.random.default_rng(K * 13 + P2)
+    a, b = make_grid_pair(rng, B, P1, P2, kind)
+    od, oi = oracle.frnn(a, b, K, r)
+    gd, gi = F.frnn(cu(a), cu(b), K, r)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
+def test_frnn_grid_per_cloud_radius_and_lengths(F, oracle):
+    rng = np.random.default_rng(31)
+    a = synth.fluid_cloud(rng, 3, 900)
+    b = synth.fluid_cloud(rng, 3, 2600)
+    r = np.array([0.03, 0.05, 0.02], np.float32)
+    l1 = np.array([900, 10, 0], np.int64)
+    l2 = np.array([2600, 2100, 3], np.int64)
+    od, oi = oracle.frnn(a, b, 8, r, l1, l2)
+    gd, gi = F.frnn(cu(a), cu(b), 8, cu(r), cu(l1), cu(l2))
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+
+
 # feature-space searches that take the tcgen05 path (csrc/knn_feat.cu): results must be
 # IDENTICAL to the oracle (indices and canonical distances), including the cases that
 # overflow the tf32 margin and are recomputed by the exact fallback.
@@ -394,6 +459,7 @@ def test_three_nn_and_interpolate(F, oracle, B, n, m):
 
 # ----------------------------------------------------------------------------- Chamfer
 @pytest.mark.parametrize("B,P1,P2,directions", [(2, 512, 2048, 3), (2, 2048, 512, 3), (3, 100, 100, 1),
+                                                 (2, 8192, 8192, 3), (1, 2048, 8192, 3), (1, 5000, 3000, 2),
                                                (3, 100, 333, 2), (1, 8192, 8192, 3), (2, 300, 300, 3)])
 def test_chamfer_fwd_bwd(F, oracle, B, P1, P2, directions):
     rng = np.random.default_rng(14)
