@@ -179,8 +179,7 @@ static int launch_nn1(const float* q, const float* c, const int64_t* ql, const i
 using namespace tpg;
 
 TPG_API size_t tpg_chamfer_fwd_workspace_bytes(int B, int P1, int P2, int D) {
-  const int pmax = P1 > P2 ? P1 : P2;
-  return grid_eligible(D, pmax, 1) ? grid_workspace_bytes(B, pmax) : 0;
+  return D == 3 ? grid_chamfer_workspace_bytes(B, P1, P2) : 0;
 }
 
 TPG_API int tpg_chamfer_fwd_f32(const float* src, const float* tgt, const int64_t* lengths_src,
@@ -193,20 +192,24 @@ TPG_API int tpg_chamfer_fwd_f32(const float* src, const float* tgt, const int64_
   TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "chamfer_fwd: B > 65535");
   if (B == 0) return TPG_OK;
   cudaStream_t st = as_stream(stream);
+  if (directions & TPG_CHAMFER_FWD) TPG_REQUIRE(d_src && i_src && sum_src, TPG_EINVAL, "chamfer_fwd: null forward outputs");
+  if (directions & TPG_CHAMFER_REV) TPG_REQUIRE(d_tgt && i_tgt && sum_tgt, TPG_EINVAL, "chamfer_fwd: null reverse outputs");
+  int handled = 0;
+  if (D == 3) {
+    int rc = grid_chamfer_nn(src, tgt, lengths_src, lengths_tgt, B, P1, P2, directions, d_src, i_src, d_tgt, i_tgt,
+                             workspace, workspace_bytes, &handled, st);
+    if (rc) return rc;
+  }
   if (directions & TPG_CHAMFER_FWD) {
-    TPG_REQUIRE(d_src && i_src && sum_src, TPG_EINVAL, "chamfer_fwd: null forward outputs");
-    int rc = (grid_eligible(D, P2, 1) && P1 > 0)
-                 ? grid_nn1_chamfer(src, tgt, lengths_src, lengths_tgt, B, P1, P2, d_src, i_src, workspace, workspace_bytes, st)
-                 : launch_nn1(src, tgt, lengths_src, lengths_tgt, B, P1, P2, D, d_src, i_src, st);
+    int rc = (handled & TPG_CHAMFER_FWD) ? TPG_OK
+                                         : launch_nn1(src, tgt, lengths_src, lengths_tgt, B, P1, P2, D, d_src, i_src, st);
     if (rc) return rc;
     cloud_sum_kernel<<<B, 1024, 0, st>>>(d_src, lengths_src, P1, sum_src);
     TPG_CHECK_LAUNCH("cloud_sum_kernel");
   }
   if (directions & TPG_CHAMFER_REV) {
-    TPG_REQUIRE(d_tgt && i_tgt && sum_tgt, TPG_EINVAL, "chamfer_fwd: null reverse outputs");
-    int rc = (grid_eligible(D, P1, 1) && P2 > 0)
-                 ? grid_nn1_chamfer(tgt, src, lengths_tgt, lengths_src, B, P2, P1, d_tgt, i_tgt, workspace, workspace_bytes, st)
-                 : launch_nn1(tgt, src, lengths_tgt, lengths_src, B, P2, P1, D, d_tgt, i_tgt, st);
+    int rc = (handled & TPG_CHAMFER_REV) ? TPG_OK
+                                         : launch_nn1(tgt, src, lengths_tgt, lengths_src, B, P2, P1, D, d_tgt, i_tgt, st);
     if (rc) return rc;
     cloud_sum_kernel<<<B, 1024, 0, st>>>(d_tgt, lengths_tgt, P2, sum_tgt);
     TPG_CHECK_LAUNCH("cloud_sum_kernel");

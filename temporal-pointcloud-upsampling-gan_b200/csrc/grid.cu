@@ -28,7 +28,6 @@ namespace tpg {
 
 constexpr int GRID_AXIS = 32;
 constexpr int GRID_CELLS = GRID_AXIS * GRID_AXIS * GRID_AXIS;  // counters allocated per cloud
-constexpr float GRID_TARGET = 4.0f;                            // points per cell for kNN / NN
 
 struct GridParams {
   float ox, oy, oz, h, inv_h, slack;
@@ -49,10 +48,11 @@ __device__ __forceinline__ int cell_of(float v, float o, float inv_h, int g) {
 
 // ---- build --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) grid_setup_kernel(const float* __restrict__ p, const int64_t* __restrict__ len,
-                                                          int P, int use_radius, float r,
+                                                          int P, int K, int use_radius, float r,
                                                           const float* __restrict__ r_per_cloud,
                                                           GridParams* __restrict__ prm, int* __restrict__ counts) {
   __shared__ float red[6][32];
+  __shared__ int ncell_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = len ? min((int)len[b], P) : P;
   const float* pb = p + (size_t)b * P * 3;
@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(1024) grid_setup_kernel(const float* __restric
       } else {
         const float e0 = fmaxf(emax * 1e-3f, 1e-20f);
         const float vol = fmaxf(ex, e0) * fmaxf(ey, e0) * fmaxf(ez, e0);
-        h = cbrtf(vol * GRID_TARGET / (float)max(n, 1));
+        // the K-th neighbour sits at ~ (3K / (4 pi density))^(1/3); cells 1.3x that wide make the
+        // 27-cell block cover it almost always: 0.55 K points per cell (at least 2)
+        const float target = fmaxf(2.0f, 0.55f * (float)K);
+        h = cbrtf(vol * target / (float)max(n, 1));
       }
       h = fmaxf(h, emax / (float)GRID_AXIS * 1.0001f);
       if (!(h > 0.f) || !(h < INF)) h = 1.0f;
@@ -115,10 +118,13 @@ __global__ void __launch_bounds__(1024) grid_setup_kernel(const float* __restric
       // slack of every coverage bound: rounding of (v - o) * inv_h at a cell face
       g.slack = 4e-6f * (amax + emax + h) + 1e-5f * h;
       prm[b] = g;
+      ncell_s = g.gx * g.gy * g.gz;
     }
   }
+  __syncthreads();
   int* cb = counts + (size_t)b * GRID_CELLS;
-  for (int i = tid; i < GRID_CELLS; i += 1024) cb[i] = 0;
+  const int ncell = ncell_s;
+  for (int i = tid; i < ncell; i += 1024) cb[i] = 0;
 }
 
 __global__ void grid_count_kernel(const float* __restrict__ p, int B, int P, const GridParams* __restrict__ prm,
@@ -136,42 +142,45 @@ __global__ void grid_count_kernel(const float* __restrict__ p, int B, int P, con
   }
 }
 
-// exclusive scan of the GRID_CELLS counters of a cloud -> cell_start[0..GRID_CELLS]; counters become cursors
-__global__ void __launch_bounds__(1024) grid_scan_kernel(int* __restrict__ counts, int* __restrict__ cell_start) {
+// exclusive scan of the used cell counters of a cloud -> cell_start[0..ncell]; counters become cursors
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const GridParams* __restrict__ prm, int* __restrict__ counts,
+                                                         int* __restrict__ cell_start) {
   __shared__ int wsum[32];
+  __shared__ int carry_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int PER = GRID_CELLS / 1024;
+  const int ncell = prm[b].gx * prm[b].gy * prm[b].gz;
   int* cb = counts + (size_t)b * GRID_CELLS;
   int* cs = cell_start + (size_t)b * (GRID_CELLS + 1);
-  int v[PER], s = 0;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) { v[i] = cb[tid * PER + i]; s += v[i]; }
-  int inc = s;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int t = __shfl_up_sync(FULL, inc, d);
-    if (lane >= d) inc += t;
-  }
-  if (lane == 31) wsum[warp] = inc;
+  if (tid == 0) carry_s = 0;
   __syncthreads();
-  if (warp == 0) {
-    int w = wsum[lane];
+  for (int base = 0; base < ncell; base += 1024) {
+    const int e = base + tid;
+    const int v = e < ncell ? cb[e] : 0;
+    int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(FULL, w, d);
-      if (lane >= d) w += t;
+      const int t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += t;
     }
-    wsum[lane] = w;
-  }
-  __syncthreads();
-  int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    cs[tid * PER + i] = run;
-    cb[tid * PER + i] = run;
-    run += v[i];
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, w, d);
+        if (lane >= d) w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int excl = carry_s + (warp > 0 ? wsum[warp - 1] : 0) + inc - v;
+    if (e < ncell) { cs[e] = excl; cb[e] = excl; }
+    __syncthreads();
+    if (tid == 1023) carry_s = excl + v;
+    __syncthreads();
   }
-  if (tid == 1023) cs[GRID_CELLS] = run;
+  if (tid == 0) cs[ncell] = carry_s;
 }
 
 __global__ void grid_fill_kernel(const float* __restrict__ p, int B, int P, const GridParams* __restrict__ prm,
@@ -215,6 +224,7 @@ __device__ __forceinline__ Block make_block(const GridParams& g, float qx, float
 // ---- K >= 2: one warp per query --------------------------------------------------------------------
 struct GridKnnArgs {
   const float* p1;
+  const float4* qrec;  // != null: queries are visited in the cell order of their own grid (self search)
   const int64_t* len1;
   int B, P1, K, use_radius;
   float r;
@@ -227,18 +237,29 @@ struct GridKnnArgs {
 
 __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
   const int lane = threadIdx.x & 31;
-  const long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (wq >= (long long)a.B * a.P1) return;
-  const int b = (int)(wq / a.P1), qi = (int)(wq - (long long)b * a.P1);
+  const int b = (int)(wq / a.P1);
+  int qi = (int)(wq - (long long)b * a.P1);
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
   const float INF = __int_as_float(0x7f800000);
   const int K = a.K;
   WarpList L;
   L.init();
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (qi < n1) {
+    if (a.qrec) {  // neighbouring warps handle neighbouring points: shared candidate cells, L1/L2 hits
+      const float4 v = __ldg(a.qrec + (size_t)b * a.P1 + qi);
+      qx = v.x; qy = v.y; qz = v.z;
+      qi = __float_as_int(v.w);
+      wq = (long long)b * a.P1 + qi;
+    } else {
+      const float* q = a.p1 + (size_t)wq * 3;
+      qx = q[0]; qy = q[1]; qz = q[2];
+    }
+  }
   if (qi < n1) {
     const GridParams g = a.g.prm[b];
-    const float* q = a.p1 + (size_t)wq * 3;
-    const float qx = q[0], qy = q[1], qz = q[2];
     const int* cs = a.g.cell_start + (size_t)b * (GRID_CELLS + 1);
     const float4* rec = a.g.rec + (size_t)b * a.g.P;
     float r2 = INF;
@@ -323,6 +344,7 @@ __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
 // ---- K == 1: one thread per query --------------------------------------------------------------------
 struct GridNn1Args {
   const float* q;          // [B,Pq,3]
+  const float4* qrec;      // != null: queries visited in the cell order of their own grid
   const int64_t* qlen;
   int B, Pq, use_radius;
   float r;
@@ -335,17 +357,28 @@ struct GridNn1Args {
 };
 
 __global__ void __launch_bounds__(128) grid_nn1_kernel(GridNn1Args a) {
-  const long long e = (long long)blockIdx.x * 128 + threadIdx.x;
+  long long e = (long long)blockIdx.x * 128 + threadIdx.x;
   if (e >= (long long)a.B * a.Pq) return;
-  const int b = (int)(e / a.Pq), qi = (int)(e - (long long)b * a.Pq);
+  const int b = (int)(e / a.Pq);
+  int qi = (int)(e - (long long)b * a.Pq);
   const int nq = a.qlen ? min((int)a.qlen[b], a.Pq) : a.Pq;
   const float INF = __int_as_float(0x7f800000);
   float best = INF;
   int bi = -1;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (qi < nq) {
+    if (a.qrec) {
+      const float4 v = __ldg(a.qrec + (size_t)b * a.Pq + qi);
+      qx = v.x; qy = v.y; qz = v.z;
+      qi = __float_as_int(v.w);
+      e = (long long)b * a.Pq + qi;
+    } else {
+      const float* q = a.q + (size_t)e * 3;
+      qx = q[0]; qy = q[1]; qz = q[2];
+    }
+  }
   if (qi < nq) {
     const GridParams g = a.g.prm[b];
-    const float* q = a.q + (size_t)e * 3;
-    const float qx = q[0], qy = q[1], qz = q[2];
     const int* cs = a.g.cell_start + (size_t)b * (GRID_CELLS + 1);
     const float4* rec = a.g.rec + (size_t)b * a.g.P;
     float r2 = INF;
@@ -412,16 +445,16 @@ size_t grid_workspace_bytes(int B, int P) { return grid_carve(nullptr, B, P).tot
 bool grid_eligible(int D, int P2, int K) { return D == 3 && P2 >= 2048 && K >= 1 && K <= 32; }
 
 // builds the grid of cloud set p [B,P,3] inside `workspace` and returns a reference to it
-static int grid_build(const float* p, const int64_t* len, int B, int P, int use_radius, float r,
+static int grid_build(const float* p, const int64_t* len, int B, int P, int K, int use_radius, float r,
                       const float* r_per_cloud, void* workspace, GridRef* out, cudaStream_t st) {
   GridWs w = grid_carve(workspace, B, P);
-  grid_setup_kernel<<<B, 1024, 0, st>>>(p, len, P, use_radius, r, r_per_cloud, w.prm, w.counts);
+  grid_setup_kernel<<<B, 1024, 0, st>>>(p, len, P, K, use_radius, r, r_per_cloud, w.prm, w.counts);
   TPG_CHECK_LAUNCH("grid_setup_kernel");
   const long long total = (long long)B * P;
   const unsigned blocks = (unsigned)min((total + 255) / 256, (long long)num_sms() * 16);
   grid_count_kernel<<<blocks, 256, 0, st>>>(p, B, P, w.prm, w.counts, w.cellid);
   TPG_CHECK_LAUNCH("grid_count_kernel");
-  grid_scan_kernel<<<B, 1024, 0, st>>>(w.counts, w.cell_start);
+  grid_scan_kernel<<<B, 1024, 0, st>>>(w.prm, w.counts, w.cell_start);
   TPG_CHECK_LAUNCH("grid_scan_kernel");
   grid_fill_kernel<<<blocks, 256, 0, st>>>(p, B, P, w.prm, w.counts, w.cellid, w.rec);
   TPG_CHECK_LAUNCH("grid_fill_kernel");
@@ -437,33 +470,59 @@ int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes,
               "grid search: workspace too small (need %zu bytes)", grid_workspace_bytes(a.B, a.P2));
   TPG_REQUIRE(a.B <= 65535, TPG_EUNSUPPORTED, "grid search: B > 65535");
   GridRef g;
-  int rc = grid_build(a.p2, a.len2, a.B, a.P2, a.use_radius, a.r, a.r_per_cloud, workspace, &g, st);
+  int rc = grid_build(a.p2, a.len2, a.B, a.P2, a.K, a.use_radius, a.r, a.r_per_cloud, workspace, &g, st);
   if (rc) return rc;
   const long long queries = (long long)a.B * a.P1;
+  // self search: visit the queries in the cell order of the grid that was just built
+  const float4* qrec = (a.p1 == a.p2 && a.P1 == a.P2 && a.len1 == a.len2) ? g.rec : nullptr;
   if (a.K == 1 && a.out_mode != OUT_THREE) {
-    GridNn1Args n{a.p1, a.len1, a.B, a.P1, a.use_radius, a.r, a.r_per_cloud, g, a.dists, nullptr,
+    GridNn1Args n{a.p1, qrec, a.len1, a.B, a.P1, a.use_radius, a.r, a.r_per_cloud, g, a.dists, nullptr,
                   reinterpret_cast<int64_t*>(a.idx), a.out_mode};
     grid_nn1_kernel<<<(unsigned)((queries + 127) / 128), 128, 0, st>>>(n);
     TPG_CHECK_LAUNCH("grid_nn1_kernel");
     return TPG_OK;
   }
-  GridKnnArgs k{a.p1, a.len1, a.B, a.P1, a.K, a.use_radius, a.r, a.r_per_cloud, g, a.dists, a.idx, a.out_mode};
+  GridKnnArgs k{a.p1, qrec, a.len1, a.B, a.P1, a.K, a.use_radius, a.r, a.r_per_cloud, g, a.dists, a.idx, a.out_mode};
   grid_knn_kernel<<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
   TPG_CHECK_LAUNCH("grid_knn_kernel");
   return TPG_OK;
 }
 
-int grid_nn1_chamfer(const float* q, const float* c, const int64_t* ql, const int64_t* cl, int B, int Pq, int Pc,
-                     float* d_out, int32_t* i_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  TPG_REQUIRE(workspace && workspace_bytes >= grid_workspace_bytes(B, Pc), TPG_EWORKSPACE,
+// Chamfer: both directions.  Clouds of >= 2048 points get a grid; a direction whose candidate cloud
+// has a grid searches it, visiting its queries in the cell order of the query cloud's own grid when
+// that exists.  Returns which directions were handled (bit 0: src->tgt, bit 1: tgt->src).
+size_t grid_chamfer_workspace_bytes(int B, int P1, int P2) {
+  return (grid_eligible(3, P1, 1) ? grid_workspace_bytes(B, P1) : 0) + (grid_eligible(3, P2, 1) ? grid_workspace_bytes(B, P2) : 0);
+}
+
+int grid_chamfer_nn(const float* src, const float* tgt, const int64_t* ls, const int64_t* lt, int B, int P1, int P2,
+                    int directions, float* d_src, int32_t* i_src, float* d_tgt, int32_t* i_tgt, void* workspace,
+                    size_t workspace_bytes, int* handled, cudaStream_t st) {
+  *handled = 0;
+  const bool gs = grid_eligible(3, P1, 1), gt = grid_eligible(3, P2, 1);
+  if (!gs && !gt) return TPG_OK;
+  TPG_REQUIRE(workspace && workspace_bytes >= grid_chamfer_workspace_bytes(B, P1, P2), TPG_EWORKSPACE,
               "chamfer grid search: workspace too small");
-  GridRef g;
-  int rc = grid_build(c, cl, B, Pc, 0, 0.f, nullptr, workspace, &g, st);
-  if (rc) return rc;
-  const long long queries = (long long)B * Pq;
-  GridNn1Args n{q, ql, B, Pq, 0, 0.f, nullptr, g, d_out, i_out, nullptr, OUT_KNN};
-  grid_nn1_kernel<<<(unsigned)((queries + 127) / 128), 128, 0, st>>>(n);
-  TPG_CHECK_LAUNCH("grid_nn1_kernel");
+  char* ws = reinterpret_cast<char*>(workspace);
+  GridRef rs{}, rt{};
+  int rc;
+  if (gs) {
+    if ((rc = grid_build(src, ls, B, P1, 1, 0, 0.f, nullptr, ws, &rs, st))) return rc;
+    ws += grid_workspace_bytes(B, P1);
+  }
+  if (gt && (rc = grid_build(tgt, lt, B, P2, 1, 0, 0.f, nullptr, ws, &rt, st))) return rc;
+  if ((directions & TPG_CHAMFER_FWD) && gt && P1 > 0) {
+    GridNn1Args n{src, gs ? rs.rec : nullptr, ls, B, P1, 0, 0.f, nullptr, rt, d_src, i_src, nullptr, OUT_KNN};
+    grid_nn1_kernel<<<(unsigned)(((long long)B * P1 + 127) / 128), 128, 0, st>>>(n);
+    TPG_CHECK_LAUNCH("grid_nn1_kernel");
+    *handled |= TPG_CHAMFER_FWD;
+  }
+  if ((directions & TPG_CHAMFER_REV) && gs && P2 > 0) {
+    GridNn1Args n{tgt, gt ? rt.rec : nullptr, lt, B, P2, 0, 0.f, nullptr, rs, d_tgt, i_tgt, nullptr, OUT_KNN};
+    grid_nn1_kernel<<<(unsigned)(((long long)B * P2 + 127) / 128), 128, 0, st>>>(n);
+    TPG_CHECK_LAUNCH("grid_nn1_kernel");
+    *handled |= TPG_CHAMFER_REV;
+  }
   return TPG_OK;
 }
 

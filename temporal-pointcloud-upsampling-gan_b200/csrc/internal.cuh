@@ -32,8 +32,10 @@ int knn_feat_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes,
 bool grid_eligible(int D, int P2, int K);
 size_t grid_workspace_bytes(int B, int P);
 int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int grid_nn1_chamfer(const float* q, const float* c, const int64_t* ql, const int64_t* cl, int B, int Pq, int Pc,
-                     float* d_out, int32_t* i_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t grid_chamfer_workspace_bytes(int B, int P1, int P2);
+int grid_chamfer_nn(const float* src, const float* tgt, const int64_t* ls, const int64_t* lt, int B, int P1, int P2,
+                    int directions, float* d_src, int32_t* i_src, float* d_tgt, int32_t* i_tgt, void* workspace,
+                    size_t workspace_bytes, int* handled, cudaStream_t st);
 
 // group.cu — inverse index (CSR) of an int32 index tensor idx [B,L] with keys in
 // [0,N): seg_offsets [B,N+1], seg_items [B,L] (ascending positions per key).
