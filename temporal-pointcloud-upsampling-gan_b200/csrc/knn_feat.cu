@@ -35,14 +35,15 @@
 
 namespace tpg {
 
-constexpr int FT_THREADS = 256;
+constexpr int FT_THREADS = 512;
 constexpr int FT_TM = 128;   // candidates per tile (UMMA M)
-constexpr int FT_NQ = 32;    // queries per CTA (UMMA N)
-constexpr int FT_QW = 16;    // queries (accumulator columns) per warp
-constexpr int FT_TMEM_COLS = 64;
+constexpr int FT_NQ = 128;   // queries per CTA (UMMA N): 8 clouds x 16 CTAs = 128 CTAs, one wave on 148 SMs
+constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
+constexpr int FT_TMEM_COLS = 2 * FT_NQ;  // double-buffered accumulator (power of two >= 32)
 constexpr int FT_MAX_K = 24; // needs slack below the 32 list slots for the margin zone
 constexpr int FT_MAXGROUPS = 256;  // group-value slots per query (groups beyond that fold modulo)
-constexpr int FT_CAP = 24;         // candidate slots per (quarter, query) buffer
+constexpr int FT_CAP = 64;         // candidate slots per query (all four lane quarters append to one buffer)
+constexpr int FT_STAGES = 3;       // candidate-tile ring: the load of tile u+3 has a full iteration to land
 
 struct FeatArgs {
   const float* p1;
@@ -57,6 +58,7 @@ struct FeatArgs {
   int64_t* idx;            // [B,P1,K]
   int* fb_count;           // [1]
   int* fb_list;            // [B*P1]
+  long long* dbg;          // [ctas][8] phase timestamps (tools/bench_knn_feat.py)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -155,13 +157,37 @@ __device__ __forceinline__ unsigned warp_radix_bound16(const unsigned (&uk)[NV],
 #pragma unroll 1
   for (int bit = 31; bit >= 16; --bit) {
     const unsigned bmask = 1u << bit;
-    int c = 0;
+    unsigned local = 0;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) c += __popc(__ballot_sync(FULL, (uk[v] & (himask | bmask)) == prefix));
+    for (int v = 0; v < NV; ++v) local += ((uk[v] & (himask | bmask)) == prefix) ? 1u : 0u;
+    const int c = (int)__reduce_add_sync(FULL, local);  // one REDUX per step instead of NV ballots
     if (k > c) { prefix |= bmask; k -= c; }
     himask |= bmask;
   }
   return prefix | 0xffffu;
+}
+// same bound for NQ independent value sets at once (their dependent bit steps interleave)
+template <int NQ, int NV>
+__device__ __forceinline__ void warp_radix_bound16_multi(const unsigned (&uk)[NQ][NV], int k0, unsigned (&out)[NQ]) {
+  unsigned prefix[NQ], himask = 0u;
+  int k[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) { prefix[q] = 0u; k[q] = k0; }
+#pragma unroll 1
+  for (int bit = 31; bit >= 16; --bit) {
+    const unsigned bmask = 1u << bit;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      unsigned local = 0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) local += ((uk[q][v] & (himask | bmask)) == prefix[q]) ? 1u : 0u;
+      const int c = (int)__reduce_add_sync(FULL, local);
+      if (k[q] > c) { prefix[q] |= bmask; k[q] -= c; }
+    }
+    himask |= bmask;
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) out[q] = prefix[q] | 0xffffu;
 }
 __device__ __forceinline__ unsigned ordered_key(float f) {  // unsigned order == float order
   const int bits = __float_as_int(f);
@@ -195,34 +221,38 @@ __global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int 
 }
 
 // ---- main tcgen05 kernel -----------------------------------------------------------------------
-// 8 warps: warp w reads TMEM lane quarter (w & 3) — candidates 32(w&3)..+31 of every tile —
-// and owns the query half (w >> 2): 16 of the CTA's 32 queries (accumulator columns).
+// 16 warps: warp w reads TMEM lane quarter (w & 3) — candidates 32(w&3)..+31 of every tile —
+// and owns the column group (w >> 2): 32 of the CTA's 128 queries (accumulator columns).
+// The kernel is bound by the latency of its 2*T dependent tile iterations, so the CTA is made
+// as wide as TMEM/smem allow and the whole problem runs as ONE wave of CTAs.
 //
 // Two passes over the e-matrix (the MMAs are simply issued twice: the tensor pipe is idle
-// otherwise, and the tiles come from L2):
-//   pass 0  per query, one element of every group of 32 candidates that is <= all the others
-//           (CREDUX.MIN on the raw bits; for a group that contains negative e the result is
-//           still an ELEMENT of the group, which is all the argument needs).  The R smallest
-//           group values are R distinct candidates, so the R-th smallest of them (tau0) is a
-//           VALID upper bound of the R-th smallest e overall — and a tight one (about the
-//           1.4 R-th smallest for 64 groups).  R = K + 8.
-//   pass 1  every candidate with e <= tau0 is APPENDED (ballot + popc, no ordering work) to
-//           the (quarter, query) buffer: ~1.4 R candidates per query in total.
-// Finalisation per query (one warp): T_K = K-th smallest buffered e; every canonical top-K
-// neighbour has e <= T_K + 2 eps, and everything with e <= tau0 is buffered, so if
-// T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset; they are
-// re-ranked with the canonical distance.  Otherwise (or on a buffer overflow) -> fallback.
-__global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) {
+// otherwise, and the tiles come from L2).  Neither pass has a cross-lane operation in its inner
+// loop (shuffle / vote / redux throughput was the limiter of the first versions):
+//   pass 0  every lane keeps, per query, the running minimum of the e-values of the candidates it
+//           sees (one FMNMX per value): 128 disjoint candidate groups per query (4 lane quarters
+//           x 32 lanes).  The R smallest group minima are R distinct candidates, so the R-th
+//           smallest of them (tau0, 16-bit radix select, upper bucket end) is a VALID upper bound
+//           of the R-th smallest e overall — and a tight one.  R = K + 8.
+//   pass 1  the 32 bounds of a warp's queries sit in registers; every candidate with e <= tau0 is
+//           appended to the (quarter, query) buffer through a shared-memory counter (predicated
+//           ATOMS + STS; ~1.2 R candidates per query in total).  Buffer order is irrelevant.
+// Finalisation: (F1) per query, T_K = K-th smallest buffered e (radix bound); every canonical
+// top-K neighbour has e <= T_K + 2 eps and everything with e <= tau0 is buffered, so if
+// T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset (else -> fallback);
+// (F2) all threads evaluate the canonical distance of the (query, candidate) pairs; (F3) per
+// query, rank by (d_canon, idx) and write the K best.
+__global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) {
   extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
   __shared__ __align__(8) uint64_t mbar_s[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float tau0_s[FT_NQ];
-  __shared__ int cnt_s[4][FT_NQ];
-  __shared__ int scratch_s[FT_THREADS / 32][32];
+  __shared__ int cnt_s[FT_NQ];
+  __shared__ int ncand_s[FT_NQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
-  const int nq0 = half * FT_QW;  // first query (column) of this warp
+  const int quarter = warp & 3, colgrp = warp >> 2;
+  const int nq0 = colgrp * FT_QW;  // first query (column) of this warp
   const int b = blockIdx.y, q0 = blockIdx.x * FT_NQ;
   const int D = a.D, K = a.K;
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
@@ -236,8 +266,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   unsigned char* base_ptr = ft_smem_raw + (base - raw);
   const uint32_t stage_bytes = (uint32_t)D * 512u;   // 128 rows x D floats
   const uint32_t atomA = 128u * 128u;                // one 32-float K-slab of a stage
-  const uint32_t qtile = base + 2u * stage_bytes;
-  const uint32_t atomB = 32u * 128u;
+  const uint32_t qtile = base + (uint32_t)FT_STAGES * stage_bytes;
+  const uint32_t atomB = (uint32_t)FT_NQ * 128u;
   const int cpr = D >> 2;                            // 16-byte chunks per row: 8, 16 or 32
   const int T = (n2 + FT_TM - 1) / FT_TM;
 
@@ -264,6 +294,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
     }
   };
 
+  long long* dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && tid == 0) dbg[0] = clock64();
   // ---- setup ----
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
@@ -287,17 +319,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
       cp_async16(dst, src, ok ? 16 : 0);
     }
   }
-  const int G = 4 * T;
   const int U = 2 * T;
-  const int Gs = min(G, FT_MAXGROUPS);
-  const int Gpad = max((Gs + 31) & ~31, 32);
-  unsigned char* aux = base_ptr + 2u * stage_bytes + (uint32_t)D * 128u;
-  int* gval_s = reinterpret_cast<int*>(aux);        // pass 0: [32][Gpad] raw float bits
-  float2* buf_s = reinterpret_cast<float2*>(aux);   // pass 1: [4][32][FT_CAP] (e, idx) — aliases gval_s
-  for (int g = tid; g < FT_NQ * Gpad; g += FT_THREADS) gval_s[g] = 0x7f800000;  // +inf
+  unsigned char* aux = base_ptr + (uint32_t)FT_STAGES * stage_bytes + (uint32_t)D * 4u * FT_NQ;
+  float* gval_s = reinterpret_cast<float*>(aux);    // pass 0 -> select: [FT_NQ][128] group minima
+  float2* buf_s = reinterpret_cast<float2*>(aux);   // pass 1: [FT_NQ][FT_CAP] (e, idx) — aliases gval_s
+  for (int g = tid; g < FT_NQ; g += FT_THREADS) cnt_s[g] = 0;
 
-  if (U > 0) load_tile(0, 0);
-  if (U > 1) load_tile(1 % T, 1);
+  for (int u0 = 0; u0 < FT_STAGES && u0 < U; ++u0) load_tile(u0 % T, u0);
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
@@ -306,8 +334,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
   const uint32_t tmem_base = tmem_base_s;
 
   auto issue_mma = [&](int u) {
-    const int s = u & 1;
-    const uint32_t sb = base + (uint32_t)s * stage_bytes;
+    const int s = u & 1;  // TMEM buffer / mbarrier
+    const uint32_t sb = base + (uint32_t)(u % FT_STAGES) * stage_bytes;
     const uint32_t td = tmem_base + (uint32_t)s * FT_NQ;
     const int ksteps = D >> 3;
     for (int kk = 0; kk < ksteps; ++kk) {
@@ -319,181 +347,200 @@ __global__ void __launch_bounds__(FT_THREADS, 2) knn_feat_tc_kernel(FeatArgs a) 
     umma_commit(smem_u32(&mbar_s[s]));
   };
   if (tid == 0 && U > 0) issue_mma(0);
+  if (dbg && tid == 0) dbg[1] = clock64();
 
-  int cnt[FT_QW];
+  // pass 0: running group minima; pass 1: admission bounds of this warp's 32 queries
+  float reg[FT_QW];
 #pragma unroll
-  for (int n = 0; n < FT_QW; ++n) cnt[n] = 0;
-  float tau0 = INF;  // lanes 0..15: admission bound of query nq0 + lane (e-space)
+  for (int n = 0; n < FT_QW; ++n) reg[n] = INF;
 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
     const bool list_pass = u >= T;
     if (tid == 0 && u + 1 < U) issue_mma(u + 1);
     if (u == T) {
-      // ---- tau0 = R-th smallest group value: 16-bit radix select on the ordered keys, upper end of
-      //      the selected bucket (valid: >= the exact R-th smallest; < 1% looser).  4 queries per warp.
-      const int R = min(32, K + 8);
-      for (int qq = 0; qq < FT_NQ / 8; ++qq) {
-        const int n = warp * (FT_NQ / 8) + qq;
-        const int* row = gval_s + n * Gpad;
-        unsigned uk[FT_MAXGROUPS / 32];
+      if (dbg && tid == 0) dbg[2] = clock64();
 #pragma unroll
-        for (int v = 0; v < FT_MAXGROUPS / 32; ++v)
-          uk[v] = lane + 32 * v < Gpad ? ordered_key(__int_as_float(row[lane + 32 * v])) : 0xffffffffu;
-        const unsigned bound = Gpad <= 64 ? warp_radix_bound16(reinterpret_cast<const unsigned(&)[2]>(uk), R)
-                                          : warp_radix_bound16(uk, R);
-        if (lane == 0) tau0_s[n] = ordered_key_inv(bound);
-      }
+      for (int n = 0; n < FT_QW; ++n) gval_s[(nq0 + n) * 128 + quarter * 32 + lane] = reg[n];
+      __syncthreads();
+      // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
+      //      processed together so their (dependent) radix steps overlap
+      constexpr int QPW = FT_NQ / (FT_THREADS / 32);
+      const int R = min(32, K + 8);
+      unsigned uk[QPW][4];
+#pragma unroll
+      for (int qq = 0; qq < QPW; ++qq)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 128 + v * 32 + lane]);
+      unsigned bound[QPW];
+      warp_radix_bound16_multi<QPW, 4>(uk, R, bound);
       __syncthreads();  // gval_s is dead from here on: buf_s may overwrite it
-      tau0 = tau0_s[nq0 + (lane & (FT_QW - 1))];
+      if (lane == 0)
+#pragma unroll
+        for (int qq = 0; qq < QPW; ++qq) tau0_s[warp * QPW + qq] = ordered_key_inv(bound[qq]);
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < FT_QW; ++n) reg[n] = tau0_s[nq0 + n];
+      if (dbg && tid == 0) dbg[3] = clock64();
     }
     const int j = t * FT_TM + quarter * 32 + lane;
     const float ncj = j < n2 ? __ldg(a.nrm2 + (size_t)b * a.P2 + j) : INF;
     mbar_wait(smem_u32(&mbar_s[u & 1]), (uint32_t)((u >> 1) & 1));
     tc_fence_after();
-    if (u + 2 < U) load_tile((u + 2) % T, u & 1);  // MMA(u) has released this stage
+    if (u + FT_STAGES < U) load_tile((u + FT_STAGES) % T, u % FT_STAGES);  // MMA(u) has released this stage
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
     uint32_t acc[FT_QW];
-    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u & 1) * FT_NQ + nq0), acc);
+    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u & 1) * FT_NQ + nq0), acc);
     if (!list_pass) {
-      int mine = 0x7f800000;
 #pragma unroll
-      for (int n = 0; n < FT_QW; ++n) {
-        const int r = __reduce_min_sync(FULL, __float_as_int(fmaf(-2.0f, __uint_as_float(acc[n]), ncj)));
-        if (lane == n) mine = r;
-      }
-      if (lane < FT_QW) {
-        int* slot = gval_s + (nq0 + lane) * Gpad + ((t * 4 + quarter) % FT_MAXGROUPS);
-        // (slot % 4, query half) identify this warp: no other writer.  Keep the smaller FLOAT.
-        if (__int_as_float(mine) < __int_as_float(*slot)) *slot = mine;
-      }
+      for (int n = 0; n < FT_QW; ++n) reg[n] = fminf(reg[n], fmaf(-2.0f, __uint_as_float(acc[n]), ncj));
     } else {
+      const float jbits = __int_as_float(j);
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) {
         const float e = fmaf(-2.0f, __uint_as_float(acc[n]), ncj);  // inf for padded candidates
-        const bool hit = e <= __shfl_sync(FULL, tau0, n);
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (m) {
-          const int pos = cnt[n] + __popc(m & lt_mask);
-          if (hit && pos < FT_CAP) buf_s[((size_t)quarter * FT_NQ + nq0 + n) * FT_CAP + pos] = make_float2(e, __int_as_float(j));
-          cnt[n] += __popc(m);
+        if (e <= reg[n] && j < n2) {
+          const int pos = atomicAdd(&cnt_s[nq0 + n], 1);
+          if (pos < FT_CAP) buf_s[(nq0 + n) * FT_CAP + pos] = make_float2(e, jbits);
         }
       }
     }
-    cp_async_wait_all();
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile u+2 (issued last iteration) has landed
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
+  cp_async_wait_all();
+  __syncthreads();
+  if (dbg && tid == 0) dbg[4] = clock64();
+
+  // ---- F1: per query (QPW per warp): margin, superset check, candidate list ----
+  constexpr int QPW = FT_NQ / (FT_THREADS / 32);
+  const float nmax = __uint_as_float(a.nmax2[b]);
+  int* cand_s = reinterpret_cast<int*>(base_ptr);                 // [FT_NQ][32] candidate indices (stage memory is free)
+  float* dcan_s = reinterpret_cast<float*>(base_ptr) + FT_NQ * 32;  // [FT_NQ][32] canonical distances
+  for (int qq = 0; qq < QPW; ++qq) {
+    const int n = warp * QPW + qq;
+    const int qi = q0 + n;
+    int ncand = -1;  // -1: nothing to do (beyond P1 / lengths1 / fallback)
+    if (qi < n1) {
+      const int C = cnt_s[n];
+      bool ok = C <= FT_CAP;
+      float ev[2];
+      int jv[2];
 #pragma unroll
-  for (int n = 0; n < FT_QW; ++n)
-    if (lane == n) cnt_s[quarter][nq0 + n] = cnt[n];
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int i = lane + 32 * s2;
+        ev[s2] = INF; jv[s2] = 0x7fffffff;
+        if (ok && i < C) {
+          const float2 v = buf_s[n * FT_CAP + i];
+          ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
+        }
+      }
+      float limit = INF;
+      const float t0 = tau0_s[n];
+      if (ok) {
+        // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
+        float tk = INF;
+        if (C >= K) {
+          const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
+          tk = ordered_key_inv(warp_radix_bound16(uk2, K));
+        }
+        const float nq = a.nrm1[(size_t)b * a.P1 + qi];
+        limit = tk + 2.0f * feat_eps(nq, nmax, D);
+        // everything with e <= tau0 is buffered, so the margin zone must end below tau0
+        // (tau0 == inf: every candidate of the cloud is buffered)
+        ok = limit < t0 || t0 == INF;
+      }
+      const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
+      const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
+      ncand = __popc(cm0) + __popc(cm1);
+      if (!ok || ncand > 32) {
+        if (lane == 0) {
+          const int pos = atomicAdd(a.fb_count, 1);
+          a.fb_list[pos] = b * a.P1 + qi;
+        }
+        ncand = -1;
+      } else {
+        if (cand0) cand_s[n * 32 + __popc(cm0 & lt_mask)] = jv[0];
+        if (cand1) cand_s[n * 32 + __popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
+      }
+    } else if (qi < a.P1 && lane < K) {  // rows beyond lengths1: zeros (pytorch3d convention)
+      a.dists[((size_t)b * a.P1 + qi) * K + lane] = 0.0f;
+      a.idx[((size_t)b * a.P1 + qi) * K + lane] = 0;
+    }
+    if (lane == 0) ncand_s[n] = ncand;
+  }
   __syncthreads();
 
-  // ---- finalisation: 4 queries per warp ----
-  const float nmax = __uint_as_float(a.nmax2[b]);
-  int* scratch = scratch_s[warp];
-  for (int qq = 0; qq < FT_NQ / 8; ++qq) {
-    const int n = warp * (FT_NQ / 8) + qq;
-    const int qi = q0 + n;
-    if (qi >= a.P1) break;
-    float* od = a.dists + ((size_t)b * a.P1 + qi) * K;
-    int64_t* oi = a.idx + ((size_t)b * a.P1 + qi) * K;
-    if (qi >= n1) {  // rows beyond lengths1: zeros (pytorch3d convention)
-      if (lane < K) { od[lane] = 0.0f; oi[lane] = 0; }
-      continue;
-    }
-    const int c0 = cnt_s[0][n], c1 = cnt_s[1][n], c2 = cnt_s[2][n], c3 = cnt_s[3][n];
-    const int C = c0 + c1 + c2 + c3;
-    bool ok = max(max(c0, c1), max(c2, c3)) <= FT_CAP && C <= 64;
-    // logical element i of the concatenated buffers -> (quarter w, slot h)
-    float ev[2];
-    int jv[2];
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const int i = lane + 32 * s2;
-      ev[s2] = INF; jv[s2] = 0x7fffffff;
-      if (ok && i < C) {
-        const int w = (i >= c0) + (i >= c0 + c1) + (i >= c0 + c1 + c2);
-        const int h = i - (w > 0 ? c0 : 0) - (w > 1 ? c1 : 0) - (w > 2 ? c2 : 0);
-        const float2 v = buf_s[((size_t)w * FT_NQ + n) * FT_CAP + h];
-        ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
-      }
-    }
-    float limit = INF;
-    const float t0 = tau0_s[n];
-    if (ok) {
-      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
-      float tk = INF;
-      if (C >= K) {
-        const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
-        tk = ordered_key_inv(warp_radix_bound16(uk2, K));
-      }
-      const float nq = a.nrm1[(size_t)b * a.P1 + qi];
-      limit = tk + 2.0f * feat_eps(nq, nmax, D);
-      // everything with e <= tau0 is buffered, so the margin zone must end below tau0
-      // (tau0 == inf: every candidate of the cloud is buffered)
-      ok = limit < t0 || t0 == INF;
-    }
-    const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
-    const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
-    const int ncand = __popc(cm0) + __popc(cm1);
-    if (!ok || ncand > 32) {
-      if (lane == 0) {
-        const int pos = atomicAdd(a.fb_count, 1);
-        a.fb_list[pos] = b * a.P1 + qi;
-      }
-      continue;
-    }
-    // one candidate per lane
-    __syncwarp();
-    if (cand0) scratch[__popc(cm0 & lt_mask)] = jv[0];
-    if (cand1) scratch[__popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
-    __syncwarp();
-    const bool cand = lane < ncand;
-    float dc = INF;
-    int ci = 0x7fffffff;
-    if (cand) {
-      ci = scratch[lane];
-      const float4* xr = reinterpret_cast<const float4*>(p1b + (size_t)qi * D);
-      const float4* yr = reinterpret_cast<const float4*>(p2b + (size_t)ci * D);
-      float acc2 = 0.0f;
+  // ---- F2: canonical distances of all (query, candidate) pairs, spread over every thread ----
+  for (int pr0 = tid; pr0 < FT_NQ * 32; pr0 += 2 * FT_THREADS) {  // two independent chains per thread
+    const int prA = pr0, prB = pr0 + FT_THREADS;
+    const bool vA = (prA & 31) < ncand_s[prA >> 5], vB = prB < FT_NQ * 32 && (prB & 31) < ncand_s[prB >> 5];
+    const float4* xA = reinterpret_cast<const float4*>(p1b + (size_t)(vA ? q0 + (prA >> 5) : 0) * D);
+    const float4* yA = reinterpret_cast<const float4*>(p2b + (size_t)(vA ? cand_s[prA] : 0) * D);
+    const float4* xB = reinterpret_cast<const float4*>(p1b + (size_t)(vB ? q0 + (prB >> 5) : 0) * D);
+    const float4* yB = reinterpret_cast<const float4*>(p2b + (size_t)(vB ? cand_s[prB] : 0) * D);
+    float accA = 0.0f, accB = 0.0f;
+    if (vA || vB) {
       for (int c = 0; c < cpr; ++c) {
-        const float4 x = __ldg(xr + c), y = __ldg(yr + c);
-        acc2 = sq_acc(acc2, x.x, y.x); acc2 = sq_acc(acc2, x.y, y.y);
-        acc2 = sq_acc(acc2, x.z, y.z); acc2 = sq_acc(acc2, x.w, y.w);
+        const float4 x0 = __ldg(xA + c), y0 = __ldg(yA + c), x1 = __ldg(xB + c), y1 = __ldg(yB + c);
+        accA = sq_acc(accA, x0.x, y0.x); accB = sq_acc(accB, x1.x, y1.x);
+        accA = sq_acc(accA, x0.y, y0.y); accB = sq_acc(accB, x1.y, y1.y);
+        accA = sq_acc(accA, x0.z, y0.z); accB = sq_acc(accB, x1.z, y1.z);
+        accA = sq_acc(accA, x0.w, y0.w); accB = sq_acc(accB, x1.w, y1.w);
       }
-      dc = acc2;
     }
+    if (vA) dcan_s[prA] = accA;
+    if (vB) dcan_s[prB] = accB;
+  }
+  __syncthreads();
+
+  // ---- F3: rank by (d_canon, idx), write the K best ----
+  for (int qq = 0; qq < QPW; ++qq) {
+    const int n = warp * QPW + qq;
+    const int ncand = ncand_s[n];
+    if (ncand < 0) continue;
+    const int qi = q0 + n;
+    const bool cand = lane < ncand;
+    const float dc = cand ? dcan_s[n * 32 + lane] : INF;
+    const int ci = cand ? cand_s[n * 32 + lane] : 0x7fffffff;
     int rank = 0;
     for (int m2 = 0; m2 < ncand; ++m2) {
       const float od2 = __shfl_sync(FULL, dc, m2);
       const int oi2 = __shfl_sync(FULL, ci, m2);
       rank += (od2 < dc || (od2 == dc && oi2 < ci)) ? 1 : 0;
     }
+    float* od = a.dists + ((size_t)b * a.P1 + qi) * K;
+    int64_t* oi = a.idx + ((size_t)b * a.P1 + qi) * K;
     if (cand && rank < K) { od[rank] = dc; oi[rank] = (int64_t)ci; }
     if (lane < K && lane >= ncand) { od[lane] = 0.0f; oi[lane] = 0; }  // fewer than K candidates in the cloud
   }
 
   __syncthreads();
+  if (dbg && tid == 0) dbg[5] = clock64();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(FT_TMEM_COLS) : "memory");
   }
 }
 
 // ---- exact fallback: one CTA per flagged query (8 warps x 1/8 of the candidates, then a merge) ------
+template <int CH>  // CH = D / 4 float4 chunks per row (8 or 16)
 __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
   __shared__ float2 part_s[8][32];
   const int total = *a.fb_count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float INF = __int_as_float(0x7f800000);
-  const int chunks = a.D >> 2;
   for (int e = blockIdx.x; e < total; e += gridDim.x) {
     const int flat = a.fb_list[e];
     const int b = flat / a.P1, qi = flat - b * a.P1;
     const int n2 = a.len2 ? min((int)a.len2[b], a.P2) : a.P2;
     const float4* xr = reinterpret_cast<const float4*>(a.p1 + ((size_t)b * a.P1 + qi) * a.D);
     const float* p2b = a.p2 + (size_t)b * a.P2 * a.D;
+    float4 x[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) x[c] = __ldg(xr + c);
     WarpList L;
     L.init();
     float tau = INF;
@@ -504,11 +551,14 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
       float acc = INF;
       if (j < jhi) {
         const float4* yr = reinterpret_cast<const float4*>(p2b + (size_t)j * a.D);
+        float4 y[CH];  // the whole row first: one L2 round trip instead of CH dependent ones
+#pragma unroll
+        for (int c = 0; c < CH; ++c) y[c] = __ldg(yr + c);
         acc = 0.0f;
-        for (int c = 0; c < chunks; ++c) {
-          const float4 x = __ldg(xr + c), y = __ldg(yr + c);
-          acc = sq_acc(acc, x.x, y.x); acc = sq_acc(acc, x.y, y.y);
-          acc = sq_acc(acc, x.z, y.z); acc = sq_acc(acc, x.w, y.w);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          acc = sq_acc(acc, x[c].x, y[c].x); acc = sq_acc(acc, x[c].y, y[c].y);
+          acc = sq_acc(acc, x[c].z, y[c].z); acc = sq_acc(acc, x[c].w, y[c].w);
         }
       }
       unsigned m = __ballot_sync(FULL, j < jhi && acc < tau);
@@ -560,6 +610,7 @@ struct FeatWs {
   unsigned* nmax2;
   int* fb_count;
   int* fb_list;
+  long long* dbg;
   size_t total;
 };
 
@@ -572,6 +623,7 @@ static FeatWs feat_carve(void* base, int B, int P1, int P2) {
   w.nrm1 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P1, 256);
   w.nrm2 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P2, 256);
   w.fb_list = reinterpret_cast<int*>(p + o);    o += align_up(sizeof(int) * (size_t)B * P1, 256);
+  w.dbg = reinterpret_cast<long long*>(p + o);  o += align_up(sizeof(long long) * 8 * (size_t)B * (size_t)((P1 + FT_NQ - 1) / FT_NQ), 256);
   w.total = o;
   return w;
 }
@@ -588,8 +640,8 @@ static bool feat_enabled() {
 bool knn_feat_eligible(const KnnArgs& a) {
   if (!feat_enabled()) return false;
   if (a.out_mode != OUT_KNN || a.use_radius) return false;
-  if (a.D != 32 && a.D != 64 && a.D != 128) return false;
-  if (a.K > FT_MAX_K || a.P2 < 1024) return false;  // needs >= 32 groups of 32 candidates
+  if (a.D != 32 && a.D != 64) return false;  // the shapes the generator uses (gcn.py:200-203,258)
+  if (a.K > FT_MAX_K || a.P2 < 1024) return false;  // below that the brute-force kernel is as fast
   if ((long long)a.B * a.P1 >= (1LL << 31)) return false;
   if ((reinterpret_cast<uintptr_t>(a.p1) | reinterpret_cast<uintptr_t>(a.p2)) & 15) return false;
   return true;
@@ -607,21 +659,24 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
     dim3 g2(ceil_div(k.P2, 128), k.B);
     feat_norm_kernel<<<g2, 128, 0, st>>>(k.p2, k.B, k.P2, k.D, w.nrm2, w.nmax2);
     TPG_CHECK_LAUNCH("feat_norm_kernel");
-    dim3 g1(ceil_div(k.P1, 128), k.B);
-    feat_norm_kernel<<<g1, 128, 0, st>>>(k.p1, k.B, k.P1, k.D, w.nrm1, nullptr);
-    TPG_CHECK_LAUNCH("feat_norm_kernel");
+    if (k.p1 == k.p2 && k.P1 == k.P2) {
+      w.nrm1 = w.nrm2;  // self search: one norm pass
+    } else {
+      dim3 g1(ceil_div(k.P1, 128), k.B);
+      feat_norm_kernel<<<g1, 128, 0, st>>>(k.p1, k.B, k.P1, k.D, w.nrm1, nullptr);
+      TPG_CHECK_LAUNCH("feat_norm_kernel");
+    }
   }
   FeatArgs a{k.p1, k.p2, k.len1, k.len2, k.B, k.P1, k.P2, k.D, k.K, w.nrm1, w.nrm2, w.nmax2,
-             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list};
-  const int groups = 4 * ceil_div(k.P2, FT_TM);
-  const int gpad = ((groups < FT_MAXGROUPS ? groups : FT_MAXGROUPS) + 31) & ~31;
-  const size_t aux = max((size_t)FT_NQ * gpad * sizeof(int), (size_t)4 * FT_NQ * FT_CAP * sizeof(float2));
-  const size_t smem = (size_t)k.D * 512 * 2 + (size_t)k.D * 128 + 1024 + aux;
+             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr};
+  const size_t aux = max((size_t)FT_NQ * 128 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
+  const size_t smem = (size_t)k.D * 512 * FT_STAGES + (size_t)k.D * 4 * FT_NQ + 1024 + aux;
   TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k.P1, FT_NQ), k.B);
   knn_feat_tc_kernel<<<grid, FT_THREADS, smem, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
-  knn_feat_fallback_kernel<<<num_sms() * 4, 256, 0, st>>>(a);
+  if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms() * 4, 256, 0, st>>>(a);
+  else knn_feat_fallback_kernel<16><<<num_sms() * 4, 256, 0, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_fallback_kernel");
   return TPG_OK;
 }

@@ -46,6 +46,7 @@ KNN_CASES = [
     (1, 64, 50, 130, 8, "feat"),
     (1, 300, 700, 96, 24, "feat"),   # D = 96 / P2 < 1024: SIMT path
     (1, 256, 512, 128, 16, "feat"),
+    (1, 256, 2048, 128, 16, "feat"),  # D = 128: SIMT path
     (1, 50, 10, 3, 16, "fluid"),     # K > P2 -> zero padding
     (1, 70, 200, 3, 40, "fluid"),    # K > 32 -> multi-pass
     (1, 40, 300, 3, 100, "dup"),
@@ -162,8 +163,8 @@ KNN_TC_CASES = [
     (1, 2048, 2048, 64, 4, "featself"),
     (1, 2048, 2048, 64, 8, "feat"),
     (2, 1000, 1500, 64, 20, "feat"),     # ragged query / candidate tiles
-    (1, 300, 1100, 128, 24, "feat"),
-    (1, 256, 4096, 128, 16, "feat"),
+    (1, 300, 1100, 64, 24, "feat"),
+    (1, 256, 4096, 32, 16, "feat"),
     (1, 100, 40000, 32, 16, "feat"),     # > 256 groups: group slots fold modulo
     (1, 1024, 1024, 64, 12, "featdup"),  # exact duplicate rows: (d2, idx) ties
     (1, 512, 1024, 32, 20, "featoffset"),   # |x| >> distances: margin overflow -> exact fallback
