@@ -137,6 +137,7 @@ def cpu_replay(workload, batch, steps, warmup):
     from tpugan_b200 import hotpath_trace as ht
 
     ops = OracleOps()
+    ops.o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     doc = ht.load_schedule(os.path.join(GOLDEN, f"{workload}_step_schedule.json"), batch)
     rp = ht.TraceReplay(doc, ops, seed=1)
     for _ in range(warmup):

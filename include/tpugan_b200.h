@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 3
+#define TPG_ABI_VERSION 4
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -100,9 +100,12 @@ int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* lengths1,
  *   new_xyz) used inside QueryAndGroup — discriminator.py:190.
  * xyz [B,N,3], new_xyz [B,M,3] -> idx [B,M,nsample] int32: the `nsample`
  * LOWEST indices with d2 < radius^2, slots beyond the hit count repeat the
- * first hit, no hit -> all 0.                                              */
+ * first hit, no hit -> all 0.  Clouds of >= 8192 points are searched through the
+ * uniform grid (workspace: tpg_ball_query_workspace_bytes(), else 0 / NULL).    */
+size_t tpg_ball_query_workspace_bytes(int B, int N, int M, int nsample);
 int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N,
                        int M, float radius, int nsample, int32_t* idx,
+                       void* workspace, size_t workspace_bytes,
                        tpg_stream_t stream);
 
 /* ---- K5: farthest point sampling -----------------------------------------

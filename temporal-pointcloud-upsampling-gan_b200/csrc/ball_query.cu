@@ -10,6 +10,7 @@
 // warps of a CTA scan the same cloud, so every 128-byte line is fetched from L2 once
 // per CTA and re-served from L1.
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace tpg {
 
@@ -67,11 +68,22 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* _
 
 using namespace tpg;
 
+// grid search pays off once the index-ordered scan can no longer stop early: big clouds
+static bool ball_query_uses_grid(int N, int nsample) { return N >= 8192 && grid_eligible(3, N, nsample); }
+
+TPG_API size_t tpg_ball_query_workspace_bytes(int B, int N, int M, int nsample) {
+  (void)M;
+  return ball_query_uses_grid(N, nsample) ? grid_workspace_bytes(B, N) : 0;
+}
+
 TPG_API int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N, int M, float radius,
-                               int nsample, int32_t* idx, tpg_stream_t stream) {
+                               int nsample, int32_t* idx, void* workspace, size_t workspace_bytes,
+                               tpg_stream_t stream) {
   TPG_REQUIRE(B >= 0 && N >= 0 && M >= 0 && nsample >= 1, TPG_EINVAL, "ball_query: bad size");
   if (B == 0 || M == 0) return TPG_OK;
   TPG_REQUIRE((xyz || N == 0) && new_xyz && idx, TPG_EINVAL, "ball_query: null pointer");
+  if (ball_query_uses_grid(N, nsample))
+    return grid_ball_query(xyz, new_xyz, B, N, M, radius, nsample, idx, workspace, workspace_bytes, as_stream(stream));
   const float r2 = radius * radius;
   const long long warps = (long long)B * M;
   const long long blocks = (warps + BQ_THREADS / 32 - 1) / (BQ_THREADS / 32);

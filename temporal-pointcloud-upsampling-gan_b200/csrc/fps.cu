@@ -227,7 +227,7 @@ static int fps_launch(const FpsArgs& a, int threads, cudaStream_t st) {
   auto kern = fps_reg_kernel<PPT, CL, MODEB>;
   const int ppc = CL == 1 ? a.N : (ceil_div(a.N, CL) + 31) & ~31;
   const size_t smem = sizeof(float) * 3 * (size_t)ppc;
-  if (smem > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static smem counts too
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.B * CL));
   cfg.blockDim = dim3((unsigned)threads);

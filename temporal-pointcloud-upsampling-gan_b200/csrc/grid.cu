@@ -232,8 +232,11 @@ struct GridKnnArgs {
   GridRef g;
   float* dists;
   void* idx;
-  int out_mode;
+  int out_mode;  // OUT_KNN / OUT_FRNN / OUT_THREE, or OUT_BALL: the K LOWEST INDICES inside the radius (int32,
+                 // remaining slots repeat the first hit, no hit -> 0): pointnet2 ball_query semantics
 };
+
+constexpr int OUT_BALL = 100;
 
 __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
   const int lane = threadIdx.x & 31;
@@ -302,8 +305,10 @@ __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
           int ci = 0x7fffffff;
           if (t < total) {
             const float4 v = __ldg(rec + rstart + (t - (rinc - rcnt)));
+            // ball query: the centre is the FIRST operand upstream (new_xyz - xyz); (a-b)^2 == (b-a)^2 exactly
             d = sqdist3(qx, qy, qz, v.x, v.y, v.z);
             ci = __float_as_int(v.w);
+            if (a.out_mode == OUT_BALL) d = d < r2 ? 0.0f : __int_as_float(0x7f800000);  // rank by index only
           }
           unsigned m = __ballot_sync(FULL, t < total && d < r2 && (d < tau_d || (d == tau_d && ci < tau_i)));
           while (m) {
@@ -325,6 +330,13 @@ __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
       if (a.use_radius || k.cover == INF) break;
       if (tau_d < INF && tau_d < __fmul_rn(k.cover, k.cover)) break;
     }
+  }
+  if (a.out_mode == OUT_BALL) {
+    if (qi < a.P1 && lane < K) {
+      const int first = __shfl_sync(FULL, L.i, 0);
+      reinterpret_cast<int32_t*>(a.idx)[(size_t)wq * K + lane] = L.i >= 0 ? L.i : (first >= 0 ? first : 0);
+    }
+    return;
   }
   if (qi < a.P1 && lane < K) {
     const size_t o = (size_t)wq * K + lane;
@@ -462,6 +474,19 @@ static int grid_build(const float* p, const int64_t* len, int B, int P, int K, i
   out->cell_start = w.cell_start;
   out->rec = w.rec;
   out->P = P;
+  return TPG_OK;
+}
+
+int grid_ball_query(const float* xyz, const float* new_xyz, int B, int N, int M, float radius, int nsample,
+                    int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TPG_REQUIRE(workspace && workspace_bytes >= grid_workspace_bytes(B, N), TPG_EWORKSPACE,
+              "ball_query grid search: workspace too small (need %zu bytes)", grid_workspace_bytes(B, N));
+  GridRef g;
+  int rc = grid_build(xyz, nullptr, B, N, nsample, 1, radius, nullptr, workspace, &g, st);
+  if (rc) return rc;
+  GridKnnArgs k{new_xyz, nullptr, nullptr, B, M, nsample, 1, radius, nullptr, g, nullptr, idx, OUT_BALL};
+  grid_knn_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(k);
+  TPG_CHECK_LAUNCH("grid_knn_kernel");
   return TPG_OK;
 }
 

@@ -113,24 +113,45 @@ __global__ void __launch_bounds__(GRP_THREADS) group_reduce_fwd_kernel(ReduceFwd
   }
   const float* rows = SMEM ? rows_s : fb;
   const int m0 = blockIdx.x * a.MT, m1 = min(a.M, m0 + a.MT);
+  constexpr int TCMAX = 8;
   for (int m = m0 + tid; m < m1; m += GRP_THREADS) {
     const int32_t* im = a.idx + ((size_t)b * a.M + m) * a.k;
     const float* wm = a.w ? a.w + ((size_t)b * a.M + m) * a.k : nullptr;
-    for (int c = 0; c < tc; ++c) {
-      const float* r = rows + (size_t)c * a.N;
-      float acc = SMEM ? r[im[0]] : __ldg(r + im[0]);
-      if (wm) acc = __fmul_rn(wm[0], acc);
-      int best = 0;
-      for (int j = 1; j < a.k; ++j) {
-        float v = SMEM ? r[im[j]] : __ldg(r + im[j]);
-        if (wm) acc = __fadd_rn(acc, __fmul_rn(wm[j], v));
-        else if (a.op == TPG_REDUCE_MAX) { if (v > acc) { acc = v; best = j; } }
-        else if (a.op == TPG_REDUCE_MIN) { if (v < acc) { acc = v; best = j; } }
-        else acc = __fadd_rn(acc, v);
+    // neighbour-major: every index (and weight) is loaded once and serves all the channels of the tile
+    float acc[TCMAX];
+    int best[TCMAX];
+    {
+      const int i0 = __ldg(im);
+      const float w0 = wm ? __ldg(wm) : 1.0f;
+#pragma unroll
+      for (int c = 0; c < TCMAX; ++c) {
+        float v = 0.0f;
+        if (c < tc) v = SMEM ? rows[(size_t)c * a.N + i0] : __ldg(rows + (size_t)c * a.N + i0);
+        acc[c] = wm ? __fmul_rn(w0, v) : v;
+        best[c] = 0;
       }
-      const size_t o = ((size_t)b * a.C + c0 + c) * a.M + m;
-      a.out[o] = acc;
-      if (a.arg) a.arg[o] = best;
+    }
+    for (int j = 1; j < a.k; ++j) {
+      const int i = __ldg(im + j);
+      const float wj = wm ? __ldg(wm + j) : 1.0f;
+#pragma unroll
+      for (int c = 0; c < TCMAX; ++c) {
+        if (c < tc) {
+          const float v = SMEM ? rows[(size_t)c * a.N + i] : __ldg(rows + (size_t)c * a.N + i);
+          if (wm) acc[c] = __fadd_rn(acc[c], __fmul_rn(wj, v));
+          else if (a.op == TPG_REDUCE_MAX) { if (v > acc[c]) { acc[c] = v; best[c] = j; } }
+          else if (a.op == TPG_REDUCE_MIN) { if (v < acc[c]) { acc[c] = v; best[c] = j; } }
+          else acc[c] = __fadd_rn(acc[c], v);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < TCMAX; ++c) {
+      if (c < tc) {
+        const size_t o = ((size_t)b * a.C + c0 + c) * a.M + m;
+        a.out[o] = acc[c];
+        if (a.arg) a.arg[o] = best[c];
+      }
     }
   }
 }
@@ -467,14 +488,11 @@ TPG_API int tpg_group_fwd_f32(const float* f, const int32_t* idx, const float* c
 static int launch_reduce_fwd(ReduceFwdArgs a, cudaStream_t st) {
   const int max_tc = (int)(GRP_SMEM_MAX / ((size_t)a.N * sizeof(float)));
   const bool smem = max_tc >= 1;
-  const int target = 4 * num_sms();
-  int TC = 1;
-  for (int t = 8; t >= 1; t >>= 1) {
-    if (t > a.C && t > 1) continue;
-    if (smem && t > max_tc) continue;
-    TC = t;
-    if ((long long)a.B * ceil_div(a.C, t) >= target) break;
-  }
+  const int target = 2 * num_sms();
+  // every index is re-read once per channel tile, every feature row once per m tile: take the widest
+  // channel tile that fits and split M only as far as needed to fill the machine
+  int TC = 8;
+  while (TC > 1 && (TC > a.C || (smem && TC > max_tc))) TC >>= 1;
   a.TC = TC;
   int mt = max(1, ceil_div(target, a.B * ceil_div(a.C, TC)));
   mt = min(mt, max(1, a.M / GRP_THREADS));
@@ -534,7 +552,7 @@ int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, 
   {
     bool wide = false;
     const int W = csr_stable_warps(N, L, &wide);
-    if (W > 0) {
+    if (W == 32) {  // fewer warps per cloud: the count / scan / fill / sort path over all SMs is faster
       const size_t sm = sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3) + (size_t)W * N * (wide ? 5 : 3);
       if (wide) {
         auto kern = csr_stable_kernel<uint32_t>;

@@ -32,6 +32,8 @@ int knn_feat_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes,
 bool grid_eligible(int D, int P2, int K);
 size_t grid_workspace_bytes(int B, int P);
 int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int grid_ball_query(const float* xyz, const float* new_xyz, int B, int N, int M, float radius, int nsample,
+                    int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t grid_chamfer_workspace_bytes(int B, int P1, int P2);
 int grid_chamfer_nn(const float* src, const float* tgt, const int64_t* ls, const int64_t* lt, int B, int P1, int P2,
                     int directions, float* d_src, int32_t* i_src, float* d_tgt, int32_t* i_tgt, void* workspace,

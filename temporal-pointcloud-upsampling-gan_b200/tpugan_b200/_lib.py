@@ -14,7 +14,7 @@ LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
@@ -39,7 +39,8 @@ _PROTOS = {
     "tpg_knn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_frnn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "tpg_frnn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
-    "tpg_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    "tpg_ball_query_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "tpg_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _Z, _P]),
     "tpg_fps_workspace_bytes": (_Z, [_I, _I]),
     "tpg_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),
     "tpg_fps_start_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
@@ -101,5 +102,13 @@ def check(status: int, what: str) -> None:
         raise TpgError(f"{what} failed (status {status}): {last_error()}")
 
 
+_fns = {}
+
+
 def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args), name)
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(load(), name)
+    status = fn(*args)
+    if status != TPG_OK:
+        check(status, name)

@@ -39,6 +39,25 @@ def _req(t, name, dtype, ndim=None, exc=RuntimeError):
         raise exc(f"{name} must have {ndim} dimensions, got shape {tuple(t.shape)}")
 
 
+class _on_device:
+    """`with torch.cuda.device(d)` costs several microseconds per call; the common case (tensor on the
+    current device) needs no guard at all."""
+    __slots__ = ("guard",)
+
+    def __init__(self, device):
+        self.guard = None if device.index is None or device.index == torch.cuda.current_device() \
+            else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
+
+
 def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -69,7 +88,7 @@ def knn(p1, p2, K: int, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, tor
     l2 = _lengths(lengths2, B, P2, p1.device, "lengths2")
     dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
-    with torch.cuda.device(p1.device):
+    with _on_device(p1.device):
         nbytes = _lib.load().tpg_knn_workspace_bytes(B, P1, P2, D, K)  # > 0: tensor-core (tcgen05) path
         ws = _ws(nbytes, p1.device) if nbytes else None
         _lib.call("tpg_knn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, _ptr(dists), _ptr(idx),
@@ -100,7 +119,7 @@ def frnn(p1, p2, K: int, r, lengths1=None, lengths2=None) -> Tuple[torch.Tensor,
         r_host = float(r)
     dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
-    with torch.cuda.device(p1.device):
+    with _on_device(p1.device):
         nbytes = _lib.load().tpg_frnn_workspace_bytes(B, P1, P2, D, K)
         ws = _ws(nbytes, p1.device)
         _lib.call("tpg_frnn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, r_host, _ptr(r_dev),
@@ -117,9 +136,11 @@ def ball_query(radius: float, nsample: int, xyz, new_xyz) -> torch.Tensor:
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
     idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _on_device(xyz.device):
+        nbytes = _lib.load().tpg_ball_query_workspace_bytes(B, N, M, int(nsample))  # > 0: uniform-grid search
+        ws = _ws(nbytes, xyz.device) if nbytes else None
         _lib.call("tpg_ball_query_f32", _ptr(xyz), _ptr(new_xyz), B, N, M, float(radius), int(nsample), _ptr(idx),
-                  _stream())
+                  _ptr(ws), nbytes, _stream())
     return idx
 
 
@@ -131,7 +152,7 @@ def fps(xyz, npoint: int) -> torch.Tensor:
         raise RuntimeError("furthest_point_sample expects xyz (B,N,3)")
     B, N, _ = xyz.shape
     out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _on_device(xyz.device):
         nbytes = _lib.load().tpg_fps_workspace_bytes(B, N)
         ws = _ws(nbytes, xyz.device)
         _lib.call("tpg_fps_f32", _ptr(xyz), B, N, int(npoint), _ptr(out), _ptr(ws), ws.numel() if nbytes else 0,
@@ -146,7 +167,7 @@ def fps_start(pts, k: int, start, return_rows: bool = False):
     start = torch.as_tensor(start, dtype=torch.int64, device=pts.device).expand(B).contiguous()
     out = torch.empty((B, k), dtype=torch.int64, device=pts.device)
     rows = torch.empty((B, k, N), dtype=torch.float32, device=pts.device) if return_rows else None
-    with torch.cuda.device(pts.device):
+    with _on_device(pts.device):
         nbytes = _lib.load().tpg_fps_workspace_bytes(B, N)
         ws = _ws(nbytes, pts.device)
         _lib.call("tpg_fps_start_f32", _ptr(pts), B, N, D, int(k), _ptr(start), _ptr(out), _ptr(rows), _ptr(ws),
@@ -168,7 +189,7 @@ def group_fwd(f, idx, center=None) -> torch.Tensor:
         if tuple(center.shape) != (B, C, M):
             raise RuntimeError("group_fwd: center must be [B,C,M]")
     out = torch.empty((B, C, M, k), dtype=torch.float32, device=f.device)
-    with torch.cuda.device(f.device):
+    with _on_device(f.device):
         _lib.call("tpg_group_fwd_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _stream())
     return out
 
@@ -180,7 +201,7 @@ def inverse_index(idx, N: int) -> Tuple[torch.Tensor, torch.Tensor]:
     L = idx.numel() // max(B, 1)
     off = torch.empty((B, N + 1), dtype=torch.int32, device=idx.device)
     items = torch.empty((B, max(L, 1)), dtype=torch.int32, device=idx.device)
-    with torch.cuda.device(idx.device):
+    with _on_device(idx.device):
         nbytes = _lib.load().tpg_inverse_index_workspace_bytes(B, N, L)
         ws = _ws(nbytes, idx.device)
         _lib.call("tpg_inverse_index_build", _ptr(idx), B, N, L, _ptr(off), _ptr(items), _ptr(ws), ws.numel(),
@@ -221,7 +242,7 @@ def group_bwd(grad_out, off, items, N: int) -> torch.Tensor:
     B, C = grad_out.shape[0], grad_out.shape[1]
     L = grad_out.numel() // max(B * C, 1)
     gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with _on_device(grad_out.device):
         _lib.call("tpg_group_bwd_f32", _ptr(grad_out), _ptr(off), _ptr(items), B, C, N, L, _ptr(gf), _stream())
     return gf
 
@@ -234,7 +255,7 @@ def group_reduce_fwd(f, idx, op: int = _lib.REDUCE_MAX, want_arg: bool = True):
     _, M, k = idx.shape
     out = torch.empty((B, C, M), dtype=torch.float32, device=f.device)
     arg = torch.empty((B, C, M), dtype=torch.int32, device=f.device) if (want_arg and op != _lib.REDUCE_SUM) else None
-    with torch.cuda.device(f.device):
+    with _on_device(f.device):
         _lib.call("tpg_group_reduce_fwd_f32", _ptr(f), _ptr(idx), B, C, N, M, k, int(op), _ptr(out), _ptr(arg),
                   _stream())
     return out, arg
@@ -244,7 +265,7 @@ def group_reduce_bwd(grad_out, arg, off, items, N: int, k: int, op: int) -> torc
     _req(grad_out, "grad_out", torch.float32, 3)
     B, C, M = grad_out.shape
     gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with _on_device(grad_out.device):
         _lib.call("tpg_group_reduce_bwd_f32", _ptr(grad_out), _ptr(arg), _ptr(off), _ptr(items), B, C, N, M, k,
                   int(op), _ptr(gf), _stream())
     return gf
@@ -258,7 +279,7 @@ def three_nn(unknown, known):
     m = known.shape[1]
     dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
-    with torch.cuda.device(unknown.device):
+    with _on_device(unknown.device):
         _lib.call("tpg_three_nn_f32", _ptr(unknown), _ptr(known), B, n, m, _ptr(dist), _ptr(idx), _stream())
     return dist, idx
 
@@ -270,7 +291,7 @@ def three_interpolate_fwd(f, idx, w):
     B, c, m = f.shape
     n = idx.shape[1]
     out = torch.empty((B, c, n), dtype=torch.float32, device=f.device)
-    with torch.cuda.device(f.device):
+    with _on_device(f.device):
         _lib.call("tpg_three_interpolate_fwd_f32", _ptr(f), _ptr(idx), _ptr(w), B, c, m, n, _ptr(out), _stream())
     return out
 
@@ -279,7 +300,7 @@ def three_interpolate_bwd(grad_out, w, off, items, m: int):
     _req(grad_out, "grad_out", torch.float32, 3)
     B, c, n = grad_out.shape
     gf = torch.empty((B, c, m), dtype=torch.float32, device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with _on_device(grad_out.device):
         _lib.call("tpg_three_interpolate_bwd_f32", _ptr(grad_out), _ptr(w), _ptr(off), _ptr(items), B, c, m, n,
                   _ptr(gf), _stream())
     return gf
@@ -299,7 +320,7 @@ def chamfer_fwd(src, tgt, directions: int, lengths_src=None, lengths_tgt=None):
     d_t = torch.empty((B, P2), dtype=torch.float32, device=dev) if r else None
     i_t = torch.empty((B, P2), dtype=torch.int32, device=dev) if r else None
     s_t = torch.empty((B,), dtype=torch.float32, device=dev) if r else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nbytes = _lib.load().tpg_chamfer_fwd_workspace_bytes(B, P1, P2, D)  # > 0: uniform-grid search
         ws = _ws(nbytes, dev) if nbytes else None
         _lib.call("tpg_chamfer_fwd_f32", _ptr(src), _ptr(tgt), _ptr(lengths_src), _ptr(lengths_tgt), B, P1, P2, D,
@@ -315,7 +336,7 @@ def chamfer_bwd(src, tgt, i_src, i_tgt, g_src, g_tgt, directions: int, need_src=
     dev = src.device
     gs = torch.empty_like(src) if need_src else None
     gt = torch.empty_like(tgt) if need_tgt else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nbytes = _lib.load().tpg_chamfer_bwd_workspace_bytes(B, P1, P2)
         ws = _ws(nbytes, dev)
         _lib.call("tpg_chamfer_bwd_f32", _ptr(src), _ptr(tgt), _ptr(lengths_src), _ptr(lengths_tgt), _ptr(i_src),
@@ -335,7 +356,7 @@ def cubic_interp(query, field, pos, cutoff: float) -> torch.Tensor:
     if pos.shape != (S, P, 3) or query.shape[2] != 3:
         raise ValueError("cubic_interp: expected query [S,Q,3], field [S,P,F], pos [S,P,3]")
     out = torch.empty((S, Q, F), dtype=torch.float32, device=query.device)
-    with torch.cuda.device(query.device):
+    with _on_device(query.device):
         nbytes = _lib.load().tpg_cubic_interp_workspace_bytes(S, Q, P)
         ws = _ws(nbytes, query.device)
         _lib.call("tpg_cubic_interp_f32", _ptr(query), _ptr(field), _ptr(pos), S, Q, P, F, float(cutoff), _ptr(out),
@@ -350,7 +371,7 @@ def gather_rows(x, idx) -> torch.Tensor:
     B, N, U = x.shape
     L = idx.shape[1]
     out = torch.empty((B, L, U), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.call("tpg_gather_rows_f32", _ptr(x), _ptr(idx), B, N, U, L, _ptr(out), _stream())
     return out
 

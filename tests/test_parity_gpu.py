@@ -281,6 +281,10 @@ def test_frnn_per_cloud_radius_and_lengths(F, oracle):
 @pytest.mark.parametrize("B,N,M,r,ns,kind", [
     (2, 1000, 128, 0.15, 32, "fluid"), (2, 512, 512, 0.05, 16, "fluid"), (1, 300, 50, 0.01, 8, "fluid"),
     (2, 600, 100, 0.3, 64, "action"), (1, 343, 343, 0.025, 8, "lattice"), (2, 400, 64, 0.1, 32, "dummy"),
+    # >= 8192 points: uniform-grid search, same index-ordered semantics
+    (2, 8192, 1024, 0.10, 32, "fluid"), (1, 8192, 1024, 0.15, 32, "fluid"), (1, 9261, 700, 0.025 * 1.0001, 16, "lattice"),
+    (1, 8192, 512, 0.1, 32, "dummy"), (1, 20000, 3000, 0.02, 16, "fluid"), (1, 8192, 100, 0.6, 16, "fluid"),
+    (1, 8192, 256, 0.05, 64, "fluid"),   # nsample > 32: scan path
 ])
 def test_ball_query_bit_exact(F, oracle, B, N, M, r, ns, kind):
     rng = np.random.default_rng(5)
@@ -305,6 +309,7 @@ def test_ball_query_bit_exact(F, oracle, B, N, M, r, ns, kind):
     (8, 8192, 1024, "fluid"),   # BASELINE config 2: one 8-CTA cluster per cloud
     (1, 2049, 64, "fluid"), (2, 4096, 256, "dup"), (1, 3000, 300, "dummy"), (1, 4913, 200, "lattice"),
     (1, 65536, 24, "fluid"), (1, 70000, 12, "fluid"),   # largest cluster case / global-memory kernel
+    (2, 32768, 40, "fluid"), (1, 16384, 64, "dup"),
     (2, 200, 64, "fluid"), (1, 40, 40, "dup"),
 ])
 def test_fps_pointnet2_bit_exact(F, oracle, B, N, npoint, kind):
