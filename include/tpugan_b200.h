@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 4
+#define TPG_ABI_VERSION 5
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -100,7 +100,7 @@ int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* lengths1,
  *   new_xyz) used inside QueryAndGroup — discriminator.py:190.
  * xyz [B,N,3], new_xyz [B,M,3] -> idx [B,M,nsample] int32: the `nsample`
  * LOWEST indices with d2 < radius^2, slots beyond the hit count repeat the
- * first hit, no hit -> all 0.  Clouds of >= 8192 points are searched through the
+ * first hit, no hit -> all 0.  Clouds of >= 16384 points are searched through the
  * uniform grid (workspace: tpg_ball_query_workspace_bytes(), else 0 / NULL).    */
 size_t tpg_ball_query_workspace_bytes(int B, int N, int M, int nsample);
 int tpg_ball_query_f32(const float* xyz, const float* new_xyz, int B, int N,
@@ -171,8 +171,10 @@ int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg,
  *   site in the reference tree).
  * unknown [B,n,3], known [B,m,3] -> dist [B,n,3] = sqrt(d2), idx [B,n,3] int32.
  * f [B,c,m], idx, w [B,n,3] -> out [B,c,n] = sum_k w_k f[idx_k].           */
+size_t tpg_three_nn_workspace_bytes(int B, int n, int m); /* > 0: grid search (m >= 2048) */
 int tpg_three_nn_f32(const float* unknown, const float* known, int B, int n,
-                     int m, float* dist, int32_t* idx, tpg_stream_t stream);
+                     int m, float* dist, int32_t* idx, void* workspace,
+                     size_t workspace_bytes, tpg_stream_t stream);
 int tpg_three_interpolate_fwd_f32(const float* f, const int32_t* idx,
                                   const float* w, int B, int c, int m, int n,
                                   float* out, tpg_stream_t stream);

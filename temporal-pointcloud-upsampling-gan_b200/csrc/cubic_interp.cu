@@ -144,6 +144,8 @@ struct CubicWs {
   int64_t* ni;
   unsigned char* mark;
   int* any_empty;
+  char* grid;
+  size_t grid_bytes;
   size_t total;
 };
 
@@ -155,6 +157,9 @@ static CubicWs carve(void* base, int S, int Q, int P) {
   w.nd = reinterpret_cast<float*>(p + o);   o += align_up(sizeof(float) * (size_t)S * Q * CI_K, 256);
   w.mark = reinterpret_cast<unsigned char*>(p + o); o += align_up((size_t)S * P, 256);
   w.any_empty = reinterpret_cast<int*>(p + o); o += align_up(sizeof(int) * (size_t)S, 256);
+  w.grid = p + o;
+  w.grid_bytes = grid_eligible(3, P, CI_K) ? grid_workspace_bytes(S, P) : 0;
+  o += align_up(w.grid_bytes, 256);
   w.total = o;
   return w;
 }
@@ -179,7 +184,7 @@ TPG_API int tpg_cubic_interp_f32(const float* query, const float* field, const f
   cudaStream_t st = as_stream(stream);
   CubicWs w = carve(workspace, S, Q, P);
   KnnArgs ka{query, pos, nullptr, nullptr, S, Q, P, 3, CI_K, cutoff, nullptr, 1, w.nd, w.ni, OUT_FRNN};
-  int rc = knn_dispatch(ka, st);
+  int rc = w.grid_bytes ? grid_knn_dispatch(ka, w.grid, w.grid_bytes, st) : knn_dispatch(ka, st);
   if (rc) return rc;
   TPG_CUDA(cudaMemsetAsync(w.mark, 0, (size_t)S * P, st));
   TPG_CUDA(cudaMemsetAsync(w.any_empty, 0, sizeof(int) * (size_t)S, st));

@@ -245,12 +245,19 @@ TPG_API int tpg_frnn_f32(const float* p1, const float* p2, const int64_t* length
   return knn_dispatch(a, as_stream(stream));
 }
 
+TPG_API size_t tpg_three_nn_workspace_bytes(int B, int n, int m) {
+  (void)n;
+  return grid_eligible(3, m, 3) ? grid_workspace_bytes(B, m) : 0;
+}
+
 TPG_API int tpg_three_nn_f32(const float* unknown, const float* known, int B, int n, int m,
-                             float* dist, int32_t* idx, tpg_stream_t stream) {
+                             float* dist, int32_t* idx, void* workspace, size_t workspace_bytes,
+                             tpg_stream_t stream) {
   TPG_REQUIRE(B >= 0 && n >= 0 && m >= 0, TPG_EINVAL, "three_nn: negative size");
   TPG_REQUIRE(B <= 65535, TPG_EUNSUPPORTED, "three_nn: B=%d > 65535", B);
   if (B == 0 || n == 0) return TPG_OK;
   TPG_REQUIRE(unknown && (known || m == 0) && dist && idx, TPG_EINVAL, "three_nn: null pointer");
   KnnArgs a{unknown, known, nullptr, nullptr, B, n, m, 3, 3, 0.f, nullptr, 0, dist, idx, OUT_THREE};
+  if (grid_eligible(3, m, 3)) return grid_knn_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   return knn_dispatch(a, as_stream(stream));
 }

@@ -14,7 +14,7 @@ LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
@@ -50,7 +50,8 @@ _PROTOS = {
     "tpg_group_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "tpg_group_reduce_fwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "tpg_group_reduce_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "tpg_three_nn_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "tpg_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
+    "tpg_three_nn_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_three_interpolate_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "tpg_three_interpolate_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "tpg_chamfer_fwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -280,7 +280,10 @@ def three_nn(unknown, known):
     dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
     with _on_device(unknown.device):
-        _lib.call("tpg_three_nn_f32", _ptr(unknown), _ptr(known), B, n, m, _ptr(dist), _ptr(idx), _stream())
+        nbytes = _lib.load().tpg_three_nn_workspace_bytes(B, n, m)
+        ws = _ws(nbytes, unknown.device) if nbytes else None
+        _lib.call("tpg_three_nn_f32", _ptr(unknown), _ptr(known), B, n, m, _ptr(dist), _ptr(idx), _ptr(ws), nbytes,
+                  _stream())
     return dist, idx
 
 

@@ -281,10 +281,11 @@ def test_frnn_per_cloud_radius_and_lengths(F, oracle):
 @pytest.mark.parametrize("B,N,M,r,ns,kind", [
     (2, 1000, 128, 0.15, 32, "fluid"), (2, 512, 512, 0.05, 16, "fluid"), (1, 300, 50, 0.01, 8, "fluid"),
     (2, 600, 100, 0.3, 64, "action"), (1, 343, 343, 0.025, 8, "lattice"), (2, 400, 64, 0.1, 32, "dummy"),
-    # >= 8192 points: uniform-grid search, same index-ordered semantics
-    (2, 8192, 1024, 0.10, 32, "fluid"), (1, 8192, 1024, 0.15, 32, "fluid"), (1, 9261, 700, 0.025 * 1.0001, 16, "lattice"),
-    (1, 8192, 512, 0.1, 32, "dummy"), (1, 20000, 3000, 0.02, 16, "fluid"), (1, 8192, 100, 0.6, 16, "fluid"),
-    (1, 8192, 256, 0.05, 64, "fluid"),   # nsample > 32: scan path
+    (2, 8192, 1024, 0.10, 32, "fluid"), (1, 9261, 700, 0.025 * 1.0001, 16, "lattice"),
+    # >= 16384 points: uniform-grid search, same index-ordered semantics
+    (2, 16384, 1024, 0.10, 32, "fluid"), (1, 16384, 1024, 0.15, 32, "fluid"), (1, 17576, 700, 0.025 * 1.0001, 16, "lattice"),
+    (1, 16384, 512, 0.1, 32, "dummy"), (1, 20000, 3000, 0.02, 16, "fluid"), (1, 16384, 100, 0.6, 16, "fluid"),
+    (1, 16384, 256, 0.05, 64, "fluid"),   # nsample > 32: scan path
 ])
 def test_ball_query_bit_exact(F, oracle, B, N, M, r, ns, kind):
     rng = np.random.default_rng(5)
@@ -439,7 +440,7 @@ def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
 
 
 # ----------------------------------------------------------------------------- three_nn / interpolate
-@pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2)])
+@pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2), (2, 3000, 2048), (1, 8192, 4096)])
 def test_three_nn_and_interpolate(F, oracle, B, n, m):
     rng = np.random.default_rng(13)
     unknown = synth.fluid_cloud(rng, B, n)
@@ -518,7 +519,9 @@ def test_chamfer_module_value_and_grad(oracle):
 
 # ----------------------------------------------------------------------------- cubic interpolation
 @pytest.mark.parametrize("S,Q,P,F_,cutoff,far", [(2, 400, 500, 3, 0.16, False), (1, 300, 300, 3, 0.04, False),
-                                               (2, 200, 600, 3, 0.05, True), (1, 100, 50, 6, 0.03, True)])
+                                               (2, 200, 600, 3, 0.05, True), (1, 100, 50, 6, 0.03, True),
+                                               (2, 3000, 4096, 3, 0.16 * 0.35, False),   # >= 2048 candidates: grid FRNN
+                                               (1, 2500, 2500, 3, 0.03, True)])
 def test_cubic_interp(F, oracle, S, Q, P, F_, cutoff, far):
     rng = np.random.default_rng(16)
     pos = synth.fluid_cloud(rng, S, P)
