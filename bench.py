@@ -39,9 +39,9 @@ METRIC = "kNN+group queries/s"
 UNIT = "queries/s"
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 # kernel launched by each schedule op (csrc/*.cu) — for the roofline object
-OP_KERNEL = {"knn": "knn_warp_kernel", "frnn": "knn_warp_kernel", "ball_query": "ball_query_kernel",
+OP_KERNEL = {"knn": "knn_feat_tc_kernel", "frnn": "grid_knn_kernel", "ball_query": "ball_query_kernel",
              "fps": "fps_reg_kernel", "gather": "group_fwd_kernel", "group": "group_fwd_kernel",
-             "group_bwd": "group_bwd_kernel", "gather_bwd": "group_bwd_kernel", "chamfer": "nn1_kernel",
+             "group_bwd": "group_bwd_kernel", "gather_bwd": "group_bwd_kernel", "chamfer": "grid_nn1_kernel",
              "chamfer_bwd": "chamfer_bwd_kernel"}
 # GAN-step gradient buckets all-reduced at N > 1 (G / tempo-D / spatial-D parameters)
 GRAD_BUCKETS = (439461, 738177, 308737)
@@ -348,10 +348,19 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     ach = op_bytes[dom] / (op_ms[dom] * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": OP_KERNEL[dom], "op": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-        "frac": ach / peak, "traffic": None,
+        "frac": ach / peak, "traffic": (traffic.get(OP_KERNEL[dom]) or {}).get("dram_bytes_per_launch"),
+        "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of one launch of this kernel)",
+        "note": ("FPS is a chain of npoint dependent arg-max rounds: latency-bound, its algorithmic bytes are tiny; "
+                 "see roofline_hbm_op for the largest bandwidth-bound op" if dom == "fps" else None),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
         "launches_per_step": op_calls[dom] // max(args.steps, 1),
         "avg_launch_us": op_ms[dom] * 1e3 / op_calls[dom],
@@ -360,6 +369,16 @@ def run_ours(args):
         "per_op_ms_per_step": {k: v / args.steps for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])},
         "per_op_gbs": {k: op_bytes[k] / (op_ms[k] * 1e-3) / 1e9 for k in op_ms},
     }
+    hbm_ops = [k for k in ("group", "group_bwd", "gather", "gather_bwd") if k in op_ms]
+    hop = max(hbm_ops, key=lambda k: op_bytes[k]) if hbm_ops else None
+    roofline_hbm = None
+    if hop:
+        a2 = op_bytes[hop] / (op_ms[hop] * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "kernel": OP_KERNEL[hop], "op": hop, "achieved": a2, "peak": peak, "unit": "GB/s",
+                        "frac": a2 / peak, "launches_per_step": op_calls[hop] // max(args.steps, 1),
+                        "avg_launch_us": op_ms[hop] * 1e3 / op_calls[hop],
+                        "alg_bytes_per_launch": op_bytes[hop] / op_calls[hop],
+                        "note": "average over every call of the step incl. small launch-bound ones; per-shape numbers: profiles/*_ops_sweep.md"}
     if args.per_call and rank == 0:
         agg = {}
         for ci, c in enumerate(doc["calls"]):
@@ -401,10 +420,11 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_replay(args.workload, args.cpu_sample_batch, 1, 0)
+        r = cpu_replay(args.workload, args.cpu_sample_batch, 6, 1)
         cpu_baseline = {"value": r["queries"] / r["s_per_step"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                        "sample": f"one pass of the {args.workload} schedule at batch {args.cpu_sample_batch} of "
-                                  f"{batch} clouds ({r['queries']} queries, {r['s_per_step']:.1f} s), C oracle + OpenMP"}
+                        "sample": f"6 passes (+1 warm-up) of the {args.workload} schedule at batch {args.cpu_sample_batch} of "
+                                  f"{batch} clouds ({r['queries']} queries and {r['s_per_step']:.2f} s per pass), "
+                                  f"C oracle with OpenMP"}
 
     if rank == 0:
         line = {
@@ -415,7 +435,7 @@ def run_ours(args):
             "train_step_hot_path_per_s": world * 1e3 / ms_res,
             "queries_per_step": total_queries,
             "cuda_graph": graph_info,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_hbm_op": roofline_hbm, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)

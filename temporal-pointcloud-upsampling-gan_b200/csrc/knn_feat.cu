@@ -1,4 +1,4 @@
-// knn_feat.cu — K2: feature-space kNN (D = 32..128) on the 5th-gen tensor cores.
+// knn_feat.cu — K2: feature-space kNN (D = 32 / 64) on the 5th-gen tensor cores.
 //
 // Replaces pytorch3d knn_points on the generator's dynamic-graph features
 // (gcn_lib/pointnet/gcn.py:200-203,258: D = 32/64, K = 4..20, P = 2048).
@@ -6,28 +6,27 @@
 // The distance matrix is a genuine dense contraction, so it goes to tcgen05:
 //   e[j][i] = |y_j|^2 - 2 <y_j, x_i>        (the |x_i|^2 term is constant per query)
 // with <y,x> from tcgen05.mma kind::tf32 (fp32 operands read as tf32, fp32 accumulate in
-// TMEM).  e only RANKS candidates; the neighbours that are returned are re-ranked with
-// the canonical distance (sequential fp32, no FMA), so indices and distances are bit-exact:
-//   * per query keep the 32 smallest e (approximate list);
-//   * with T_K the K-th smallest e and eps a rigorous bound on |e - E| + |d_canon - d_true|,
-//     every canonical top-K neighbour has e <= T_K + 2 eps (proof in DESIGN.md §K2); if the
-//     33rd-smallest e is provably beyond that margin the list is a superset and the K
+// TMEM).  e only SELECTS candidates; the neighbours that are returned are re-ranked with
+// the canonical distance (sequential fp32, no FMA), so indices and distances are identical
+// to the brute-force kernel:
+//   * a first pass over the e-matrix yields, per query, a valid upper bound tau0 of the
+//     (K+8)-th smallest e; a second pass buffers every candidate with e <= tau0;
+//   * with T_K the K-th smallest buffered e and eps a rigorous bound on
+//     |e - E| + |d_canon - d_true|, every canonical top-K neighbour has e <= T_K + 2 eps
+//     (proof in DESIGN.md §4 K2); if T_K + 2 eps < tau0 the buffer is a superset and the K
 //     results are the (d_canon, idx)-smallest of its members inside the margin;
-//   * otherwise (margin zone overflows the 32 slots: near-duplicate features, huge norms)
-//     the query is appended to a fallback list and recomputed by an exact SIMT warp scan.
+//   * otherwise (near-duplicate features, huge norms, buffer overflow) the query goes to
+//     an exact SIMT fallback (a fraction of a percent of the queries on N(0,1) features).
 //
-// Kernel anatomy (one CTA = 32 queries of one cloud, 4 warps):
-//   MMA shape M=128 (candidates) x N=32 (queries) x K=8 per instruction, cta_group::1.
-//   Candidates are the M operand on purpose: TMEM lane == candidate, so the 32 lanes of a
-//   warp hold 32 candidates' e-values for the same query in the same register — exactly
-//   the shape of a warp-ballot admission test + register-resident sorted list (WarpList).
-//   smem: 2 candidate stages (128 x D fp32, K-major, 128B-swizzled, filled with cp.async)
-//         + the query tile; TMEM: 2 x 32 columns (double-buffered accumulator).
-//   Per tile t: [tid 0] issue MMA(t+1) -> TMEM buf (t+1)&1, tcgen05.commit -> mbar;
-//               wait mbar(t); cp.async tile t+2 into the stage MMA(t) just released;
-//               tcgen05.ld buf t&1 -> registers; ballot/insert; one __syncthreads.
-//   The four warps see disjoint candidate quarters; they share their current 32nd-best
-//   through smem so each prunes with the tightest bound, and merge their lists at the end.
+// Kernel anatomy (one CTA = 128 queries of one cloud, 16 warps, one wave of CTAs):
+//   MMA shape M=128 (candidates) x N=128 (queries) x K=8 per instruction, cta_group::1.
+//   Candidates are the M operand on purpose: TMEM lane == candidate, so a thread owns one
+//   candidate row of the accumulator tile and sweeps its queries without any cross-lane
+//   operation.  smem: 3-stage ring of candidate tiles (128 x D fp32, K-major, 128B-swizzled,
+//   filled with cp.async, descriptors built by hand) + the query tile; TMEM: 2 x 128 columns
+//   (double-buffered accumulator); tcgen05.commit -> mbarrier per tile; tcgen05.ld.32x32b.x32.
+//   Per tile u: [tid 0] issue MMA(u+1); wait mbar(u); cp.async tile u+3 into the stage MMA(u)
+//   released; tcgen05.ld -> registers; per-lane min / predicated append; one __syncthreads.
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -41,7 +40,6 @@ constexpr int FT_NQ = 128;   // queries per CTA (UMMA N): 8 clouds x 16 CTAs = 1
 constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
 constexpr int FT_TMEM_COLS = 2 * FT_NQ;  // double-buffered accumulator (power of two >= 32)
 constexpr int FT_MAX_K = 24; // needs slack below the 32 list slots for the margin zone
-constexpr int FT_MAXGROUPS = 256;  // group-value slots per query (groups beyond that fold modulo)
 constexpr int FT_CAP = 64;         // candidate slots per query (all four lane quarters append to one buffer)
 constexpr int FT_STAGES = 3;       // candidate-tile ring: the load of tile u+3 has a full iteration to land
 
