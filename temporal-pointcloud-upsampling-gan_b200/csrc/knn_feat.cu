@@ -23,13 +23,19 @@
 //   Candidates are the M operand on purpose: TMEM lane == candidate, so a thread owns one
 //   candidate row of the accumulator tile and sweeps its queries without any cross-lane
 //   operation.  smem: 3-stage ring of candidate tiles (128 x D fp32, K-major, 128B-swizzled,
-//   filled with cp.async, descriptors built by hand) + the query tile; TMEM: 2 x 128 columns
-//   (double-buffered accumulator); tcgen05.commit -> mbarrier per tile; tcgen05.ld.32x32b.x32.
-//   Per tile u: [tid 0] issue MMA(u+1); wait mbar(u); cp.async tile u+3 into the stage MMA(u)
-//   released; tcgen05.ld -> registers; per-lane min / predicated append; one __syncthreads.
+//   filled by TMA: cp.async.bulk.tensor.2d, one box per 32-float K-slab, complete_tx on a
+//   per-stage mbarrier; UMMA descriptors built by hand) + the query tile; TMEM: 4 x 128 columns
+//   (the issue-to-commit latency of a tile is ~2000 cycles although the tensor pipe is busy for
+//   ~180 of them, so three MMAs are kept in flight).  mbarrier pipeline, no CTA barrier in the loop:
+//     full[stage]   TMA -> MMA issuer        tile landed
+//     done[buf]     tcgen05.commit -> all     accumulator ready, smem stage free
+//     tfree[buf]    16 warps -> MMA issuer    accumulator drained (tcgen05.ld complete)
+//   Per tile u: [tid 0] wait full/tfree, issue MMA(u+3); all: wait done(u); [tid 0] TMA tile u+4;
+//   tcgen05.ld -> registers; per-lane min / predicated append; arrive tfree(u).
 #include "common.cuh"
 #include "internal.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 namespace tpg {
@@ -38,10 +44,11 @@ constexpr int FT_THREADS = 512;
 constexpr int FT_TM = 128;   // candidates per tile (UMMA M)
 constexpr int FT_NQ = 128;   // queries per CTA (UMMA N): 8 clouds x 16 CTAs = 128 CTAs, one wave on 148 SMs
 constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
-constexpr int FT_TMEM_COLS = 2 * FT_NQ;  // double-buffered accumulator (power of two >= 32)
+constexpr int FT_NBUF = 4;             // TMEM accumulator buffers: MMA(u+1..u+3) in flight while tile u is consumed
+constexpr int FT_TMEM_COLS = FT_NBUF * FT_NQ;  // 512 columns: all of TMEM (one CTA per SM)
 constexpr int FT_MAX_K = 24; // needs slack below the 32 list slots for the margin zone
-constexpr int FT_CAP = 64;         // candidate slots per query (all four lane quarters append to one buffer)
-constexpr int FT_STAGES = 3;       // candidate-tile ring: the load of tile u+3 has a full iteration to land
+constexpr int FT_CAP = 60;         // candidate slots per query (all four lane quarters append to one buffer)
+constexpr int FT_STAGES = 4;       // candidate-tile ring: tiles u+1..u+3 feed the MMAs in flight, u+4 is loading
 
 struct FeatArgs {
   const float* p1;
@@ -57,6 +64,10 @@ struct FeatArgs {
   int* fb_count;           // [1]
   int* fb_list;            // [B*P1]
   long long* dbg;          // [ctas][8] phase timestamps (tools/bench_knn_feat.py)
+};
+
+struct FeatMaps {  // TMA descriptors: [B*P, D] fp32, box 32 floats x 128 rows, 128B swizzle
+  CUtensorMap cand, query;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -75,7 +86,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // bounded spin: a descriptor bug must surface as a trap, never as a hung GPU
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -87,6 +98,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (ok) return;
   }
   __trap();
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// one 32-float x 128-row box of a [rows, D] fp32 matrix -> 128B-swizzled K-major slab (16 KB)
+__device__ __forceinline__ void tma_load_slab(uint32_t dst, const CUtensorMap* map, int col, int row, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(map), "r"(col), "r"(row), "r"(bar)
+      : "memory");
 }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
@@ -240,9 +265,12 @@ __global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int 
 // T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset (else -> fallback);
 // (F2) all threads evaluate the canonical distance of the (query, candidate) pairs; (F3) per
 // query, rank by (d_canon, idx) and write the K best.
-__global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, const __grid_constant__ FeatMaps maps) {
   extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
-  __shared__ __align__(8) uint64_t mbar_s[2];
+  __shared__ __align__(8) uint64_t mbar_s[FT_NBUF];       // MMA(u) done (tcgen05.commit), per TMEM buffer
+  __shared__ __align__(8) uint64_t full_s[FT_STAGES];     // candidate tile landed (TMA complete_tx), per smem stage
+  __shared__ __align__(8) uint64_t qfull_s;               // query tile landed
+  __shared__ __align__(8) uint64_t tfree_s[FT_NBUF];      // all 16 warps have drained the TMEM buffer
   __shared__ uint32_t tmem_base_s;
   __shared__ float tau0_s[FT_NQ];
   __shared__ int cnt_s[FT_NQ];
@@ -272,27 +300,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
   const float* p2b = a.p2 + (size_t)b * a.P2 * D;
   const float* p1b = a.p1 + (size_t)b * a.P1 * D;
 
-  // tile fill: thread -> (row r0 + i*rstep, chunk c) with c and (r & 7) fixed per thread, so the
-  // swizzled destination and the source advance by constants (256 % cpr == 0 for D = 32/64/128)
-  const int lt_c = tid % cpr, lt_r0 = tid / cpr, lt_rstep = FT_THREADS / cpr;
-  const uint32_t lt_dst0 = (uint32_t)(lt_c >> 3) * atomA + (uint32_t)lt_r0 * 128u + (uint32_t)(((lt_c & 7) ^ (lt_r0 & 7)) << 4);
+  // candidate tile t -> smem stage: one TMA box per 32-float K-slab, issued by ONE thread; rows of
+  // the next cloud that ride along in a ragged last tile are masked by their +inf norm
+  const int slabs = D >> 5;
   auto load_tile = [&](int t, int stage) {
-    const uint32_t sb = base + (uint32_t)stage * stage_bytes + lt_dst0;
-    const float* src0 = p2b + (size_t)(t * FT_TM + lt_r0) * D + lt_c * 4;
-    const size_t sstep = (size_t)lt_rstep * D;
-    if ((t + 1) * FT_TM <= n2) {  // full tile: no predicates
-#pragma unroll 4
-      for (int i = 0; i < FT_TM / lt_rstep; ++i) cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, src0 + i * sstep, 16);
-    } else {
-      const int rows_left = n2 - t * FT_TM - lt_r0;  // row valid iff i*rstep < rows_left
-      for (int i = 0; i < FT_TM / lt_rstep; ++i) {
-        const bool ok = i * lt_rstep < rows_left;
-        cp_async16(sb + (uint32_t)(i * lt_rstep) * 128u, ok ? src0 + i * sstep : p2b, ok ? 16 : 0);
-      }
-    }
+    const uint32_t bar = smem_u32(&full_s[stage]);
+    mbar_expect_tx(bar, stage_bytes);
+    for (int sl = 0; sl < slabs; ++sl)
+      tma_load_slab(base + (uint32_t)stage * stage_bytes + (uint32_t)sl * atomA, &maps.cand, sl * 32, b * a.P2 + t * FT_TM, bar);
   };
 
-  long long* dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long* dbg = a.dbg ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
   if (dbg && tid == 0) dbg[0] = clock64();
   // ---- setup ----
   if (warp == 0) {
@@ -302,37 +320,37 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&mbar_s[0]), 1);
-    mbar_init(smem_u32(&mbar_s[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  {
-    const int total = FT_NQ * cpr;
-    for (int g = tid; g < total; g += FT_THREADS) {
-      const int r = g / cpr, c = g - r * cpr;
-      const int qi = q0 + r;
-      const bool ok = qi < n1;
-      const float* src = p1b + (size_t)(ok ? qi : 0) * D + c * 4;
-      const uint32_t dst = qtile + (uint32_t)(c >> 3) * atomB + (uint32_t)r * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
-      cp_async16(dst, src, ok ? 16 : 0);
+    for (int st = 0; st < FT_NBUF; ++st) {
+      mbar_init(smem_u32(&mbar_s[st]), 1);
+      mbar_init(smem_u32(&tfree_s[st]), FT_THREADS / 32);
     }
+    for (int st = 0; st < FT_STAGES; ++st) mbar_init(smem_u32(&full_s[st]), 1);
+    mbar_init(smem_u32(&qfull_s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   const int U = 2 * T;
   unsigned char* aux = base_ptr + (uint32_t)FT_STAGES * stage_bytes + (uint32_t)D * 4u * FT_NQ;
-  float* gval_s = reinterpret_cast<float*>(aux);    // pass 0 -> select: [FT_NQ][128] group minima
+  float* gval_s = reinterpret_cast<float*>(aux);    // pass 0 -> select: [FT_NQ][64] group minima
   float2* buf_s = reinterpret_cast<float2*>(aux);   // pass 1: [FT_NQ][FT_CAP] (e, idx) — aliases gval_s
   for (int g = tid; g < FT_NQ; g += FT_THREADS) cnt_s[g] = 0;
 
-  for (int u0 = 0; u0 < FT_STAGES && u0 < U; ++u0) load_tile(u0 % T, u0);
-  cp_async_wait_all();
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    mbar_expect_tx(smem_u32(&qfull_s), (uint32_t)D * 4u * FT_NQ);
+    for (int sl = 0; sl < slabs; ++sl)
+      tma_load_slab(qtile + (uint32_t)sl * atomB, &maps.query, sl * 32, b * a.P1 + q0, smem_u32(&qfull_s));
+    for (int u0 = 0; u0 < FT_STAGES && u0 < U; ++u0) load_tile(u0 % T, u0);
+  }
 
+  // [tid 0] MMA(u): needs tile u in smem and TMEM buffer u&1 drained by the epilogue of u-2
   auto issue_mma = [&](int u) {
-    const int s = u & 1;  // TMEM buffer / mbarrier
+    const int s = u % FT_NBUF;  // TMEM buffer / mbarrier
+    mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
+    if (u >= FT_NBUF) mbar_wait(smem_u32(&tfree_s[s]), (uint32_t)((u / FT_NBUF - 1) & 1));
+    tc_fence_after();
     const uint32_t sb = base + (uint32_t)(u % FT_STAGES) * stage_bytes;
     const uint32_t td = tmem_base + (uint32_t)s * FT_NQ;
     const int ksteps = D >> 3;
@@ -344,7 +362,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
     }
     umma_commit(smem_u32(&mbar_s[s]));
   };
-  if (tid == 0 && U > 0) issue_mma(0);
+  if (tid == 0) mbar_wait(smem_u32(&qfull_s), 0u);
+  if (tid == 0)
+    for (int u0 = 0; u0 < FT_NBUF - 1 && u0 < U; ++u0) issue_mma(u0);
   if (dbg && tid == 0) dbg[1] = clock64();
 
   // pass 0: running group minima; pass 1: admission bounds of this warp's 32 queries
@@ -355,23 +375,26 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
     const bool list_pass = u >= T;
-    if (tid == 0 && u + 1 < U) issue_mma(u + 1);
+    if (tid == 0 && u + FT_NBUF - 1 < U) issue_mma(u + FT_NBUF - 1);
     if (u == T) {
       if (dbg && tid == 0) dbg[2] = clock64();
 #pragma unroll
-      for (int n = 0; n < FT_QW; ++n) gval_s[(nq0 + n) * 128 + quarter * 32 + lane] = reg[n];
+      for (int n = 0; n < FT_QW; ++n) {  // 64 groups per query: lanes l and l^16 merge (halves the smem footprint)
+        const float m2 = fminf(reg[n], __shfl_xor_sync(FULL, reg[n], 16));
+        if (lane < 16) gval_s[(nq0 + n) * 64 + quarter * 16 + lane] = m2;
+      }
       __syncthreads();
       // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
       //      processed together so their (dependent) radix steps overlap
       constexpr int QPW = FT_NQ / (FT_THREADS / 32);
       const int R = min(32, K + 8);
-      unsigned uk[QPW][4];
+      unsigned uk[QPW][2];
 #pragma unroll
       for (int qq = 0; qq < QPW; ++qq)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 128 + v * 32 + lane]);
+        for (int v = 0; v < 2; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 64 + v * 32 + lane]);
       unsigned bound[QPW];
-      warp_radix_bound16_multi<QPW, 4>(uk, R, bound);
+      warp_radix_bound16_multi<QPW, 2>(uk, R, bound);
       __syncthreads();  // gval_s is dead from here on: buf_s may overwrite it
       if (lane == 0)
 #pragma unroll
@@ -383,12 +406,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
     }
     const int j = t * FT_TM + quarter * 32 + lane;
     const float ncj = j < n2 ? __ldg(a.nrm2 + (size_t)b * a.P2 + j) : INF;
-    mbar_wait(smem_u32(&mbar_s[u & 1]), (uint32_t)((u >> 1) & 1));
+    mbar_wait(smem_u32(&mbar_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF) & 1));
     tc_fence_after();
-    if (u + FT_STAGES < U) load_tile((u + FT_STAGES) % T, u % FT_STAGES);  // MMA(u) has released this stage
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (tid == 0 && u + FT_STAGES < U) load_tile((u + FT_STAGES) % T, u % FT_STAGES);  // MMA(u) has released this stage
     uint32_t acc[FT_QW];
-    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u & 1) * FT_NQ + nq0), acc);
+    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u % FT_NBUF) * FT_NQ + nq0), acc);
     if (!list_pass) {
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) reg[n] = fminf(reg[n], fmaf(-2.0f, __uint_as_float(acc[n]), ncj));
@@ -403,13 +425,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a) 
         }
       }
     }
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile u+2 (issued last iteration) has landed
-    fence_proxy_async();
+    // this warp has drained TMEM buffer u&1 (tcgen05.wait::ld inside tmem_ld32): MMA(u+2) may overwrite it.
+    // No CTA-wide barrier in the loop: warps run ahead until the next MMA-done barrier.
     tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&tfree_s[u % FT_NBUF]));
   }
-  cp_async_wait_all();
   __syncthreads();
   if (dbg && tid == 0) dbg[4] = clock64();
 
@@ -621,9 +642,41 @@ static FeatWs feat_carve(void* base, int B, int P1, int P2) {
   w.nrm1 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P1, 256);
   w.nrm2 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P2, 256);
   w.fb_list = reinterpret_cast<int*>(p + o);    o += align_up(sizeof(int) * (size_t)B * P1, 256);
-  w.dbg = reinterpret_cast<long long*>(p + o);  o += align_up(sizeof(long long) * 8 * (size_t)B * (size_t)((P1 + FT_NQ - 1) / FT_NQ), 256);
+  w.dbg = reinterpret_cast<long long*>(p + o);  o += align_up(sizeof(long long) * 16 * (size_t)B * (size_t)((P1 + FT_NQ - 1) / FT_NQ), 256);
   w.total = o;
   return w;
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeFn>(p);
+  }
+  return fn;
+}
+
+// [rows, D] fp32 row-major -> boxes of 32 floats x 128 rows, 128B swizzle (the K-major UMMA slab layout)
+static bool make_feat_map(CUtensorMap* m, const float* ptr, long long rows, int D) {
+  TmapEncodeFn fn = tmap_encoder();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)D * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static bool feat_enabled() {
@@ -642,6 +695,7 @@ bool knn_feat_eligible(const KnnArgs& a) {
   if (a.K > FT_MAX_K || a.P2 < 1024) return false;  // below that the brute-force kernel is as fast
   if ((long long)a.B * a.P1 >= (1LL << 31)) return false;
   if ((reinterpret_cast<uintptr_t>(a.p1) | reinterpret_cast<uintptr_t>(a.p2)) & 15) return false;
+  if (!tmap_encoder()) return false;  // no TMA descriptor encoder: SIMT path
   return true;
 }
 
@@ -667,11 +721,15 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   }
   FeatArgs a{k.p1, k.p2, k.len1, k.len2, k.B, k.P1, k.P2, k.D, k.K, w.nrm1, w.nrm2, w.nmax2,
              k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr};
-  const size_t aux = max((size_t)FT_NQ * 128 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
+  const size_t aux = max((size_t)FT_NQ * 64 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
   const size_t smem = (size_t)k.D * 512 * FT_STAGES + (size_t)k.D * 4 * FT_NQ + 1024 + aux;
   TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k.P1, FT_NQ), k.B);
-  knn_feat_tc_kernel<<<grid, FT_THREADS, smem, st>>>(a);
+  FeatMaps maps;
+  TPG_REQUIRE(make_feat_map(&maps.cand, k.p2, (long long)k.B * k.P2, k.D) &&
+                  make_feat_map(&maps.query, k.p1, (long long)k.B * k.P1, k.D),
+              TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
+  knn_feat_tc_kernel<<<grid, FT_THREADS, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
   if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms() * 4, 256, 0, st>>>(a);
   else knn_feat_fallback_kernel<16><<<num_sms() * 4, 256, 0, st>>>(a);

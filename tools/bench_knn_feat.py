@@ -20,8 +20,8 @@ for (B, P, D, K) in [(8, 2048, 32, 20), (8, 2048, 64, 12), (8, 2048, 32, 9), (8,
         b.record(); torch.cuda.synchronize()
         assert rc == 0, lib.tpg_last_error()
     nct = B * ((P + 127) // 128)
-    dbg_bytes = ((8 * 8 * nct + 255) // 256) * 256
-    dbg = ws[n - dbg_bytes: n - dbg_bytes + 64 * nct].view(torch.int64).view(nct, 8).cpu().numpy()
+    dbg_bytes = ((16 * 8 * nct + 255) // 256) * 256
+    dbg = ws[n - dbg_bytes: n - dbg_bytes + 128 * nct].view(torch.int64).view(nct, 16).cpu().numpy()
     ph = np.diff(dbg[:, :6], axis=1)
     names = ["setup", "pass0", "tau0-select", "pass1", "final"]
     print(f"B={B} P={P} D={D} K={K}: call {a.elapsed_time(b) * 1e3:.1f} us; per-CTA cycles (mean/max): " +

@@ -36,7 +36,12 @@ def launches(tag):
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        v = float(row["Metric Value"].replace(",", ""))
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if v != v:  # ncu occasionally reports nan for a launch
+            continue
         v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
         k = row["Kernel Name"].split("(")[0].replace("void ", "")
         agg[k][0] += 1
