@@ -40,7 +40,8 @@
 
 namespace tpg {
 
-constexpr int FT_THREADS = 512;
+constexpr int FT_THREADS = 512;   // 16 epilogue warps (4 per TMEM lane quarter)
+constexpr int FT_BLOCK = FT_THREADS + 64;  // + one warp that only issues the MMAs + one that only issues the TMA loads
 constexpr int FT_TM = 128;   // candidates per tile (UMMA M)
 constexpr int FT_NQ = 128;   // queries per CTA (UMMA N): 8 clouds x 16 CTAs = 128 CTAs, one wave on 148 SMs
 constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
@@ -86,14 +87,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // bounded spin: a descriptor bug must surface as a trap, never as a hung GPU
-  for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)  // suspend up to 20 us per poll instead of spinning
+        : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
   }
@@ -113,6 +114,9 @@ __device__ __forceinline__ void tma_load_slab(uint32_t dst, const CUtensorMap* m
       "l"(map), "r"(col), "r"(row), "r"(bar)
       : "memory");
 }
+
+// barrier among the 16 epilogue warps only (the MMA-issuer warp never joins it)
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
 //   start address >> 4 | LBO(=1, unused for swizzled K-major) << 16 | SBO(1024 B) >> 4 << 32
@@ -265,7 +269,7 @@ __global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int 
 // T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset (else -> fallback);
 // (F2) all threads evaluate the canonical distance of the (query, candidate) pairs; (F3) per
 // query, rank by (d_canon, idx) and write the K best.
-__global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, const __grid_constant__ FeatMaps maps) {
+__global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, const __grid_constant__ FeatMaps maps) {
   extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
   __shared__ __align__(8) uint64_t mbar_s[FT_NBUF];       // MMA(u) done (tcgen05.commit), per TMEM buffer
   __shared__ __align__(8) uint64_t full_s[FT_STAGES];     // candidate tile landed (TMA complete_tx), per smem stage
@@ -351,20 +355,54 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
     mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
     if (u >= FT_NBUF) mbar_wait(smem_u32(&tfree_s[s]), (uint32_t)((u / FT_NBUF - 1) & 1));
     tc_fence_after();
-    const uint32_t sb = base + (uint32_t)(u % FT_STAGES) * stage_bytes;
     const uint32_t td = tmem_base + (uint32_t)s * FT_NQ;
+    // descriptors differ from their stage base only in the 14-bit start-address field (>> 4)
+    const uint64_t ad0 = umma_desc_sw128(base + (uint32_t)(u % FT_STAGES) * stage_bytes);
+    const uint64_t bd0 = umma_desc_sw128(qtile);
     const int ksteps = D >> 3;
     for (int kk = 0; kk < ksteps; ++kk) {
-      const uint32_t off = (uint32_t)(kk & 3) * 32u;
-      const uint64_t ad = umma_desc_sw128(sb + (uint32_t)(kk >> 2) * atomA + off);
-      const uint64_t bd = umma_desc_sw128(qtile + (uint32_t)(kk >> 2) * atomB + off);
-      umma_tf32(td, ad, bd, kk > 0 ? 1u : 0u);
+      const uint64_t off = (uint64_t)(((uint32_t)(kk >> 2) * atomA + (uint32_t)(kk & 3) * 32u) >> 4);
+      umma_tf32(td, ad0 + off, bd0 + off, kk > 0 ? 1u : 0u);  // atomA == atomB (128 rows x 128 B)
     }
     umma_commit(smem_u32(&mbar_s[s]));
   };
-  if (tid == 0) mbar_wait(smem_u32(&qfull_s), 0u);
-  if (tid == 0)
-    for (int u0 = 0; u0 < FT_NBUF - 1 && u0 < U; ++u0) issue_mma(u0);
+  if (warp == FT_THREADS / 32 + 1) {
+    // ===== TMA-producer warp: refills a stage the moment the MMA that read it has completed =====
+    if (lane == 0) {
+      for (int u = 0; u + FT_STAGES < U; ++u) {
+        mbar_wait(smem_u32(&mbar_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF) & 1));
+        load_tile((u + FT_STAGES) % T, u % FT_STAGES);
+      }
+    }
+    __syncwarp();
+    __syncthreads();
+    return;
+  }
+  if (warp == FT_THREADS / 32) {
+    // ===== MMA-issuer warp: one thread feeds the tensor pipe as fast as tiles land and accumulators
+    //       drain; it does no epilogue work, so issue never waits behind this warp's own share =====
+    if (lane == 0) {
+      mbar_wait(smem_u32(&qfull_s), 0u);
+      if (dbg) {  // tuning: where the issuer's time goes (tools/bench_knn_feat.py)
+        long long tf = 0, tt = 0, ti = 0;
+        for (int u = 0; u < U; ++u) {
+          const long long c0 = clock64();
+          mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
+          const long long c1 = clock64();
+          if (u >= FT_NBUF) mbar_wait(smem_u32(&tfree_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF - 1) & 1));
+          const long long c2 = clock64();
+          issue_mma(u);
+          tf += c1 - c0; tt += c2 - c1; ti += clock64() - c2;
+        }
+        dbg[8] = tf; dbg[9] = tt; dbg[10] = ti;
+      } else {
+        for (int u = 0; u < U; ++u) issue_mma(u);
+      }
+    }
+    __syncwarp();
+    __syncthreads();  // joins the epilogue warps before the TMEM dealloc
+    return;
+  }
   if (dbg && tid == 0) dbg[1] = clock64();
 
   // pass 0: running group minima; pass 1: admission bounds of this warp's 32 queries
@@ -375,7 +413,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
     const bool list_pass = u >= T;
-    if (tid == 0 && u + FT_NBUF - 1 < U) issue_mma(u + FT_NBUF - 1);
     if (u == T) {
       if (dbg && tid == 0) dbg[2] = clock64();
 #pragma unroll
@@ -383,7 +420,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
         const float m2 = fminf(reg[n], __shfl_xor_sync(FULL, reg[n], 16));
         if (lane < 16) gval_s[(nq0 + n) * 64 + quarter * 16 + lane] = m2;
       }
-      __syncthreads();
+      epi_sync();
       // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
       //      processed together so their (dependent) radix steps overlap
       constexpr int QPW = FT_NQ / (FT_THREADS / 32);
@@ -395,11 +432,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
         for (int v = 0; v < 2; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 64 + v * 32 + lane]);
       unsigned bound[QPW];
       warp_radix_bound16_multi<QPW, 2>(uk, R, bound);
-      __syncthreads();  // gval_s is dead from here on: buf_s may overwrite it
+      epi_sync();  // gval_s is dead from here on: buf_s may overwrite it
       if (lane == 0)
 #pragma unroll
         for (int qq = 0; qq < QPW; ++qq) tau0_s[warp * QPW + qq] = ordered_key_inv(bound[qq]);
-      __syncthreads();
+      epi_sync();
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) reg[n] = tau0_s[nq0 + n];
       if (dbg && tid == 0) dbg[3] = clock64();
@@ -408,7 +445,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
     const float ncj = j < n2 ? __ldg(a.nrm2 + (size_t)b * a.P2 + j) : INF;
     mbar_wait(smem_u32(&mbar_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF) & 1));
     tc_fence_after();
-    if (tid == 0 && u + FT_STAGES < U) load_tile((u + FT_STAGES) % T, u % FT_STAGES);  // MMA(u) has released this stage
     uint32_t acc[FT_QW];
     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((u % FT_NBUF) * FT_NQ + nq0), acc);
     if (!list_pass) {
@@ -431,7 +467,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&tfree_s[u % FT_NBUF]));
   }
-  __syncthreads();
+  epi_sync();
   if (dbg && tid == 0) dbg[4] = clock64();
 
   // ---- F1: per query (QPW per warp): margin, superset check, candidate list ----
@@ -491,7 +527,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
     }
     if (lane == 0) ncand_s[n] = ncand;
   }
-  __syncthreads();
+  epi_sync();
 
   // ---- F2: canonical distances of all (query, candidate) pairs, spread over every thread ----
   for (int pr0 = tid; pr0 < FT_NQ * 32; pr0 += 2 * FT_THREADS) {  // two independent chains per thread
@@ -514,7 +550,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) knn_feat_tc_kernel(FeatArgs a, 
     if (vA) dcan_s[prA] = accA;
     if (vB) dcan_s[prB] = accB;
   }
-  __syncthreads();
+  epi_sync();
 
   // ---- F3: rank by (d_canon, idx), write the K best ----
   for (int qq = 0; qq < QPW; ++qq) {
@@ -729,7 +765,7 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_REQUIRE(make_feat_map(&maps.cand, k.p2, (long long)k.B * k.P2, k.D) &&
                   make_feat_map(&maps.query, k.p1, (long long)k.B * k.P1, k.D),
               TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
-  knn_feat_tc_kernel<<<grid, FT_THREADS, smem, st>>>(a, maps);
+  knn_feat_tc_kernel<<<grid, FT_BLOCK, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
   if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms() * 4, 256, 0, st>>>(a);
   else knn_feat_fallback_kernel<16><<<num_sms() * 4, 256, 0, st>>>(a);
