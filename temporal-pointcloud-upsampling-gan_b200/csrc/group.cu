@@ -17,6 +17,8 @@
 //   turns idx into a CSR (for every source point n: the ascending list of flat
 //   positions that read it); grad_f[b,c,n] is then a private sequential sum —
 //   no atomics, deterministic, and the CSR is reused by every op sharing the idx.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -379,6 +381,185 @@ __global__ void __launch_bounds__(1024) csr_stable_kernel(const int32_t* __restr
   }
 }
 
+// ---- inverse index, stable build over a thread-block cluster (Q CTAs per cloud) ---------------
+// Same scheme as csr_stable_kernel, with the positions of a cloud cut into Q * 32 contiguous chunks
+// (CTA r of the cluster owns chunks r*32 .. r*32+31, one per warp), so a warp walks L / (32 Q)
+// positions instead of L / 32.  The only cross-CTA step is the per-key prefix over CTAs: every CTA
+// publishes its per-key totals in shared memory, and after one cluster barrier each CTA reads its
+// peers' totals through DSMEM.  Deterministic, stable, no atomics.
+template <typename CT>
+__global__ void __launch_bounds__(1024, 1) csr_cluster_kernel(const int32_t* __restrict__ idx,
+                                                              const int64_t* __restrict__ item_len, int N, int L, int Q,
+                                                              int32_t* __restrict__ off_g,
+                                                              int32_t* __restrict__ items_g) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char csr_smem[];
+  __shared__ int warp_tot[32];
+  constexpr int W = 32, T = 1024;
+  const int r = (int)cluster.block_rank(), b = blockIdx.x / Q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Np = (N + 3) & ~3;
+  int32_t* off_s = reinterpret_cast<int32_t*>(csr_smem);        // [Np]  slot of the first item of (this CTA, key)
+  int32_t* tot_s = off_s + Np;                                   // [Np]  per-key count of this CTA (read by peers)
+  CT* cnt = reinterpret_cast<CT*>(tot_s + Np);                   // [W][N]
+  unsigned char* tag = reinterpret_cast<unsigned char*>(cnt + (size_t)W * N);  // [W][N]
+  const int Lb = item_len ? (int)min((long long)item_len[b], (long long)L) : L;
+  const int32_t* ib = idx + (size_t)b * L;
+  int32_t* itb = items_g + (size_t)b * L;
+  int32_t* ob = off_g + (size_t)b * (N + 1);
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(cnt);
+    const int words = (int)(((size_t)W * N * sizeof(CT) + 3) / 4);
+    for (int e = tid; e < words; e += T) z[e] = 0u;
+  }
+  __syncthreads();
+  const int CL = (((Lb + Q * W - 1) / (Q * W)) + 31) & ~31;
+  const int l_lo = min(Lb, (r * W + warp) * CL), l_hi = min(Lb, l_lo + CL);
+  CT* mycnt = cnt + (size_t)warp * N;
+  unsigned char* mytag = tag + (size_t)warp * N;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int l0 = l_lo; l0 < l_hi; l0 += 128) {
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * 32 + lane;
+      keys[u] = l < l_hi ? __ldg(ib + l) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (l0 + u * 32 >= l_hi) break;  // (warp-uniform)
+      const int key = keys[u];
+      const bool valid = key >= 0 && key < N;
+      const unsigned m = same_key_mask(mytag, key, valid, lane, N);
+      if (valid && (m & lt) == 0) mycnt[key] = (CT)(mycnt[key] + __popc(m));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // per key: exclusive prefix over this CTA's warps, CTA total published for the peers
+  const int KPT = (N + T - 1) / T;  // <= 3
+  const int k0 = tid * KPT, k1 = min(N, k0 + KPT);
+  for (int key = k0; key < k1; ++key) {
+    int tot = 0;
+#pragma unroll 8
+    for (int w = 0; w < W; ++w) {
+      const int c = cnt[(size_t)w * N + key];
+      cnt[(size_t)w * N + key] = (CT)tot;
+      tot += c;
+    }
+    tot_s[key] = tot;
+  }
+  cluster.sync();
+  int ktot[3], kbase[3], mine = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ktot[i] = kbase[i] = 0;
+    const int key = k0 + i;
+    if (i < KPT && key < k1) {
+      for (int q = 0; q < Q; ++q) {
+        const int t = cluster.map_shared_rank(tot_s, q)[key];
+        ktot[i] += t;
+        if (q < r) kbase[i] += t;
+      }
+      mine += ktot[i];
+    }
+  }
+  cluster.barrier_arrive();  // this CTA no longer reads its peers' shared memory
+  int v = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += t;
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  int run = v - mine + (warp > 0 ? warp_tot[warp - 1] : 0);  // exclusive prefix of this thread's first key
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int key = k0 + i;
+    if (i < KPT && key < k1) {
+      off_s[key] = run + kbase[i];
+      if (r == 0) ob[key] = run;
+      run += ktot[i];
+    }
+  }
+  if (r == 0 && k1 == N && k0 < N) ob[N] = run;
+  __syncthreads();
+  for (int l0 = l_lo; l0 < l_hi; l0 += 128) {
+    int keys[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * 32 + lane;
+      keys[u] = l < l_hi ? __ldg(ib + l) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (l0 + u * 32 >= l_hi) break;
+      const int key = keys[u];
+      const int l = l0 + u * 32 + lane;
+      const bool valid = key >= 0 && key < N;
+      const unsigned m = same_key_mask(mytag, key, valid, lane, N);
+      int base = 0;
+      if (valid) base = off_s[key] + (int)mycnt[key];
+      __syncwarp();
+      if (valid) {
+        itb[base + __popc(m & lt)] = l;
+        if ((m & lt) == 0) mycnt[key] = (CT)(mycnt[key] + __popc(m));
+      }
+      __syncwarp();
+    }
+  }
+  cluster.barrier_wait();  // no CTA may exit while a peer still reads its totals
+}
+
+// cluster size for the cluster build (0 = not eligible)
+static int csr_cluster_size(int N, int L, bool* wide, size_t* smem) {
+  if (N < 1 || N > 2048 || L < 2048) return 0;
+  int Q = 8;
+  while (Q > 1 && L < 1024 * Q) Q >>= 1;
+  const int CL = (((L + Q * 32 - 1) / (Q * 32)) + 31) & ~31;
+  // cnt[w][key] ends up holding the prefix over the CTA's 32 warps: up to 32 * CL
+  *wide = 32LL * CL > 65535;
+  *smem = sizeof(int32_t) * 2 * (size_t)((N + 3) & ~3) + (size_t)32 * N * ((*wide ? 4 : 2) + 1);
+  return *smem <= 220 * 1024 ? Q : 0;
+}
+
+template <typename CT>
+static int launch_csr_cluster(const int32_t* idx, const int64_t* item_len, int B, int N, int L, int Q, size_t smem,
+                              int32_t* off, int32_t* items, cudaStream_t st) {
+  auto kern = csr_cluster_kernel<CT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * Q));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)Q;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TPG_CUDA(cudaLaunchKernelEx(&cfg, kern, idx, item_len, N, L, Q, off, items));
+  return TPG_OK;
+}
+
 // warps per cloud for the stable build (0 = does not fit: use the count/scan/fill/sort path)
 static int csr_stable_warps(int N, int L, bool* wide) {
   *wide = false;
@@ -551,6 +732,14 @@ int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, 
               "inverse_index: workspace too small");
   {
     bool wide = false;
+    size_t sm = 0;
+    const int Q = csr_cluster_size(N, L, &wide, &sm);
+    if (Q >= 1)
+      return wide ? launch_csr_cluster<uint32_t>(idx, item_len, B, N, L, Q, sm, seg_offsets, seg_items, st)
+                  : launch_csr_cluster<uint16_t>(idx, item_len, B, N, L, Q, sm, seg_offsets, seg_items, st);
+  }
+  {
+    bool wide = false;
     const int W = csr_stable_warps(N, L, &wide);
     if (W == 32) {  // fewer warps per cloud: the count / scan / fill / sort path over all SMs is faster
       const size_t sm = sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3) + (size_t)W * N * (wide ? 5 : 3);
@@ -608,8 +797,23 @@ TPG_API int tpg_group_bwd_f32(const float* grad_out, const int32_t* seg_offsets,
   TPG_REQUIRE(B >= 0 && C >= 0 && N >= 0 && L >= 0, TPG_EINVAL, "group_bwd: negative size");
   if (B == 0 || C == 0 || N == 0) return TPG_OK;
   TPG_REQUIRE(grad_f && seg_offsets && (L == 0 || (grad_out && seg_items)), TPG_EINVAL, "group_bwd: null pointer");
+  if (L > 0 && tpg::group_bwd_staged_eligible(grad_out, seg_items, B, C, N, L))
+    return tpg::group_bwd_staged(grad_out, seg_offsets, seg_items, B, C, N, L, grad_f, 0, as_stream(stream));
   BwdArgs a{grad_out, nullptr, nullptr, seg_offsets, seg_items, B, C, N, 0, 1, L, BWD_GROUP, grad_f};
   return launch_bwd(a, as_stream(stream));
+}
+
+// tuning hook (tools/bench_group_bwd.py; not part of the ABI): variant 0 = plain CSR gather, 1/2/4 = staged kernel
+// with that many channels per thread, -1 = the dispatch of tpg_group_bwd_f32
+TPG_API int tpg_debug_group_bwd_variant(const float* grad_out, const int32_t* seg_offsets, const int32_t* seg_items,
+                                        int B, int C, int N, int L, float* grad_f, int variant, tpg_stream_t stream) {
+  if (variant < 0) return tpg_group_bwd_f32(grad_out, seg_offsets, seg_items, B, C, N, L, grad_f, stream);
+  if (variant == 0) {
+    BwdArgs a{grad_out, nullptr, nullptr, seg_offsets, seg_items, B, C, N, 0, 1, L, BWD_GROUP, grad_f};
+    return launch_bwd(a, as_stream(stream));
+  }
+  TPG_REQUIRE(tpg::group_bwd_staged_eligible(grad_out, seg_items, B, C, N, L), TPG_EUNSUPPORTED, "group_bwd: shape not eligible for the staged kernel");
+  return tpg::group_bwd_staged(grad_out, seg_offsets, seg_items, B, C, N, L, grad_f, variant, as_stream(stream));
 }
 
 TPG_API int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg, const int32_t* seg_offsets,

@@ -46,4 +46,8 @@ size_t csr_workspace_bytes(int B, int N, int L);
 int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, int32_t* seg_offsets,
               int32_t* seg_items, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// group_bwd_staged.cu: grouping backward that streams grad_out rows through shared memory (TMA bulk copies)
+bool group_bwd_staged_eligible(const float* go, const int32_t* items, int B, int C, int N, int L);
+int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L, float* gf,
+                     int force_tcg, cudaStream_t st);
 }  // namespace tpg

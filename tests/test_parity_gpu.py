@@ -385,7 +385,12 @@ def test_group_fwd_exact(F, oracle, B, C, N, M, k):
 
 @pytest.mark.parametrize("B,C,N,M,k,hubs", [(2, 16, 512, 512, 12, False), (2, 8, 256, 300, 9, True),
                                             (1, 3, 2048, 256, 32, False), (2, 5, 100, 100, 1, False),
-                                            (1, 4, 64, 2000, 20, True)])
+                                            (1, 4, 64, 2000, 20, True),
+                                            # shared-memory-staged backward + cluster-built inverse index
+                                            (3, 32, 2048, 2048, 20, False), (2, 64, 256, 256, 32, True),
+                                            (2, 20, 1000, 1024, 12, False), (1, 8, 3000, 2048, 16, False),
+                                            (1, 130, 96, 4096, 16, True), (2, 35, 2048, 1024, 32, True),
+                                            (1, 2, 512, 30000, 20, True)])
 def test_group_bwd_deterministic_and_exact(F, oracle, B, C, N, M, k, hubs):
     rng = np.random.default_rng(10)
     f, idx = make_group(rng, B, C, N, M, k, hubs)
