@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lanes", type=int, default=32, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
     ap.add_argument("--per-op", action="store_true", help="print the per-op time table to stderr")
     ap.add_argument("--per-call", action="store_true", help="print every call of the schedule with its mean device time")
     return ap.parse_args()
@@ -325,6 +326,39 @@ def run_ours(args):
         except Exception as e:  # capture is an optimisation of the host side only
             graph_info = {"error": repr(e)[:300]}
             torch.cuda.synchronize()
+    # the same calls again, issued over several streams along the data flow recorded from the reference's step
+    # (schedule "deps"): independent chains -- the frames of a window, G vs D passes -- overlap inside one graph
+    graph_lanes = None
+    if not args.no_graph and args.lanes > 1:
+        try:
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                rp.run_step(lanes=args.lanes)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g2):
+                lanes_loss = rp.run_step(lanes=args.lanes)
+
+            def step_lanes():
+                g2.replay()
+                return reduce_step(lanes_loss)
+
+            ms_lanes = timed(step_lanes, args.steps, args.warmup)
+            graph_lanes = {"value": total_queries / (ms_lanes * 1e-3), "unit": UNIT, "ms_per_step": ms_lanes,
+                           "streams": args.lanes, "loss_matches_single_stream": None,
+                           "note": "same kernels; issue order relaxed to the recorded data dependencies of the "
+                                   "reference's train step, one cudaGraphLaunch per step"}
+            if graph_info and "error" not in graph_info:
+                g.replay()
+                g2.replay()
+                torch.cuda.synchronize()
+                graph_lanes["loss_matches_single_stream"] = bool(torch.equal(graph_loss, lanes_loss))
+        except Exception as e:
+            graph_lanes = {"error": repr(e)[:300]}
+            torch.cuda.synchronize()
 
     # per-op device time inside the timed region (events recorded around every call)
     op_ms, op_bytes, op_calls = {}, {}, {}
@@ -427,14 +461,26 @@ def run_ours(args):
                                   f"C oracle with OpenMP"}
 
     if rank == 0:
+        # headline = the step as the product issues it: one CUDA graph over the recorded data-flow DAG when that
+        # capture succeeded, else the single-stream graph, else eager per-call launches (always reported too)
+        mode, ms_head = "eager (one host launch per call)", ms_res
+        if graph_info and "error" not in graph_info:
+            mode, ms_head = "cuda graph, single stream", graph_info["ms_per_step"]
+        if graph_lanes and "error" not in graph_lanes and graph_lanes["ms_per_step"] < ms_head:
+            mode, ms_head = f"cuda graph, {args.lanes} streams along the recorded data dependencies", graph_lanes["ms_per_step"]
+        cfg = workload_config(args, doc, batch)
+        cfg["issue"] = mode
         line = {
-            "metric": METRIC, "value": total_queries / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
+            "metric": METRIC, "value": total_queries / (ms_head * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_head, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, doc, batch),
-            "train_step_hot_path_per_s": world * 1e3 / ms_res,
+            "config": cfg,
+            "train_step_hot_path_per_s": world * 1e3 / ms_head,
+            "eager": {"value": total_queries / (ms_res * 1e-3), "unit": UNIT, "ms_per_step": ms_res,
+                      "note": "same calls launched one by one from Python; the per-op / roofline timings below are "
+                              "CUDA events around the calls of this leg"},
             "queries_per_step": total_queries,
-            "cuda_graph": graph_info,
+            "cuda_graph": graph_info, "cuda_graph_streams": graph_lanes,
             "roofline": roofline, "roofline_hbm_op": roofline_hbm, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }

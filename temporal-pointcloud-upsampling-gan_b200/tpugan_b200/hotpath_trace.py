@@ -177,75 +177,179 @@ class TraceReplay:
         return d
 
     # ---- replay -------------------------------------------------------------------------
-    def _pick_idx(self, state, want, fallback):
-        """Most recent index tensor of the wanted shape [B,M,k]; a [B,M,k*d] list is strided
-        by d (Dilated, gcn_lib/pointnet/gcn.py:71); otherwise a seeded random one."""
-        for shape, t in reversed(state["idx"]):
-            if shape == want:
-                return t
-            if len(shape) == 3 and shape[:2] == want[:2] and shape[2] > want[2] and shape[2] % want[2] == 0:
-                return self.ops.stride_last(t, shape[2] // want[2])
-        return fallback
+    # ---- recorded data flow ------------------------------------------------------------
+    def _deps(self, n):
+        """Boundary calls whose results call n consumes (recorded by the dependency tracker of
+        tests/golden/make_schedule.py; group_bwd also depends on the forward call it mirrors)."""
+        d = self.calls[n]["in"].get("deps") or {}
+        out = set()
+        for v in d.values():
+            out.update(int(x) for x in v)
+        return out
 
-    def run_step(self):
+    def plan_lanes(self, lanes):
+        """Static stream assignment: a call continues the lane of the latest of its producers that is
+        still the tail of its lane (a dependent chain stays on one stream); otherwise it opens the
+        lane whose tail it transitively depends on, an unused lane, or the least recently used one.  Independent chains (the frames of a window, G vs D passes) therefore
+        land on different streams; every cross-lane edge becomes an event wait."""
+        tail = [-1] * lanes
+        lane_of = []
+        anc: List[set] = []  # transitive producers
+        for n in range(len(self.calls)):
+            D = self._deps(n)
+            A = set(D)
+            for d in D:
+                A |= anc[d]
+            anc.append(A)
+            cands = [l for l in range(lanes) if tail[l] in D]             # continue a producer's chain
+            if not cands:
+                cands = [l for l in range(lanes) if tail[l] in A]         # behind an ancestor: the edge is implied
+            if cands:
+                l = max(cands, key=lambda x: tail[x])
+            else:
+                l = min(range(lanes), key=lambda x: tail[x])              # unused, else least recently used
+            lane_of.append(l)
+            tail[l] = n
+        return lane_of
+
+    def run_step(self, lanes=1):
+        """One pass over the schedule.  lanes > 1 issues independent chains on separate streams (for CUDA
+        graph capture): a call waits for every recorded producer and for the producer of every tensor it
+        actually reads, so the overlap never exceeds what the recorded data flow of the reference allows."""
         ops = self.ops
         ops.new_step()
+        multi = lanes > 1 and hasattr(ops, "lanes_begin")
+        if multi:
+            if getattr(self, "_lane_plan", (0, None))[0] != lanes:
+                self._lane_plan = (lanes, self.plan_lanes(lanes))
+            lane_of = self._lane_plan[1]
+            ops.lanes_begin(lanes)
         state: Dict[str, Any] = {"idx": [], "fwd": {}, "cloud": {}, "chamfer": None, "last_fps": None,
-                                 "last_gather": None, "frnn": None}
+                                 "last_gather": None, "frnn": None, "csr": {}}
+        prod: Dict[int, int] = {}   # id(tensor) -> call that produced it
+        done: Dict[int, Any] = {}   # call -> completion event (multi-lane only)
+        keep: List[Any] = []        # every produced tensor stays alive until the step ends (cross-stream use)
         results = []
+
+        def made(n, *tensors):
+            for t in tensors:
+                prod[id(t)] = n
+                keep.append(t)
+
         for n, c in enumerate(self.calls):
             op, i, d = c["op"], c["in"], self.inputs[n]
-            t0 = ops.tick() if self.timers is not None else None
+            used: List[Any] = []  # tensors of earlier calls this call reads
+            run = None
             if op == "knn":
-                idx = ops.knn(d["p1"], d["p2"], int(i["K"]))
-                if state["frnn"] is not None and state["frnn"][0] == _shape(c["out"]["idx"]):
-                    # ball_query_wrapper (discriminator.py:39): fill FRNN's -1 slots from kNN
-                    idx = ops.fill_negative(state["frnn"][1], idx)
+                fr = state["frnn"] if state["frnn"] is not None and state["frnn"][0] == _shape(c["out"]["idx"]) else None
+                if fr is not None:
+                    used.append(fr[1])
                     state["frnn"] = None
-                state["idx"].append((_shape(c["out"]["idx"]), ops.to_i32(idx)))
+
+                def run(d=d, i=i, c=c, fr=fr, n=n):
+                    idx = ops.knn(d["p1"], d["p2"], int(i["K"]))
+                    if fr is not None:  # ball_query_wrapper (discriminator.py:39): fill FRNN's -1 slots from kNN
+                        idx = ops.fill_negative(fr[1], idx)
+                    idx = ops.to_i32(idx)
+                    made(n, idx)
+                    state["idx"].append((_shape(c["out"]["idx"]), idx))
             elif op == "frnn":
-                idx = ops.frnn(d["p1"], d["p2"], int(i["K"]), float(i["r"]))
-                state["frnn"] = (_shape(c["out"]["idx"]), idx)
+                def run(d=d, i=i, c=c, n=n):
+                    idx = ops.frnn(d["p1"], d["p2"], int(i["K"]), float(i["r"]))
+                    made(n, idx)
+                    state["frnn"] = (_shape(c["out"]["idx"]), idx)
             elif op == "fps":
                 B, N, _ = _shape(i["xyz"])
                 xyz = state["cloud"].get((B, N), d["xyz"])
-                idx = ops.fps(xyz, int(i["npoint"]))
-                state["last_fps"] = (xyz, idx)
+                used.append(xyz)
+
+                def run(xyz=xyz, i=i, n=n):
+                    idx = ops.fps(xyz, int(i["npoint"]))
+                    made(n, idx)
+                    state["last_fps"] = (xyz, idx)
             elif op == "gather":
                 xyz, idx = state["last_fps"]
-                out = ops.gather(ops.transpose12(xyz), idx)  # [B,3,M]
-                new_xyz = ops.transpose12(out)
-                state["last_gather"] = (xyz, new_xyz)
-                state["cloud"][(new_xyz.shape[0], new_xyz.shape[1])] = new_xyz
-                state["fwd"][i["id"]] = idx
+                used += [xyz, idx]
+
+                def run(xyz=xyz, idx=idx, i=i, n=n):
+                    out = ops.gather(ops.transpose12(xyz), idx)  # [B,3,M]
+                    new_xyz = ops.transpose12(out)
+                    made(n, out, new_xyz)
+                    state["last_gather"] = (xyz, new_xyz)
+                    state["cloud"][(new_xyz.shape[0], new_xyz.shape[1])] = new_xyz
+                    state["fwd"][i["id"]] = idx
             elif op == "ball_query":
                 xyz, new_xyz = state["last_gather"]
-                idx = ops.ball_query(float(i["radius"]), int(i["nsample"]), xyz, new_xyz)
-                state["idx"].append((_shape(c["out"]["idx"]), idx))
-                state["last_xyz"] = xyz
+                used += [xyz, new_xyz]
+
+                def run(xyz=xyz, new_xyz=new_xyz, i=i, c=c, n=n):
+                    idx = ops.ball_query(float(i["radius"]), int(i["nsample"]), xyz, new_xyz)
+                    made(n, idx)
+                    state["idx"].append((_shape(c["out"]["idx"]), idx))
             elif op == "group":
                 B, C, N = _shape(i["f"])
-                idx = self._pick_idx(state, _shape(i["idx"]), d["rand_idx"])
+                want = _shape(i["idx"])
+                src_idx, stride = None, 1
+                for shape, t in reversed(state["idx"]):  # most recent index tensor of the wanted shape
+                    if shape == want:
+                        src_idx = t
+                        break
+                    if len(shape) == 3 and shape[:2] == want[:2] and shape[2] > want[2] and shape[2] % want[2] == 0:
+                        src_idx, stride = t, shape[2] // want[2]  # Dilated (gcn_lib/pointnet/gcn.py:71)
+                        break
+                if src_idx is None:
+                    src_idx = d["rand_idx"]
+                used.append(src_idx)
+                src = None
                 if C == 3:
                     src = state["cloud"].get((B, N))
                     if src is None:
                         src = self.base_cloud(B, N, slot=0)
-                    f = ops.transpose12(src)
-                else:
-                    f = d["f"]
-                results.append(ops.group(f, idx))
-                state["fwd"][i["id"]] = idx
+                    used.append(src)
+
+                def run(src=src, src_idx=src_idx, stride=stride, d=d, i=i, n=n):
+                    idx = ops.stride_last(src_idx, stride) if stride > 1 else src_idx
+                    f = ops.transpose12(src) if src is not None else d["f"]
+                    out = ops.group(f, idx)
+                    made(n, out, idx, f)
+                    results.append(out)
+                    state["fwd"][i["id"]] = idx
             elif op in ("group_bwd", "gather_bwd"):
                 idx = state["fwd"][i["fwd_id"]]
-                results.append(ops.group_bwd(d["grad_out"], idx, int(i["N"])))
+                used.append(idx)
+                owner = state["csr"].setdefault((id(idx), int(i["N"])), n)  # the call that builds the shared CSR
+
+                def run(idx=idx, d=d, i=i, n=n):
+                    out = ops.group_bwd(d["grad_out"], idx, int(i["N"]))
+                    made(n, out)
+                    results.append(out)
             elif op == "chamfer":
-                state["chamfer"] = ops.chamfer(d["src"], d["tgt"], int(i["directions"]))
+                def run(d=d, i=i, n=n):
+                    state["chamfer"] = ops.chamfer(d["src"], d["tgt"], int(i["directions"]))
+                    state["chamfer_call"] = n
             elif op == "chamfer_bwd":
-                results.append(ops.chamfer_bwd(state["chamfer"], d["g"]))
+                def run(d=d, n=n):
+                    out = ops.chamfer_bwd(state["chamfer"], d["g"])
+                    made(n, out)
+                    results.append(out)
             else:
                 raise ValueError(f"unknown op in schedule: {op}")
+            if multi:
+                waits = set(self._deps(n))
+                waits.update(prod[id(t)] for t in used if id(t) in prod)
+                if op in ("group_bwd", "gather_bwd") and owner != n:
+                    waits.add(owner)
+                if op == "chamfer_bwd":
+                    waits.add(state["chamfer_call"])
+                ops.lane_enter(lane_of[n], [done[w] for w in sorted(waits) if w in done and lane_of[w] != lane_of[n]])
+            t0 = ops.tick() if self.timers is not None else None
+            run()
             if t0 is not None:
                 self.timers.setdefault(op, []).append((t0, ops.tick()))
+            if multi:
+                done[n] = ops.lane_exit()
+        if multi:
+            ops.lanes_end()
         return ops.finish(state["chamfer"], results)
 
 
@@ -271,6 +375,37 @@ class TorchCudaOps:
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
         return e
+
+    # ---- multi-stream issue (TraceReplay.run_step(lanes=S)); lane 0 is the caller's stream ----
+    def lanes_begin(self, lanes):
+        t = self.torch
+        self._main = t.cuda.current_stream()
+        if len(getattr(self, "_streams", [])) != lanes:
+            self._streams = [None] + [t.cuda.Stream() for _ in range(lanes - 1)]
+        self._streams[0] = self._main
+        fork = t.cuda.Event()
+        fork.record(self._main)
+        for s in self._streams[1:]:
+            s.wait_event(fork)
+
+    def lane_enter(self, lane, wait_events):
+        s = self._streams[lane]
+        self.torch.cuda.set_stream(s)
+        for e in wait_events:
+            s.wait_event(e)
+
+    def lane_exit(self):
+        e = self.torch.cuda.Event()
+        e.record(self.torch.cuda.current_stream())
+        return e
+
+    def lanes_end(self):
+        t = self.torch
+        t.cuda.set_stream(self._main)
+        for s in self._streams[1:]:
+            e = t.cuda.Event()
+            e.record(s)
+            self._main.wait_event(e)
 
     def knn(self, p1, p2, K):
         return self.F.knn(p1, p2, K)[1]

@@ -67,7 +67,7 @@ def main():
         g, sd, td = NoMaskSRNet(3, 128, ratio), ActionSpatialDis(), ActionTempoDis(3)
         opt = Namespace(R=2.0, w=2.0)
     og, ot, os_ = (torch.optim.Adam(m.parameters(), lr=1e-4) for m in (g, td, sd))
-    sh.recorder.start(shapes_only=True)
+    sh.recorder.start(shapes_only=True, track_deps=True)
     t = time.time()
     if domain == "fluid":
         out = train_step_final.tempo_gan_step(g, sd, td, lo, None, hi, None, 1.0, opt, 12, og, ot, os_)

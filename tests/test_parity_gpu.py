@@ -547,6 +547,38 @@ def test_gather_rows(F, oracle):
     np.testing.assert_array_equal(F.gather_rows(cu(x), cu(idx)).cpu().numpy(), oracle.gather_rows(x, idx))
 
 
+@pytest.mark.parametrize("name,batch", [("action", 2), ("fluid", 2)])
+def test_multi_stream_replay_equals_single_stream(F, name, batch):
+    """TraceReplay.run_step(lanes=S) issues independent chains of the recorded step on S streams; every
+    result (all grouping outputs / gradients and the Chamfer loss) must equal the in-order replay."""
+    import os
+
+    import torch
+    from tpugan_b200 import hotpath_trace as ht
+
+    doc = ht.load_schedule(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}_step_schedule.json"), batch)
+    ops = ht.TorchCudaOps("cuda")
+    rp = ht.TraceReplay(doc, ops, seed=5)
+    got = {}
+    orig_finish = ops.finish
+
+    def finish(chamfer, results, tag=[None]):
+        got[tag[0]] = [r.clone() for r in results]
+        return orig_finish(chamfer, results)
+
+    ops.finish = finish
+    for lanes in (1, 3, 32):
+        finish.__defaults__[0][0] = lanes
+        loss = rp.run_step(lanes=lanes)
+        torch.cuda.synchronize()
+        got[("loss", lanes)] = float(loss)
+    for lanes in (3, 32):
+        assert got[("loss", lanes)] == got[("loss", 1)]
+        assert len(got[lanes]) == len(got[1])
+        for a, b in zip(got[lanes], got[1]):
+            assert torch.equal(a, b)
+
+
 def test_library_was_used(F):
     import tpugan_b200
 

@@ -55,3 +55,66 @@ def test_replay_runs_on_the_oracle_backend():
     loss = rp.run_step()
     assert np.isfinite(loss) and loss > 0
     assert rp.queries == ht.count_queries(doc)
+
+
+def test_dependency_tracker_follows_weights_views_and_autograd():
+    """oracle.shims.DepTracker (used by tests/golden/make_schedule.py): the producer sets recorded with a
+    call must follow data through optimizer updates, writes through views and autograd."""
+    import torch
+
+    import oracle.shims as sh
+
+    sh.activate()
+    from oracle.shims import _backend as B
+
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(4, 3))
+    opt = torch.optim.Adam([w], lr=0.1)
+    x = torch.randn(2, 64, 3)
+    sh.recorder.start(shapes_only=True, track_deps=True)
+    try:
+        f = torch.einsum("bnc,dc->bdn", x, w).contiguous()
+        _, i = B.knn(x, x, 4)                                    # call 0
+        g = B.Grouping.apply(f, i.to(torch.int32))               # call 1
+        g.sum().backward()                                       # call 2: group_bwd
+        opt.step()
+        f2 = torch.einsum("bnc,dc->bdn", x, w).contiguous()      # reads the updated weight
+        g2 = B.Grouping.apply(f2, i.to(torch.int32))             # call 3
+        v = f2.view(2, -1)
+        v[:, 0] = g2.reshape(2, -1)[:, 0]                        # write through a view
+        B.knn(f2.transpose(1, 2)[..., :3].contiguous(), x, 2)    # call 4
+    finally:
+        calls = sh.recorder.stop()
+    deps = [c[1]["deps"] for c in calls]
+    assert [c[0] for c in calls] == ["knn", "group", "group_bwd", "group", "knn"]
+    assert deps[0] == {"p1": [], "p2": []}
+    assert deps[1] == {"f": [], "idx": [0]}
+    assert deps[2]["grad_out"] == [1] and deps[2]["idx"] == [0]
+    assert deps[3] == {"f": [2], "idx": [0]}          # through the Adam update of w
+    assert deps[4] == {"p1": [2, 3], "p2": []}       # through the view write
+
+
+@pytest.mark.parametrize("name", ["fluid", "action"])
+def test_schedule_dependencies_form_a_dag_with_parallel_chains(name):
+    from tpugan_b200 import hotpath_trace as ht
+
+    doc = ht.load_schedule(os.path.join(GOLDEN, f"{name}_step_schedule.json"))
+    calls = doc["calls"]
+    prod_of_idx = {"knn", "frnn", "ball_query"}
+    for n, c in enumerate(calls):
+        d = c["in"]["deps"]
+        assert all(0 <= x < n for v in d.values() for x in v)
+        if c["op"] == "group":   # the neighbour lists come from exactly one search call (or FRNN + kNN fill)
+            assert d["idx"] and all(calls[x]["op"] in prod_of_idx for x in d["idx"])
+        if c["op"] == "gather":
+            assert [calls[x]["op"] for x in d["idx"]] == ["fps"]
+        if c["op"] == "ball_query":
+            assert [calls[x]["op"] for x in d["new_xyz"]] == ["gather"]
+    # the generator passes over frames 0 and 2 start from external inputs only: independent chains exist
+    roots = [n for n, c in enumerate(calls) if not any(c["in"]["deps"].values())]
+    assert len(roots) >= 3
+    rp = ht.TraceReplay.__new__(ht.TraceReplay)
+    rp.calls = calls
+    for lanes in (2, 8, 32):
+        plan = rp.plan_lanes(lanes)
+        assert len(plan) == len(calls) and 0 <= min(plan) and max(plan) < lanes
