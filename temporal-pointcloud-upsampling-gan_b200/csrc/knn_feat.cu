@@ -278,7 +278,6 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   __shared__ uint32_t tmem_base_s;
   __shared__ float tau0_s[FT_NQ];
   __shared__ int cnt_s[FT_NQ];
-  __shared__ int ncand_s[FT_NQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, colgrp = warp >> 2;
@@ -470,97 +469,106 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   epi_sync();
   if (dbg && tid == 0) dbg[4] = clock64();
 
-  // ---- F1: per query (QPW per warp): margin, superset check, candidate list ----
+  // ---- finalisation, one warp per query (QPW queries per warp), no CTA barrier ----
+  // F1 margin + superset check + candidate list (<= 32); F2 canonical distances: the candidate rows are
+  // fetched with fully coalesced 16-byte loads (8 or 16 lanes per row) into a padded per-warp tile, then lane r
+  // sums row r sequentially in d order (a row per lane straight from global memory is L1-tag-bound: 32
+  // lines per request); F3 rank by (d_canon, idx) with shuffles and write the K best.
   constexpr int QPW = FT_NQ / (FT_THREADS / 32);
   const float nmax = __uint_as_float(a.nmax2[b]);
-  int* cand_s = reinterpret_cast<int*>(base_ptr);                 // [FT_NQ][32] candidate indices (stage memory is free)
-  float* dcan_s = reinterpret_cast<float*>(base_ptr) + FT_NQ * 32;  // [FT_NQ][32] canonical distances
+  const int rstride = D + 4;                                         // floats; keeps float4 reads of 8 rows conflict-free
+  float* wtile = reinterpret_cast<float*>(base_ptr) + (size_t)warp * (32 * rstride + D + 32);  // stage memory is free now
+  float* wq = wtile + 32 * rstride;                                  // the query row
+  int* wcand = reinterpret_cast<int*>(wq + D);                       // compacted candidate indices
+  const int lpr = cpr;                                               // lanes per row: 8 (D=32) or 16 (D=64)
+  const int rpi = 32 / lpr;                                          // rows per load instruction
   for (int qq = 0; qq < QPW; ++qq) {
     const int n = warp * QPW + qq;
     const int qi = q0 + n;
-    int ncand = -1;  // -1: nothing to do (beyond P1 / lengths1 / fallback)
-    if (qi < n1) {
-      const int C = cnt_s[n];
-      bool ok = C <= FT_CAP;
-      float ev[2];
-      int jv[2];
+    if (qi >= n1) {
+      if (qi < a.P1 && lane < K) {  // rows beyond lengths1: zeros (pytorch3d convention)
+        a.dists[((size_t)b * a.P1 + qi) * K + lane] = 0.0f;
+        a.idx[((size_t)b * a.P1 + qi) * K + lane] = 0;
+      }
+      continue;
+    }
+    const int C = cnt_s[n];
+    bool ok = C <= FT_CAP;
+    float ev[2];
+    int jv[2];
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int i = lane + 32 * s2;
-        ev[s2] = INF; jv[s2] = 0x7fffffff;
-        if (ok && i < C) {
-          const float2 v = buf_s[n * FT_CAP + i];
-          ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
-        }
-      }
-      float limit = INF;
-      const float t0 = tau0_s[n];
-      if (ok) {
-        // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
-        float tk = INF;
-        if (C >= K) {
-          const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
-          tk = ordered_key_inv(warp_radix_bound16(uk2, K));
-        }
-        const float nq = a.nrm1[(size_t)b * a.P1 + qi];
-        limit = tk + 2.0f * feat_eps(nq, nmax, D);
-        // everything with e <= tau0 is buffered, so the margin zone must end below tau0
-        // (tau0 == inf: every candidate of the cloud is buffered)
-        ok = limit < t0 || t0 == INF;
-      }
-      const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
-      const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
-      ncand = __popc(cm0) + __popc(cm1);
-      if (!ok || ncand > 32) {
-        if (lane == 0) {
-          const int pos = atomicAdd(a.fb_count, 1);
-          a.fb_list[pos] = b * a.P1 + qi;
-        }
-        ncand = -1;
-      } else {
-        if (cand0) cand_s[n * 32 + __popc(cm0 & lt_mask)] = jv[0];
-        if (cand1) cand_s[n * 32 + __popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
-      }
-    } else if (qi < a.P1 && lane < K) {  // rows beyond lengths1: zeros (pytorch3d convention)
-      a.dists[((size_t)b * a.P1 + qi) * K + lane] = 0.0f;
-      a.idx[((size_t)b * a.P1 + qi) * K + lane] = 0;
-    }
-    if (lane == 0) ncand_s[n] = ncand;
-  }
-  epi_sync();
-
-  // ---- F2: canonical distances of all (query, candidate) pairs, spread over every thread ----
-  for (int pr0 = tid; pr0 < FT_NQ * 32; pr0 += 2 * FT_THREADS) {  // two independent chains per thread
-    const int prA = pr0, prB = pr0 + FT_THREADS;
-    const bool vA = (prA & 31) < ncand_s[prA >> 5], vB = prB < FT_NQ * 32 && (prB & 31) < ncand_s[prB >> 5];
-    const float4* xA = reinterpret_cast<const float4*>(p1b + (size_t)(vA ? q0 + (prA >> 5) : 0) * D);
-    const float4* yA = reinterpret_cast<const float4*>(p2b + (size_t)(vA ? cand_s[prA] : 0) * D);
-    const float4* xB = reinterpret_cast<const float4*>(p1b + (size_t)(vB ? q0 + (prB >> 5) : 0) * D);
-    const float4* yB = reinterpret_cast<const float4*>(p2b + (size_t)(vB ? cand_s[prB] : 0) * D);
-    float accA = 0.0f, accB = 0.0f;
-    if (vA || vB) {
-      for (int c = 0; c < cpr; ++c) {
-        const float4 x0 = __ldg(xA + c), y0 = __ldg(yA + c), x1 = __ldg(xB + c), y1 = __ldg(yB + c);
-        accA = sq_acc(accA, x0.x, y0.x); accB = sq_acc(accB, x1.x, y1.x);
-        accA = sq_acc(accA, x0.y, y0.y); accB = sq_acc(accB, x1.y, y1.y);
-        accA = sq_acc(accA, x0.z, y0.z); accB = sq_acc(accB, x1.z, y1.z);
-        accA = sq_acc(accA, x0.w, y0.w); accB = sq_acc(accB, x1.w, y1.w);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int i = lane + 32 * s2;
+      ev[s2] = INF; jv[s2] = 0x7fffffff;
+      if (ok && i < C) {
+        const float2 v = buf_s[n * FT_CAP + i];
+        ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
       }
     }
-    if (vA) dcan_s[prA] = accA;
-    if (vB) dcan_s[prB] = accB;
-  }
-  epi_sync();
-
-  // ---- F3: rank by (d_canon, idx), write the K best ----
-  for (int qq = 0; qq < QPW; ++qq) {
-    const int n = warp * QPW + qq;
-    const int ncand = ncand_s[n];
-    if (ncand < 0) continue;
-    const int qi = q0 + n;
+    float limit = INF;
+    const float t0 = tau0_s[n];
+    if (ok) {
+      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
+      float tk = INF;
+      if (C >= K) {
+        const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
+        tk = ordered_key_inv(warp_radix_bound16(uk2, K));
+      }
+      const float nq = a.nrm1[(size_t)b * a.P1 + qi];
+      limit = tk + 2.0f * feat_eps(nq, nmax, D);
+      // everything with e <= tau0 is buffered, so the margin zone must end below tau0
+      // (tau0 == inf: every candidate of the cloud is buffered)
+      ok = limit < t0 || t0 == INF;
+    }
+    const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
+    const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
+    const int ncand = __popc(cm0) + __popc(cm1);
+    if (!ok || ncand > 32) {  // (warp-uniform) exact fallback kernel takes this query
+      if (lane == 0) {
+        const int pos = atomicAdd(a.fb_count, 1);
+        a.fb_list[pos] = b * a.P1 + qi;
+      }
+      continue;
+    }
+    __syncwarp();  // the previous query's readers are done with wtile / wcand
+    if (cand0) wcand[__popc(cm0 & lt_mask)] = jv[0];
+    if (cand1) wcand[__popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
+    if (lane < cpr) reinterpret_cast<float4*>(wq)[lane] = __ldg(reinterpret_cast<const float4*>(p1b + (size_t)qi * D) + lane);
+    __syncwarp();
+    {
+      const int sub = lane / lpr, ch = lane - sub * lpr;
+      for (int r0 = 0; r0 < ncand; r0 += 4 * rpi) {  // 4 independent loads in flight per lane
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * rpi + sub;
+          if (r < ncand) v[u] = __ldg(reinterpret_cast<const float4*>(p2b + (size_t)wcand[r] * D) + ch);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * rpi + sub;
+          if (r < ncand) *reinterpret_cast<float4*>(wtile + r * rstride + ch * 4) = v[u];
+        }
+      }
+    }
+    __syncwarp();
     const bool cand = lane < ncand;
-    const float dc = cand ? dcan_s[n * 32 + lane] : INF;
-    const int ci = cand ? cand_s[n * 32 + lane] : 0x7fffffff;
+    float dc = INF;
+    int ci = 0x7fffffff;
+    if (cand) {
+      ci = wcand[lane];
+      const float4* y = reinterpret_cast<const float4*>(wtile + lane * rstride);
+      const float4* x = reinterpret_cast<const float4*>(wq);
+      float acc = 0.0f;
+      for (int c = 0; c < cpr; ++c) {
+        const float4 x0 = x[c], y0 = y[c];
+        acc = sq_acc(acc, x0.x, y0.x);
+        acc = sq_acc(acc, x0.y, y0.y);
+        acc = sq_acc(acc, x0.z, y0.z);
+        acc = sq_acc(acc, x0.w, y0.w);
+      }
+      dc = acc;
+    }
     int rank = 0;
     for (int m2 = 0; m2 < ncand; ++m2) {
       const float od2 = __shfl_sync(FULL, dc, m2);
