@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   __shared__ __align__(8) uint64_t tfree_s[FT_NBUF];      // all 16 warps have drained the TMEM buffer
   __shared__ uint32_t tmem_base_s;
   __shared__ float tau0_s[FT_NQ];
+  __shared__ float limit_s[FT_NQ];
   __shared__ int cnt_s[FT_NQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -482,6 +483,35 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   int* wcand = reinterpret_cast<int*>(wq + D);                       // compacted candidate indices
   const int lpr = cpr;                                               // lanes per row: 8 (D=32) or 16 (D=64)
   const int rpi = 32 / lpr;                                          // rows per load instruction
+  // F1 for the warp's QPW queries at once: the 16 dependent radix steps of the queries interleave, and the
+  // norms arrive with one coalesced load
+  {
+    unsigned uk[QPW][2];
+#pragma unroll
+    for (int qq = 0; qq < QPW; ++qq) {
+      const int n = warp * QPW + qq;
+      const int C = cnt_s[n];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int i = lane + 32 * s2;
+        uk[qq][s2] = (C <= FT_CAP && i < C) ? ordered_key(buf_s[n * FT_CAP + i].x) : 0xffffffffu;
+      }
+    }
+    unsigned tkk[QPW];
+    warp_radix_bound16_multi<QPW, 2>(uk, K, tkk);
+    float eps2 = 0.0f;
+    if (lane < QPW && q0 + warp * QPW + lane < n1)
+      eps2 = 2.0f * feat_eps(a.nrm1[(size_t)b * a.P1 + q0 + warp * QPW + lane], nmax, D);
+#pragma unroll
+    for (int qq = 0; qq < QPW; ++qq) {
+      const int n = warp * QPW + qq;
+      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
+      const float tk = cnt_s[n] >= K ? ordered_key_inv(tkk[qq]) : INF;
+      const float lim = tk + __shfl_sync(FULL, eps2, qq);
+      if (lane == 0) limit_s[n] = lim;
+    }
+    __syncwarp();
+  }
   for (int qq = 0; qq < QPW; ++qq) {
     const int n = warp * QPW + qq;
     const int qi = q0 + n;
@@ -505,21 +535,11 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
       }
     }
-    float limit = INF;
+    const float limit = limit_s[n];
     const float t0 = tau0_s[n];
-    if (ok) {
-      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
-      float tk = INF;
-      if (C >= K) {
-        const unsigned uk2[2] = {lane < C ? ordered_key(ev[0]) : 0xffffffffu, lane + 32 < C ? ordered_key(ev[1]) : 0xffffffffu};
-        tk = ordered_key_inv(warp_radix_bound16(uk2, K));
-      }
-      const float nq = a.nrm1[(size_t)b * a.P1 + qi];
-      limit = tk + 2.0f * feat_eps(nq, nmax, D);
-      // everything with e <= tau0 is buffered, so the margin zone must end below tau0
-      // (tau0 == inf: every candidate of the cloud is buffered)
-      ok = limit < t0 || t0 == INF;
-    }
+    // everything with e <= tau0 is buffered, so the margin zone must end below tau0
+    // (tau0 == inf: every candidate of the cloud is buffered)
+    ok = ok && (limit < t0 || t0 == INF);
     const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
     const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
     const int ncand = __popc(cm0) + __popc(cm1);
