@@ -608,13 +608,29 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   }
 }
 
-// ---- exact fallback: one CTA per flagged query (8 warps x 1/8 of the candidates, then a merge) ------
+// ---- exact fallback: one CTA per flagged query (16 warps x 1/16 of the candidates, then a two-level merge) ------
 template <int CH>  // CH = D / 4 float4 chunks per row (8 or 16)
-__global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
-  __shared__ float2 part_s[8][32];
+__global__ void __launch_bounds__(512) knn_feat_fallback_kernel(FeatArgs a) {
+  __shared__ float2 part_s[16][32];
   const int total = *a.fb_count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float INF = __int_as_float(0x7f800000);
+  // merges the (ascending) list `v` of another slice into L; slices are merged in ascending index order, so
+  // insert_tail's "equal distance -> lower index first" rule is kept
+  auto merge = [&](WarpList& L, float& tau, const float2 v) {
+    const int vi = __float_as_int(v.y);
+    unsigned m = __ballot_sync(FULL, vi >= 0 && v.x < tau);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const float dcand = __shfl_sync(FULL, v.x, l);
+      const int icand = __shfl_sync(FULL, vi, l);
+      if (dcand < tau) {
+        L.insert_tail(dcand, icand, lane);
+        tau = L.kth(a.K);
+      }
+    }
+  };
   for (int e = blockIdx.x; e < total; e += gridDim.x) {
     const int flat = a.fb_list[e];
     const int b = flat / a.P1, qi = flat - b * a.P1;
@@ -627,7 +643,7 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
     WarpList L;
     L.init();
     float tau = INF;
-    const int per = ((n2 + 7) / 8 + 31) & ~31;  // contiguous, 32-aligned slice per warp: ascending indices
+    const int per = ((n2 + 15) / 16 + 31) & ~31;  // contiguous, 32-aligned slice per warp: ascending indices
     const int jlo = warp * per, jhi = min(n2, jlo + per);
     for (int j0 = jlo; j0 < jhi; j0 += 32) {
       const int j = j0 + lane;
@@ -658,24 +674,14 @@ __global__ void __launch_bounds__(256) knn_feat_fallback_kernel(FeatArgs a) {
     __syncthreads();  // previous query's merge has finished reading part_s
     part_s[warp][lane] = make_float2(L.d, __int_as_float(L.i));
     __syncthreads();
+    // two-level merge: warps 0, 4, 8, 12 absorb the 3 slices after theirs, then warp 0 absorbs those three
+    if ((warp & 3) == 0) {
+      for (int w = warp + 1; w < warp + 4; ++w) merge(L, tau, part_s[w][lane]);
+      if (warp != 0) part_s[warp][lane] = make_float2(L.d, __int_as_float(L.i));
+    }
+    __syncthreads();
     if (warp == 0) {
-      // slices are in ascending index order, so appending them in warp order keeps insert_tail's
-      // "equal distance -> lower index first" rule
-      for (int w = 1; w < 8; ++w) {
-        const float2 v = part_s[w][lane];
-        const int vi = __float_as_int(v.y);
-        unsigned m = __ballot_sync(FULL, vi >= 0 && v.x < tau);
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const float dcand = __shfl_sync(FULL, v.x, l);
-          const int icand = __shfl_sync(FULL, vi, l);
-          if (dcand < tau) {
-            L.insert_tail(dcand, icand, lane);
-            tau = L.kth(a.K);
-          }
-        }
-      }
+      for (int w = 4; w < 16; w += 4) merge(L, tau, part_s[w][lane]);
       if (lane < a.K) {
         const size_t o = ((size_t)b * a.P1 + qi) * a.K + lane;
         const bool found = L.i >= 0;
@@ -795,8 +801,8 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
               TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
   knn_feat_tc_kernel<<<grid, FT_BLOCK, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
-  if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms() * 4, 256, 0, st>>>(a);
-  else knn_feat_fallback_kernel<16><<<num_sms() * 4, 256, 0, st>>>(a);
+  if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms(), 512, 0, st>>>(a);
+  else knn_feat_fallback_kernel<16><<<num_sms(), 512, 0, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_fallback_kernel");
   return TPG_OK;
 }

@@ -15,7 +15,7 @@ if [ "${SKIP_REF:-0}" != "1" ]; then
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>&1; echo "ref rc=$?"
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-graph"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches rc=$?"
