@@ -41,7 +41,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 # kernel launched by each schedule op (csrc/*.cu) — for the roofline object
 OP_KERNEL = {"knn": "knn_feat_tc_kernel", "frnn": "grid_knn_kernel", "ball_query": "ball_query_kernel",
              "fps": "fps_reg_kernel", "gather": "group_fwd_kernel", "group": "group_fwd_kernel",
-             "group_bwd": "group_bwd_kernel", "gather_bwd": "group_bwd_kernel", "chamfer": "grid_nn1_kernel",
+             "group_bwd": "group_bwd_staged_kernel", "gather_bwd": "group_bwd_kernel", "chamfer": "grid_nn1_kernel",
              "chamfer_bwd": "chamfer_bwd_kernel"}
 # GAN-step gradient buckets all-reduced at N > 1 (G / tempo-D / spatial-D parameters)
 GRAD_BUCKETS = (439461, 738177, 308737)
