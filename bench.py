@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--lanes", type=int, default=32, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
+    ap.add_argument("--lanes", type=int, default=64, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
     ap.add_argument("--per-op", action="store_true", help="print the per-op time table to stderr")
     ap.add_argument("--per-call", action="store_true", help="print every call of the schedule with its mean device time")
     return ap.parse_args()
@@ -231,7 +231,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import tpugan_b200
-    from tpugan_b200 import hotpath_trace as ht
+    from tpugan_b200 import _lib, hotpath_trace as ht
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -335,12 +335,15 @@ def run_ours(args):
             g2 = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
+            # overlapped calls: an FPS call should hold 8 SMs, not a 64-SM cluster, for its whole duration
+            _lib.set_option("fps.sms_per_cloud", 1)
             with torch.cuda.stream(side):
                 rp.run_step(lanes=args.lanes)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             with torch.cuda.graph(g2):
                 lanes_loss = rp.run_step(lanes=args.lanes)
+            _lib.set_option("fps.sms_per_cloud", 8)
 
             def step_lanes():
                 g2.replay()
@@ -358,6 +361,7 @@ def run_ours(args):
                 graph_lanes["loss_matches_single_stream"] = bool(torch.equal(graph_loss, lanes_loss))
         except Exception as e:
             graph_lanes = {"error": repr(e)[:300]}
+            _lib.set_option("fps.sms_per_cloud", 8)
             torch.cuda.synchronize()
 
     # per-op device time inside the timed region (events recorded around every call)
@@ -456,6 +460,7 @@ def run_ours(args):
                     g3 = torch.cuda.CUDAGraph()
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
+                    _lib.set_option("fps.sms_per_cloud", 1 if lanes > 1 else 8)
                     with torch.cuda.stream(side):
                         rp2.run_step(lanes=lanes)
                     torch.cuda.current_stream().wait_stream(side)
@@ -464,6 +469,7 @@ def run_ours(args):
                         for dst, src in zip(rp2.frames, host_frames):
                             dst.copy_(src, non_blocking=True)
                         e2e_loss = rp2.run_step(lanes=lanes).detach().float().reshape(())
+                    _lib.set_option("fps.sms_per_cloud", 8)
 
                     def step_e2e_graph():
                         g3.replay()
@@ -482,6 +488,7 @@ def run_ours(args):
                     break
                 except Exception as e:
                     e2e_graph_err = repr(e)[:200]
+                    _lib.set_option("fps.sms_per_cloud", 8)
                     torch.cuda.synchronize()
         e2e = {"value": total_queries / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "issue": e2e_mode,

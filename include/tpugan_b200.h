@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 5
+#define TPG_ABI_VERSION 6
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -59,6 +59,13 @@ const char* tpg_last_error(void);
 /* number of kernel launches issued by this library on the calling process
  * since load (bench.py's "gpu_launches" claim is read from here). */
 uint64_t tpg_launch_count(void);
+/* Scheduling hints; never change a result.  Returns TPG_OK or TPG_EINVAL (unknown name / value).
+ *   "fps.sms_per_cloud"  1 | 2 | 4 | 8 (default 8; initial value from env TPG_FPS_CLUSTER):
+ *       size of the thread-block cluster that shares one cloud of 2049..65536 points in
+ *       tpg_fps_f32 / tpg_fps_sampling_f32.  8 gives the shortest call; 1 holds 8x fewer SMs
+ *       for a ~1.4x longer call — the better choice when calls overlap with other work
+ *       (multi-stream capture of a train step). */
+int tpg_set_option(const char* name, long value);
 
 /* ---- K1/K2: k nearest neighbours ---------------------------------------
  * replaces pytorch3d.ops.knn_points(p1, p2, lengths1, lengths2, K,

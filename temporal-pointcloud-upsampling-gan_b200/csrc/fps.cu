@@ -18,6 +18,9 @@
 // Clouds of more than 2048 points are split over a thread-block cluster of 8 CTAs (DSMEM
 // exchange of the local winners, one cluster barrier per round); beyond 65536 points the
 // running min-dist moves to a caller-provided global workspace.
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -249,6 +252,15 @@ constexpr int FPS_CL = 8;         // CTAs (SMs) per cloud for N > FPS_SINGLE_MAX
 constexpr int FPS_SINGLE_MAX = 2048;
 constexpr int FPS_REG_MAX = 65536;  // 8 CTAs x 1024 threads x 8 points
 
+std::atomic<int>& fps_cluster_option() {
+  static std::atomic<int> v{[] {
+    const char* e = getenv("TPG_FPS_CLUSTER");
+    const int c = e ? atoi(e) : FPS_CL;
+    return (c == 1 || c == 2 || c == 4 || c == 8) ? c : FPS_CL;
+  }()};
+  return v;
+}
+
 template <bool MODEB>
 static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
   if (a.B == 0 || a.npoint == 0) return TPG_OK;
@@ -257,6 +269,16 @@ static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
     // one CTA; measured on B200: 2 points per thread up to 1024 points, 4 up to 2048
     if (N <= 1024) return fps_launch<2, 1, MODEB>(a, max(32, (ceil_div(N, 2) + 31) & ~31), st);
     return fps_launch<4, 1, MODEB>(a, (ceil_div(N, 4) + 31) & ~31, st);
+  }
+  // option "fps.sms_per_cloud" = 1|2|4: fewer SMs per cloud.  A round gets slower, but a call that overlaps with
+  // other work (multi-stream replay) then holds 8/16/32 SMs instead of 64 for its whole duration.
+  const int cl_env = fps_cluster_option().load(std::memory_order_relaxed);
+  if (cl_env != FPS_CL && N <= 8192 * cl_env && (cl_env == 1 || cl_env == 2 || cl_env == 4)) {
+    const int ppc = (ceil_div(N, cl_env) + 31) & ~31;
+    const int t8 = (ceil_div(ppc, 8) + 31) & ~31, t4 = (ceil_div(ppc, 4) + 31) & ~31;
+    if (cl_env == 1) return fps_launch<8, 1, MODEB>(a, t8, st);
+    if (cl_env == 2) return t4 <= 1024 ? fps_launch<4, 2, MODEB>(a, t4, st) : fps_launch<8, 2, MODEB>(a, t8, st);
+    return t4 <= 1024 ? fps_launch<4, 4, MODEB>(a, t4, st) : fps_launch<8, 4, MODEB>(a, t8, st);
   }
   if (N <= FPS_REG_MAX) {
     const int ppc = (ceil_div(N, FPS_CL) + 31) & ~31;

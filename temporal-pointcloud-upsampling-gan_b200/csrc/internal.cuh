@@ -1,5 +1,6 @@
 // internal.cuh — cross-file internals of libtpugan_b200.so (not part of the ABI).
 #pragma once
+#include <atomic>
 #include "common.cuh"
 
 namespace tpg {
@@ -50,4 +51,6 @@ int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, 
 bool group_bwd_staged_eligible(const float* go, const int32_t* items, int B, int C, int N, int L);
 int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L, float* gf,
                      int force_tcg, cudaStream_t st);
+// fps.cu: CTAs (SMs) per cloud for 2048 < N <= 65536 (tpg_set_option "fps.sms_per_cloud")
+std::atomic<int>& fps_cluster_option();
 }  // namespace tpg

@@ -16,7 +16,7 @@ import os
 import sys
 
 from . import _lib
-from ._lib import TpgError, TpgLibraryMissing, launch_count  # noqa: F401
+from ._lib import TpgError, TpgLibraryMissing, launch_count, set_option  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -7,14 +7,14 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p, c_long
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
@@ -35,6 +35,7 @@ _PROTOS = {
     "tpg_abi_version": (_I, []),
     "tpg_last_error": (c_char_p, []),
     "tpg_launch_count": (c_uint64, []),
+    "tpg_set_option": (_I, [c_char_p, c_long]),
     "tpg_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "tpg_knn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_frnn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
@@ -113,3 +114,8 @@ def call(name: str, *args) -> None:
     status = fn(*args)
     if status != TPG_OK:
         check(status, name)
+
+
+def set_option(name: str, value: int) -> None:
+    """Scheduling hint of the library (include/tpugan_b200.h: tpg_set_option); never changes a result."""
+    call("tpg_set_option", name.encode(), int(value))

@@ -18,6 +18,7 @@ never imports ``oracle``.
 from __future__ import annotations
 
 import json
+import os
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -187,6 +188,13 @@ class TraceReplay:
             out.update(int(x) for x in v)
         return out
 
+    def _src(self, n, name, op=None):
+        """The single recorded producer call of input `name` of call n (optionally of kind `op`), else None."""
+        d = (self.calls[n]["in"].get("deps") or {}).get(name) or []
+        if op is not None:
+            d = [x for x in d if self.calls[x]["op"] == op]
+        return int(d[-1]) if len(d) == 1 else None
+
     def plan_lanes(self, lanes):
         """Static stream assignment: a call continues the lane of the latest of its producers that is
         still the tail of its lane (a dependent chain stays on one stream); otherwise it opens the
@@ -222,10 +230,14 @@ class TraceReplay:
         if multi:
             if getattr(self, "_lane_plan", (0, None))[0] != lanes:
                 self._lane_plan = (lanes, self.plan_lanes(lanes))
-            lane_of = self._lane_plan[1]
-            ops.lanes_begin(lanes)
+            plan = self._lane_plan[1]
+            # latency-critical small kernels (FPS chains: a few CTAs running for hundreds of microseconds) go to a
+            # high-priority twin of their lane, so their CTAs are placed before those of the wide streaming kernels
+            hi = set(os.environ.get("TPG_REPLAY_HIGH_PRIORITY", "fps,gather,ball_query").split(","))
+            lane_of = [2 * plan[k] + (1 if self.calls[k]["op"] in hi else 0) for k in range(len(self.calls))]
+            ops.lanes_begin(2 * lanes)
         state: Dict[str, Any] = {"idx": [], "fwd": {}, "cloud": {}, "chamfer": None, "last_fps": None,
-                                 "last_gather": None, "frnn": None, "csr": {}}
+                                 "last_gather": None, "frnn": None, "csr": {}, "by_call": {}}
         prod: Dict[int, int] = {}   # id(tensor) -> call that produced it
         done: Dict[int, Any] = {}   # call -> completion event (multi-lane only)
         keep: List[Any] = []        # every produced tensor stays alive until the step ends (cross-stream use)
@@ -253,6 +265,7 @@ class TraceReplay:
                     idx = ops.to_i32(idx)
                     made(n, idx)
                     state["idx"].append((_shape(c["out"]["idx"]), idx))
+                    state["by_call"][n] = {"idx": idx, "shape": _shape(c["out"]["idx"])}
             elif op == "frnn":
                 def run(d=d, i=i, c=c, n=n):
                     idx = ops.frnn(d["p1"], d["p2"], int(i["K"]), float(i["r"]))
@@ -260,15 +273,20 @@ class TraceReplay:
                     state["frnn"] = (_shape(c["out"]["idx"]), idx)
             elif op == "fps":
                 B, N, _ = _shape(i["xyz"])
-                xyz = state["cloud"].get((B, N), d["xyz"])
+                g = self._src(n, "xyz", "gather")  # recorded producer of the cloud (a coarser level), if unique
+                xyz = state["by_call"][g]["new_xyz"] if g is not None else state["cloud"].get((B, N), d["xyz"])
+                if tuple(xyz.shape[:2]) != (B, N):
+                    xyz = state["cloud"].get((B, N), d["xyz"])
                 used.append(xyz)
 
                 def run(xyz=xyz, i=i, n=n):
                     idx = ops.fps(xyz, int(i["npoint"]))
                     made(n, idx)
                     state["last_fps"] = (xyz, idx)
+                    state["by_call"][n] = {"xyz": xyz, "idx": idx}
             elif op == "gather":
-                xyz, idx = state["last_fps"]
+                f = self._src(n, "idx", "fps")
+                xyz, idx = (state["by_call"][f]["xyz"], state["by_call"][f]["idx"]) if f is not None else state["last_fps"]
                 used += [xyz, idx]
 
                 def run(xyz=xyz, idx=idx, i=i, n=n):
@@ -278,19 +296,26 @@ class TraceReplay:
                     state["last_gather"] = (xyz, new_xyz)
                     state["cloud"][(new_xyz.shape[0], new_xyz.shape[1])] = new_xyz
                     state["fwd"][i["id"]] = idx
+                    state["by_call"][n] = {"xyz": xyz, "new_xyz": new_xyz}
             elif op == "ball_query":
-                xyz, new_xyz = state["last_gather"]
+                g = self._src(n, "new_xyz", "gather")
+                xyz, new_xyz = (state["by_call"][g]["xyz"], state["by_call"][g]["new_xyz"]) if g is not None else state["last_gather"]
                 used += [xyz, new_xyz]
 
                 def run(xyz=xyz, new_xyz=new_xyz, i=i, c=c, n=n):
                     idx = ops.ball_query(float(i["radius"]), int(i["nsample"]), xyz, new_xyz)
                     made(n, idx)
                     state["idx"].append((_shape(c["out"]["idx"]), idx))
+                    state["by_call"][n] = {"idx": idx, "shape": _shape(c["out"]["idx"]), "xyz": xyz}
             elif op == "group":
                 B, C, N = _shape(i["f"])
                 want = _shape(i["idx"])
                 src_idx, stride = None, 1
-                for shape, t in reversed(state["idx"]):  # most recent index tensor of the wanted shape
+                cand_list = list(reversed(state["idx"]))
+                rec = [x for x in ((c["in"].get("deps") or {}).get("idx") or []) if x in state["by_call"] and "shape" in state["by_call"][x]]
+                if rec:  # the recorded producer of the neighbour lists (the kNN call when FRNN + kNN fill both appear)
+                    cand_list = [(state["by_call"][rec[-1]]["shape"], state["by_call"][rec[-1]]["idx"])] + cand_list
+                for shape, t in cand_list:  # else: most recent index tensor of the wanted shape
                     if shape == want:
                         src_idx = t
                         break
@@ -302,7 +327,10 @@ class TraceReplay:
                 used.append(src_idx)
                 src = None
                 if C == 3:
-                    src = state["cloud"].get((B, N))
+                    if rec and "xyz" in state["by_call"][rec[-1]] and tuple(state["by_call"][rec[-1]]["xyz"].shape[:2]) == (B, N):
+                        src = state["by_call"][rec[-1]]["xyz"]  # QueryAndGroup: the cloud the ball query searched
+                    else:
+                        src = state["cloud"].get((B, N))
                     if src is None:
                         src = self.base_cloud(B, N, slot=0)
                     used.append(src)
@@ -380,8 +408,8 @@ class TorchCudaOps:
     def lanes_begin(self, lanes):
         t = self.torch
         self._main = t.cuda.current_stream()
-        if len(getattr(self, "_streams", [])) != lanes:
-            self._streams = [None] + [t.cuda.Stream() for _ in range(lanes - 1)]
+        if len(getattr(self, "_streams", [])) != lanes:  # odd lanes: high priority
+            self._streams = [None] + [t.cuda.Stream(priority=-1 if (k & 1) else 0) for k in range(1, lanes)]
         self._streams[0] = self._main
         fork = t.cuda.Event()
         fork.record(self._main)

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared_functions():
         assert hasattr(lib, name), name
     lib.tpg_abi_version.restype = ctypes.c_int
-    assert lib.tpg_abi_version() == 5  # host-only call
+    assert lib.tpg_abi_version() == 6  # host-only call
 
 
 def test_library_is_sm100a_only(built):
@@ -54,6 +54,12 @@ def test_host_only_entry_points_do_not_need_a_gpu(built):
     assert lib.tpg_chamfer_bwd_workspace_bytes(2, 100, 200) > 0
     assert lib.tpg_cubic_interp_workspace_bytes(1, 100, 100) > 0
     assert lib.tpg_launch_count() >= 0
+    # scheduling hints: host-only, validated
+    assert lib.tpg_set_option(b"fps.sms_per_cloud", 1) == built.TPG_OK
+    assert lib.tpg_set_option(b"fps.sms_per_cloud", 8) == built.TPG_OK
+    assert lib.tpg_set_option(b"fps.sms_per_cloud", 3) == built.TPG_EINVAL
+    assert lib.tpg_set_option(b"no.such.option", 1) == built.TPG_EINVAL
+    assert b"no.such.option" in lib.tpg_last_error()
 
 
 def test_argument_errors_are_reported_not_thrown(built):

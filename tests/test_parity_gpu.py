@@ -331,6 +331,22 @@ def test_fps_pointnet2_bit_exact(F, oracle, B, N, npoint, kind):
     np.testing.assert_array_equal(g.cpu().numpy(), o)
 
 
+@pytest.mark.parametrize("sms", [1, 2, 4])
+@pytest.mark.parametrize("B,N,npoint", [(2, 8192, 300), (1, 3000, 200), (1, 2049, 64), (2, 16384, 50), (1, 30000, 20)])
+def test_fps_sms_per_cloud_option_never_changes_the_result(F, oracle, sms, B, N, npoint):
+    import tpugan_b200
+
+    rng = np.random.default_rng(61)
+    xyz = np.ascontiguousarray(synth.with_duplicates(rng, synth.fluid_cloud(rng, B, N)), np.float32)
+    o = oracle.fps(xyz, npoint)
+    tpugan_b200.set_option("fps.sms_per_cloud", sms)
+    try:
+        g = F.fps(cu(xyz), npoint).cpu().numpy()
+    finally:
+        tpugan_b200.set_option("fps.sms_per_cloud", 8)
+    np.testing.assert_array_equal(g, o)
+
+
 def test_fps_origin_skip_quirk(F, oracle):
     """Points with |p|^2 <= 1e-3 are never selected (except forced index 0)."""
     rng = np.random.default_rng(7)
