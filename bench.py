@@ -227,6 +227,8 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------- ours
 def run_ours(args):
+    # the DAG replay keeps many independent streams busy: use every hardware work queue (must precede CUDA init)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
 

@@ -227,21 +227,23 @@ int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, 
   a.G = SB_THREADS / a.NPs;
   a.items_bytes = (int)align_up((size_t)2 * L + 2, 128);  // + the one-past-the-end peek
   const int ring_floats = (SB_SMEM_BYTES - a.items_bytes) / 4;
-  // channels per thread: as many as still leave a tile for every SM and chunks of >= 4096 floats (or whole rows)
+  // channels per thread (one item walk serves TCG channels): as many as still leave >= min_tiles tiles and chunks
+  // of >= 4096 floats (or whole rows).  min_tiles is half a wave: the step replays many groupings concurrently,
+  // so SM-time matters more than the latency of one call.
   int TCG = 1;
-  if (NPT == 1) {
-    for (int t = 4; t >= 2; t >>= 1) {
-      const long long TC = (long long)a.G * t;
-      if (TC > SB_MAX_TC) continue;
-      const long long lc = ring_floats / (2 * TC);
-      if (lc >= min(L, 4096) && (long long)B * ((C + TC - 1) / TC) >= num_sms()) { TCG = t; break; }
-    }
+  const int max_tcg = NPT <= 2 ? 4 : (NPT == 4 ? 2 : 1);
+  const int min_tiles = num_sms() / 2;
+  for (int t = max_tcg; t >= 2; t >>= 1) {
+    const long long TC = (long long)a.G * t;
+    if (TC > SB_MAX_TC) continue;
+    const long long lc = ring_floats / (2 * TC);
+    if (lc >= min(L, 4096) && (long long)B * ((C + TC - 1) / TC) >= min_tiles) { TCG = t; break; }
   }
   int S = 0;
   if (force > 0) {
     S = force / 10;
     const int t = force % 10;
-    if (t == 1 || (NPT == 1 && (t == 2 || t == 4))) TCG = t;
+    if (t == 1 || ((t == 2 || t == 4) && t <= max_tcg)) TCG = t;
   }
   a.TC = a.G * TCG;
   if (a.TC > SB_MAX_TC) { a.G = SB_MAX_TC / TCG; a.TC = a.G * TCG; }
@@ -261,7 +263,10 @@ int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, 
     case 12: return launch_staged<1, 2>(a, grid, smem, st);
     case 14: return launch_staged<1, 4>(a, grid, smem, st);
     case 21: return launch_staged<2, 1>(a, grid, smem, st);
+    case 22: return launch_staged<2, 2>(a, grid, smem, st);
+    case 24: return launch_staged<2, 4>(a, grid, smem, st);
     case 41: return launch_staged<4, 1>(a, grid, smem, st);
+    case 42: return launch_staged<4, 2>(a, grid, smem, st);
   }
   set_error("group_bwd_staged: no variant for NPT=%d TCG=%d", NPT, TCG);
   return TPG_EUNSUPPORTED;

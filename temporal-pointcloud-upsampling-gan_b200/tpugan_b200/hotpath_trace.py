@@ -180,13 +180,74 @@ class TraceReplay:
     # ---- replay -------------------------------------------------------------------------
     # ---- recorded data flow ------------------------------------------------------------
     def _deps(self, n):
-        """Boundary calls whose results call n consumes (recorded by the dependency tracker of
-        tests/golden/make_schedule.py; group_bwd also depends on the forward call it mirrors)."""
-        d = self.calls[n]["in"].get("deps") or {}
+        """Boundary calls whose results call n consumes: the producers recorded by the dependency tracker of
+        tests/golden/make_schedule.py, plus the structural ones of the replay itself (a backward needs the
+        forward call it mirrors, the kNN of ball_query_wrapper fills the FRNN result of the call before it,
+        chamfer_bwd needs chamfer)."""
+        cache = self.__dict__.setdefault("_deps_cache", {})
+        if n in cache:
+            return cache[n]
+        c = self.calls[n]
+        d = c["in"].get("deps") or {}
         out = set()
         for v in d.values():
             out.update(int(x) for x in v)
+        if "fwd_id" in c["in"]:
+            fwd = self.__dict__.setdefault("_fwd_call", {cc["in"]["id"]: k for k, cc in enumerate(self.calls) if "id" in cc["in"]})
+            out.add(fwd[c["in"]["fwd_id"]])
+        if self._frnn_partner(n) is not None:
+            out.add(n - 1)
+        if c["op"] == "chamfer_bwd":
+            out.update(k for k in range(n) if self.calls[k]["op"] == "chamfer")
+        cache[n] = out
         return out
+
+    def _frnn_partner(self, n):
+        """ball_query_wrapper (discriminator.py:26-41) calls frnn then knn on the same clouds: call n-1."""
+        c = self.calls[n]
+        if c["op"] == "knn" and n > 0 and self.calls[n - 1]["op"] == "frnn" and \
+                _shape(self.calls[n - 1]["out"]["idx"]) == _shape(c["out"]["idx"]):
+            return n - 1
+        return None
+
+    _COST_US = {"knn": 110.0, "frnn": 40.0, "ball_query": 30.0, "gather": 8.0, "group": 15.0, "group_bwd": 45.0,
+                "gather_bwd": 20.0, "chamfer": 150.0, "chamfer_bwd": 50.0}
+
+    def plan_order(self):
+        """Issue order for the multi-stream replay: a topological order of the recorded DAG that starts the
+        longest remaining chains first (list scheduling on rough per-call costs), so that e.g. the FPS chains
+        of the real frames, which depend on nothing, are at the front of the captured graph instead of behind
+        300 other nodes.  The data flow does not depend on the issue order (every input is looked up by its
+        recorded producer)."""
+        n_calls = len(self.calls)
+        cost = []
+        for c in self.calls:
+            if c["op"] == "fps":
+                N = _shape(c["in"]["xyz"])[1]
+                cost.append(float(c["in"]["npoint"]) * (0.37 if N <= 2048 else 1.2))
+            else:
+                cost.append(self._COST_US.get(c["op"], 20.0))
+        cons = [[] for _ in range(n_calls)]
+        for n in range(n_calls):
+            for d in self._deps(n):
+                cons[d].append(n)
+        cp = [0.0] * n_calls
+        for n in range(n_calls - 1, -1, -1):
+            cp[n] = cost[n] + max((cp[k] for k in cons[n]), default=0.0)
+        import heapq
+        missing = [len(self._deps(n)) for n in range(n_calls)]
+        ready = [(-cp[n], n) for n in range(n_calls) if missing[n] == 0]
+        heapq.heapify(ready)
+        order = []
+        while ready:
+            _, n = heapq.heappop(ready)
+            order.append(n)
+            for k in cons[n]:
+                missing[k] -= 1
+                if missing[k] == 0:
+                    heapq.heappush(ready, (-cp[k], k))
+        assert len(order) == n_calls
+        return order
 
     def _src(self, n, name, op=None):
         """The single recorded producer call of input `name` of call n (optionally of kind `op`), else None."""
@@ -195,28 +256,30 @@ class TraceReplay:
             d = [x for x in d if self.calls[x]["op"] == op]
         return int(d[-1]) if len(d) == 1 else None
 
-    def plan_lanes(self, lanes):
+    def plan_lanes(self, lanes, order=None):
         """Static stream assignment: a call continues the lane of the latest of its producers that is
         still the tail of its lane (a dependent chain stays on one stream); otherwise it opens the
         lane whose tail it transitively depends on, an unused lane, or the least recently used one.  Independent chains (the frames of a window, G vs D passes) therefore
         land on different streams; every cross-lane edge becomes an event wait."""
-        tail = [-1] * lanes
-        lane_of = []
-        anc: List[set] = []  # transitive producers
-        for n in range(len(self.calls)):
+        order = list(range(len(self.calls))) if order is None else order
+        pos = {n: k for k, n in enumerate(order)}     # issue position
+        tail = [-1] * lanes                            # last call issued on the lane
+        lane_of = [0] * len(self.calls)
+        anc: Dict[int, set] = {}                       # transitive producers
+        for n in order:
             D = self._deps(n)
             A = set(D)
             for d in D:
                 A |= anc[d]
-            anc.append(A)
+            anc[n] = A
             cands = [l for l in range(lanes) if tail[l] in D]             # continue a producer's chain
             if not cands:
                 cands = [l for l in range(lanes) if tail[l] in A]         # behind an ancestor: the edge is implied
             if cands:
-                l = max(cands, key=lambda x: tail[x])
+                l = max(cands, key=lambda x: pos[tail[x]])
             else:
-                l = min(range(lanes), key=lambda x: tail[x])              # unused, else least recently used
-            lane_of.append(l)
+                l = min(range(lanes), key=lambda x: -1 if tail[x] < 0 else pos[tail[x]])  # unused, else least recently used
+            lane_of[n] = l
             tail[l] = n
         return lane_of
 
@@ -229,7 +292,8 @@ class TraceReplay:
         multi = lanes > 1 and hasattr(ops, "lanes_begin")
         if multi:
             if getattr(self, "_lane_plan", (0, None))[0] != lanes:
-                self._lane_plan = (lanes, self.plan_lanes(lanes))
+                order = self.plan_order() if all("deps" in c["in"] for c in self.calls) else None
+                self._lane_plan = (lanes, self.plan_lanes(lanes, order), order)
             plan = self._lane_plan[1]
             # latency-critical small kernels (FPS chains: a few CTAs running for hundreds of microseconds) go to a
             # high-priority twin of their lane, so their CTAs are placed before those of the wide streaming kernels
@@ -248,12 +312,18 @@ class TraceReplay:
                 prod[id(t)] = n
                 keep.append(t)
 
-        for n, c in enumerate(self.calls):
+        issue = self._lane_plan[2] if multi and self._lane_plan[2] is not None else range(len(self.calls))
+        for n in issue:
+            c = self.calls[n]
             op, i, d = c["op"], c["in"], self.inputs[n]
             used: List[Any] = []  # tensors of earlier calls this call reads
             run = None
             if op == "knn":
-                fr = state["frnn"] if state["frnn"] is not None and state["frnn"][0] == _shape(c["out"]["idx"]) else None
+                fp = self._frnn_partner(n)
+                if fp is not None and fp in state["by_call"]:
+                    fr = (_shape(c["out"]["idx"]), state["by_call"][fp]["frnn_idx"])
+                else:
+                    fr = state["frnn"] if state["frnn"] is not None and state["frnn"][0] == _shape(c["out"]["idx"]) else None
                 if fr is not None:
                     used.append(fr[1])
                     state["frnn"] = None
@@ -265,18 +335,21 @@ class TraceReplay:
                     idx = ops.to_i32(idx)
                     made(n, idx)
                     state["idx"].append((_shape(c["out"]["idx"]), idx))
-                    state["by_call"][n] = {"idx": idx, "shape": _shape(c["out"]["idx"])}
+                    state["by_call"][n] = {"idx": idx, "shape": _shape(c["out"]["idx"]), "xyz": d["p2"]}
             elif op == "frnn":
                 def run(d=d, i=i, c=c, n=n):
                     idx = ops.frnn(d["p1"], d["p2"], int(i["K"]), float(i["r"]))
                     made(n, idx)
                     state["frnn"] = (_shape(c["out"]["idx"]), idx)
+                    state["by_call"][n] = {"frnn_idx": idx}
             elif op == "fps":
                 B, N, _ = _shape(i["xyz"])
                 g = self._src(n, "xyz", "gather")  # recorded producer of the cloud (a coarser level), if unique
-                xyz = state["by_call"][g]["new_xyz"] if g is not None else state["cloud"].get((B, N), d["xyz"])
+                recorded = "deps" in i
+                xyz = state["by_call"][g]["new_xyz"] if g is not None else (
+                    d["xyz"] if recorded else state["cloud"].get((B, N), d["xyz"]))
                 if tuple(xyz.shape[:2]) != (B, N):
-                    xyz = state["cloud"].get((B, N), d["xyz"])
+                    xyz = d["xyz"] if recorded else state["cloud"].get((B, N), d["xyz"])
                 used.append(xyz)
 
                 def run(xyz=xyz, i=i, n=n):
@@ -311,7 +384,7 @@ class TraceReplay:
                 B, C, N = _shape(i["f"])
                 want = _shape(i["idx"])
                 src_idx, stride = None, 1
-                cand_list = list(reversed(state["idx"]))
+                cand_list = [] if "deps" in i else list(reversed(state["idx"]))
                 rec = [x for x in ((c["in"].get("deps") or {}).get("idx") or []) if x in state["by_call"] and "shape" in state["by_call"][x]]
                 if rec:  # the recorded producer of the neighbour lists (the kNN call when FRNN + kNN fill both appear)
                     cand_list = [(state["by_call"][rec[-1]]["shape"], state["by_call"][rec[-1]]["idx"])] + cand_list
@@ -330,7 +403,7 @@ class TraceReplay:
                     if rec and "xyz" in state["by_call"][rec[-1]] and tuple(state["by_call"][rec[-1]]["xyz"].shape[:2]) == (B, N):
                         src = state["by_call"][rec[-1]]["xyz"]  # QueryAndGroup: the cloud the ball query searched
                     else:
-                        src = state["cloud"].get((B, N))
+                        src = None if "deps" in i else state["cloud"].get((B, N))
                     if src is None:
                         src = self.base_cloud(B, N, slot=0)
                     used.append(src)
@@ -340,7 +413,7 @@ class TraceReplay:
                     f = ops.transpose12(src) if src is not None else d["f"]
                     out = ops.group(f, idx)
                     made(n, out, idx, f)
-                    results.append(out)
+                    results.append((n, out))
                     state["fwd"][i["id"]] = idx
             elif op in ("group_bwd", "gather_bwd"):
                 idx = state["fwd"][i["fwd_id"]]
@@ -350,7 +423,7 @@ class TraceReplay:
                 def run(idx=idx, d=d, i=i, n=n):
                     out = ops.group_bwd(d["grad_out"], idx, int(i["N"]))
                     made(n, out)
-                    results.append(out)
+                    results.append((n, out))
             elif op == "chamfer":
                 def run(d=d, i=i, n=n):
                     state["chamfer"] = ops.chamfer(d["src"], d["tgt"], int(i["directions"]))
@@ -359,7 +432,7 @@ class TraceReplay:
                 def run(d=d, n=n):
                     out = ops.chamfer_bwd(state["chamfer"], d["g"])
                     made(n, out)
-                    results.append(out)
+                    results.append((n, out))
             else:
                 raise ValueError(f"unknown op in schedule: {op}")
             if multi:
@@ -378,7 +451,7 @@ class TraceReplay:
                 done[n] = ops.lane_exit()
         if multi:
             ops.lanes_end()
-        return ops.finish(state["chamfer"], results)
+        return ops.finish(state["chamfer"], [t for _, t in sorted(results, key=lambda r: r[0])])
 
 
 # ============================================================================ CUDA back-ends

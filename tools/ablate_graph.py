@@ -9,9 +9,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
-from tpugan_b200 import hotpath_trace as ht  # noqa: E402
+from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
 
-lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+_lib.set_option("fps.sms_per_cloud", int(os.environ.get("FPS_SMS", "1")))
+
+lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+only_full = len(sys.argv) > 2
 doc = ht.load_schedule(os.path.join(ROOT, "tests", "golden", "fluid_step_schedule.json"), 8)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -73,6 +76,6 @@ def measure(stub):
 
 base = measure(None)
 print(f"lanes={lanes}  full step {base:.2f} ms")
-for name in ("fps", "knn", "group_bwd", "group", "ball_query", "gather", "frnn"):
+for name in (() if only_full else ("fps", "knn", "group_bwd", "group", "ball_query", "gather", "frnn")):
     t = measure(name)
     print(f"  without {name:11s} {t:6.2f} ms   (-{base - t:.2f})")

@@ -14,8 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
 from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
 
-lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib = _lib.load()
+_lib.set_option("fps.sms_per_cloud", 1)
 ts_fn = lib.tpg_debug_timestamp
 ts_fn.restype = ctypes.c_int
 ts_fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -55,6 +56,11 @@ for _ in range(3):
     g.replay()
 torch.cuda.synchronize()
 t = stamps.cpu().numpy()[: 2 * ncalls].reshape(ncalls, 2).astype(np.float64)
+order = rp._lane_plan[2]
+if order is not None:  # stamps are taken in issue order
+    tt = np.empty_like(t)
+    tt[np.asarray(order)] = t
+    t = tt
 assert (t > 0).all(), 'missing stamps'
 t0 = t[:, 0].min()
 t = (t - t0) / 1e3  # us
