@@ -339,6 +339,7 @@ def run_ours(args):
             side.wait_stream(torch.cuda.current_stream())
             # overlapped calls: an FPS call should hold 8 SMs, not a 64-SM cluster, for its whole duration
             _lib.set_option("fps.sms_per_cloud", 1)
+            _lib.set_option("fps.exclusive_sm", 1)  # ... and keeps those SMs to itself (latency-bound rounds)
             with torch.cuda.stream(side):
                 rp.run_step(lanes=args.lanes)
             torch.cuda.current_stream().wait_stream(side)
@@ -346,6 +347,7 @@ def run_ours(args):
             with torch.cuda.graph(g2):
                 lanes_loss = rp.run_step(lanes=args.lanes)
             _lib.set_option("fps.sms_per_cloud", 8)
+            _lib.set_option("fps.exclusive_sm", 0)
 
             def step_lanes():
                 g2.replay()
@@ -364,6 +366,7 @@ def run_ours(args):
         except Exception as e:
             graph_lanes = {"error": repr(e)[:300]}
             _lib.set_option("fps.sms_per_cloud", 8)
+            _lib.set_option("fps.exclusive_sm", 0)
             torch.cuda.synchronize()
 
     # per-op device time inside the timed region (events recorded around every call)
@@ -463,6 +466,7 @@ def run_ours(args):
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
                     _lib.set_option("fps.sms_per_cloud", 1 if lanes > 1 else 8)
+                    _lib.set_option("fps.exclusive_sm", 1 if lanes > 1 else 0)
                     with torch.cuda.stream(side):
                         rp2.run_step(lanes=lanes)
                     torch.cuda.current_stream().wait_stream(side)
@@ -472,6 +476,7 @@ def run_ours(args):
                             dst.copy_(src, non_blocking=True)
                         e2e_loss = rp2.run_step(lanes=lanes).detach().float().reshape(())
                     _lib.set_option("fps.sms_per_cloud", 8)
+                    _lib.set_option("fps.exclusive_sm", 0)
 
                     def step_e2e_graph():
                         g3.replay()
@@ -491,6 +496,7 @@ def run_ours(args):
                 except Exception as e:
                     e2e_graph_err = repr(e)[:200]
                     _lib.set_option("fps.sms_per_cloud", 8)
+                    _lib.set_option("fps.exclusive_sm", 0)
                     torch.cuda.synchronize()
         e2e = {"value": total_queries / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "issue": e2e_mode,

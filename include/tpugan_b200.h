@@ -64,7 +64,10 @@ uint64_t tpg_launch_count(void);
  *       size of the thread-block cluster that shares one cloud of 2049..65536 points in
  *       tpg_fps_f32 / tpg_fps_sampling_f32.  8 gives the shortest call; 1 holds 8x fewer SMs
  *       for a ~1.4x longer call — the better choice when calls overlap with other work
- *       (multi-stream capture of a train step). */
+ *       (multi-stream capture of a train step).
+ *   "fps.exclusive_sm"   0 | 1 (default 0; env TPG_FPS_EXCLUSIVE): a one-CTA-per-cloud FPS launch requests
+ *       200 KB of shared memory so that no smem-using CTA of a concurrent kernel shares its SM — the
+ *       latency-bound rounds then keep their solo speed (2.6x slower when co-resident). */
 int tpg_set_option(const char* name, long value);
 
 /* ---- K1/K2: k nearest neighbours ---------------------------------------

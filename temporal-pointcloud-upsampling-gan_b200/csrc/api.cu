@@ -46,6 +46,11 @@ TPG_API int tpg_set_option(const char* name, long value) {
     tpg::fps_cluster_option().store((int)value, std::memory_order_relaxed);
     return TPG_OK;
   }
+  if (strcmp(name, "fps.exclusive_sm") == 0) {
+    TPG_REQUIRE(value == 0 || value == 1, TPG_EINVAL, "set_option: fps.exclusive_sm must be 0 or 1");
+    tpg::fps_exclusive_option().store((int)value, std::memory_order_relaxed);
+    return TPG_OK;
+  }
   tpg::set_error("set_option: unknown option '%s'", name);
   return TPG_EINVAL;
 }

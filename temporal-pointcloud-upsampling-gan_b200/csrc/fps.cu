@@ -225,11 +225,16 @@ __global__ void __launch_bounds__(1024) fps_mem_kernel(FpsArgs a) {
   }
 }
 
+std::atomic<int>& fps_exclusive_option();
+
 template <int PPT, int CL, bool MODEB>
 static int fps_launch(const FpsArgs& a, int threads, cudaStream_t st) {
   auto kern = fps_reg_kernel<PPT, CL, MODEB>;
   const int ppc = CL == 1 ? a.N : (ceil_div(a.N, CL) + 31) & ~31;
-  const size_t smem = sizeof(float) * 3 * (size_t)ppc;
+  size_t smem = sizeof(float) * 3 * (size_t)ppc;
+  // option "fps.exclusive_sm": a single-CTA-per-cloud launch asks for (nearly) all shared memory of its SM, so no
+  // smem-using CTA of a concurrent kernel lands beside it and steals issue slots from the latency-bound rounds
+  if (CL == 1 && fps_exclusive_option().load(std::memory_order_relaxed)) smem = max(smem, (size_t)200 * 1024);
   if (smem > 40 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static smem counts too
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.B * CL));
@@ -258,6 +263,11 @@ std::atomic<int>& fps_cluster_option() {
     const int c = e ? atoi(e) : FPS_CL;
     return (c == 1 || c == 2 || c == 4 || c == 8) ? c : FPS_CL;
   }()};
+  return v;
+}
+
+std::atomic<int>& fps_exclusive_option() {
+  static std::atomic<int> v{[] { const char* e = getenv("TPG_FPS_EXCLUSIVE"); return e && e[0] == '1' ? 1 : 0; }()};
   return v;
 }
 

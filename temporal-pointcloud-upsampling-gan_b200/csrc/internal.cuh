@@ -53,4 +53,5 @@ int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, 
                      int force_tcg, cudaStream_t st);
 // fps.cu: CTAs (SMs) per cloud for 2048 < N <= 65536 (tpg_set_option "fps.sms_per_cloud")
 std::atomic<int>& fps_cluster_option();
+std::atomic<int>& fps_exclusive_option();
 }  // namespace tpg

@@ -58,6 +58,9 @@ def test_host_only_entry_points_do_not_need_a_gpu(built):
     assert lib.tpg_set_option(b"fps.sms_per_cloud", 1) == built.TPG_OK
     assert lib.tpg_set_option(b"fps.sms_per_cloud", 8) == built.TPG_OK
     assert lib.tpg_set_option(b"fps.sms_per_cloud", 3) == built.TPG_EINVAL
+    assert lib.tpg_set_option(b"fps.exclusive_sm", 1) == built.TPG_OK
+    assert lib.tpg_set_option(b"fps.exclusive_sm", 0) == built.TPG_OK
+    assert lib.tpg_set_option(b"fps.exclusive_sm", 2) == built.TPG_EINVAL
     assert lib.tpg_set_option(b"no.such.option", 1) == built.TPG_EINVAL
     assert b"no.such.option" in lib.tpg_last_error()
 

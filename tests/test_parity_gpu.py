@@ -332,7 +332,8 @@ def test_fps_pointnet2_bit_exact(F, oracle, B, N, npoint, kind):
 
 
 @pytest.mark.parametrize("sms", [1, 2, 4])
-@pytest.mark.parametrize("B,N,npoint", [(2, 8192, 300), (1, 3000, 200), (1, 2049, 64), (2, 16384, 50), (1, 30000, 20)])
+@pytest.mark.parametrize("B,N,npoint", [(2, 8192, 300), (1, 3000, 200), (1, 2049, 64), (2, 16384, 50), (1, 30000, 20),
+                                        (2, 2048, 100), (3, 700, 70)])
 def test_fps_sms_per_cloud_option_never_changes_the_result(F, oracle, sms, B, N, npoint):
     import tpugan_b200
 
@@ -340,10 +341,12 @@ def test_fps_sms_per_cloud_option_never_changes_the_result(F, oracle, sms, B, N,
     xyz = np.ascontiguousarray(synth.with_duplicates(rng, synth.fluid_cloud(rng, B, N)), np.float32)
     o = oracle.fps(xyz, npoint)
     tpugan_b200.set_option("fps.sms_per_cloud", sms)
+    tpugan_b200.set_option("fps.exclusive_sm", 1)
     try:
         g = F.fps(cu(xyz), npoint).cpu().numpy()
     finally:
         tpugan_b200.set_option("fps.sms_per_cloud", 8)
+        tpugan_b200.set_option("fps.exclusive_sm", 0)
     np.testing.assert_array_equal(g, o)
 
 

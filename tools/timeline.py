@@ -17,6 +17,7 @@ from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib = _lib.load()
 _lib.set_option("fps.sms_per_cloud", 1)
+_lib.set_option("fps.exclusive_sm", 1)
 ts_fn = lib.tpg_debug_timestamp
 ts_fn.restype = ctypes.c_int
 ts_fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
