@@ -247,7 +247,8 @@ def run_ours(args):
     batch = args.batch or 8
     doc = ht.load_schedule(os.path.join(GOLDEN, f"{args.workload}_step_schedule.json"), batch)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    buckets = [torch.zeros(n, dtype=torch.float32, device=dev) for n in GRAD_BUCKETS] if world > 1 else []
+    # one flat fp32 buffer = [loss | G grads | tempo-D grads | spatial-D grads]: a single all-reduce per step
+    flat = torch.zeros(1 + sum(GRAD_BUCKETS), dtype=torch.float32, device=dev) if world > 1 else None
 
     def flush_l2():
         flush_buf.fill_(1)
@@ -261,9 +262,9 @@ def run_ours(args):
     def reduce_step(loss):
         # the GAN step's only exchanges under batch sharding: loss + gradient buckets (NCCL over NVLink)
         if world > 1:
-            dist.all_reduce(loss, op=dist.ReduceOp.AVG)
-            for b in buckets:
-                dist.all_reduce(b, op=dist.ReduceOp.AVG)
+            flat[0:1].copy_(loss.reshape(1))
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            return flat[0].clone()
         return loss
 
     def timed(step_fn, steps, warmup):

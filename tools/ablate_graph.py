@@ -50,7 +50,7 @@ class Ops(ht.TorchCudaOps):
 ops = Ops("cuda")
 rp = ht.TraceReplay(doc, ops, seed=1)
 ops.record = {}
-rp.run_step()
+rp.run_step(lanes=lanes)  # same issue order as the measured runs (the cache is consumed by occurrence)
 ops.cache, ops.record = ops.record, None
 torch.cuda.synchronize()
 
