@@ -423,6 +423,26 @@ def run_ours(args):
                         "avg_launch_us": op_ms[hop] * 1e3 / op_calls[hop],
                         "alg_bytes_per_launch": op_bytes[hop] / op_calls[hop],
                         "note": "average over every call of the step incl. small launch-bound ones; per-shape numbers: profiles/*_ops_sweep.md"}
+    # the kernel whose removal shortens the DAG-replayed step most (tools/ablate_graph.py): feature-space kNN on
+    # tcgen05 -- tensor-bound in its contraction, so report it against the measured dense bf16 peak
+    # (tf32 runs at half the bf16 rate)
+    roofline_tc = None
+    tc_calls = [(ci, c) for ci, c in enumerate(doc["calls"])
+                if c["op"] == "knn" and c["in"]["p1"]["shape"][2] in (32, 64) and c["in"]["p2"]["shape"][1] >= 1024
+                and int(c["in"]["K"]) <= 24]
+    if tc_calls:
+        fl = sum(2.0 * c["in"]["p1"]["shape"][0] * c["in"]["p1"]["shape"][1] * c["in"]["p2"]["shape"][1] *
+                 c["in"]["p1"]["shape"][2] for _, c in tc_calls)  # algorithmic: one pass over the distance matrix
+        ms_tc = sum(call_ms[ci] for ci, _ in tc_calls) / args.steps
+        pk = float(peaks.get("bf16_tflops", 1628.7)) / 2.0
+        roofline_tc = {"bound": "tensor", "kernel": "knn_feat_tc_kernel", "op": "knn (D = 32 / 64)",
+                       "achieved": fl / (ms_tc * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                       "frac": fl / (ms_tc * 1e-3) / 1e12 / pk, "launches_per_step": len(tc_calls),
+                       "avg_launch_us": ms_tc * 1e3 / len(tc_calls),
+                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 rate)",
+                       "note": "call = norms + tcgen05 kernel + exact-fallback launch; the kernel issues the contraction "
+                               "twice (two-pass candidate selection) and spends two thirds of its time in the SIMT "
+                               "selection / exact re-ranking that make the indices bit-exact (DESIGN.md K2)"}
     if args.per_call and rank == 0:
         agg = {}
         for ci, c in enumerate(doc["calls"]):
@@ -536,7 +556,7 @@ def run_ours(args):
                               "CUDA events around the calls of this leg"},
             "queries_per_step": total_queries,
             "cuda_graph": graph_info, "cuda_graph_streams": graph_lanes,
-            "roofline": roofline, "roofline_hbm_op": roofline_hbm, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_hbm_op": roofline_hbm, "roofline_tensor_op": roofline_tc, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
