@@ -238,7 +238,30 @@ struct GridKnnArgs {
 
 constexpr int OUT_BALL = 100;
 
+
+// Upper end of the 16-bit radix bucket holding the k-th smallest (1-based) of the NV keys per lane of a warp
+// (keys of absent values = 0xffffffff): a valid upper bound of the k-th smallest, < 1 % above it.
+template <int NV>
+__device__ __forceinline__ unsigned grid_radix_bound16(const unsigned (&uk)[NV], int k) {
+  unsigned prefix = 0u, himask = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 16; --bit) {
+    const unsigned bmask = 1u << bit;
+    unsigned local = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) local += ((uk[v] & (himask | bmask)) == prefix) ? 1u : 0u;
+    const int c = (int)__reduce_add_sync(FULL, local);
+    if (k > c) { prefix |= bmask; k -= c; }
+    himask |= bmask;
+  }
+  return prefix | 0xffffu;
+}
+
+constexpr int GK_PER = 12;  // candidates per lane the select-based fast path of grid_knn_kernel keeps in registers
+
+template <bool FAST>  // FAST: plain kNN with K <= 24 -- adds the select-based first block (80 registers instead of 64)
 __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
+  __shared__ float2 sel_s[FAST ? 8 : 1][2][32];  // per warp: selected candidates, then the sorted result
   const int lane = threadIdx.x & 31;
   long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (wq >= (long long)a.B * a.P1) return;
@@ -276,6 +299,90 @@ __global__ void __launch_bounds__(256) grid_knn_kernel(GridKnnArgs a) {
       float tau_d = INF;
       int tau_i = 0x7fffffff;
       const int ny = k.y1 - k.y0 + 1, nrows = ny * (k.z1 - k.z0 + 1);
+      // ---- fast path (first block, <= 32 * GK_PER candidates, K <= 32): no sorted-list insertions.  All candidate
+      // distances stay in registers; a 16-bit radix select bounds the K-th smallest; the few candidates under the
+      // bound are ranked by (d, idx) with shuffles.  Same result as the insertion path (canonical order).
+      if (FAST && R == 1 && nrows <= 32) {
+        int start = 0, cnt = 0;
+        if (lane < nrows) {
+          const int z = k.z0 + lane / ny, y = k.y0 + lane % ny;
+          const int c0 = (z * g.gy + y) * g.gx;
+          start = cs[c0 + k.x0];
+          cnt = cs[c0 + k.x1 + 1] - start;
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d) inc += t;
+        }
+        const int total = __shfl_sync(FULL, inc, 31);
+        if (total <= 32 * GK_PER) {
+          float dv[GK_PER];
+          int iv[GK_PER];
+          int nvalid = 0;
+#pragma unroll
+          for (int s2 = 0; s2 < GK_PER; ++s2) {
+            dv[s2] = INF;
+            iv[s2] = 0x7fffffff;
+            if (s2 * 32 < total) {  // (warp-uniform)
+              const int t = s2 * 32 + lane;
+              int rsel = 0;
+              for (int rr = 0; rr < nrows - 1; ++rr) rsel += (t >= __shfl_sync(FULL, inc, rr)) ? 1 : 0;
+              const int rstart = __shfl_sync(FULL, start, rsel);
+              const int rinc = __shfl_sync(FULL, inc, rsel);
+              const int rcnt = __shfl_sync(FULL, cnt, rsel);
+              if (t < total) {
+                const float4 v = __ldg(rec + rstart + (t - (rinc - rcnt)));
+                const float d = sqdist3(qx, qy, qz, v.x, v.y, v.z);
+                if (d < r2) { dv[s2] = d; iv[s2] = __float_as_int(v.w); ++nvalid; }
+              }
+            }
+          }
+          nvalid = (int)__reduce_add_sync(FULL, (unsigned)nvalid);
+          unsigned bound = 0x7f7fffffu;  // every finite distance
+          if (nvalid > K) {
+            unsigned uk[GK_PER];
+#pragma unroll
+            for (int s2 = 0; s2 < GK_PER; ++s2) uk[s2] = iv[s2] == 0x7fffffff ? 0xffffffffu : __float_as_uint(dv[s2]);
+            bound = grid_radix_bound16(uk, K);
+          }
+          // compact the candidates under the bound (all ties at the K-th distance included) into <= 32 slots
+          const unsigned lt = (1u << lane) - 1u;
+          const int wl = threadIdx.x >> 5;
+          int nsel = 0;
+#pragma unroll
+          for (int s2 = 0; s2 < GK_PER; ++s2) {
+            const bool sel = iv[s2] != 0x7fffffff && __float_as_uint(dv[s2]) <= bound;
+            const unsigned m = __ballot_sync(FULL, sel);
+            const int pos = nsel + __popc(m & lt);
+            if (sel && pos < 32) sel_s[wl][0][pos] = make_float2(dv[s2], __int_as_float(iv[s2]));
+            nsel += __popc(m);
+          }
+          if (nsel <= 32) {
+            __syncwarp();
+            float dc = INF;
+            int ic = 0x7fffffff;
+            if (lane < nsel) { const float2 v = sel_s[wl][0][lane]; dc = v.x; ic = __float_as_int(v.y); }
+            int rank = 0;
+            for (int m2 = 0; m2 < nsel; ++m2) {
+              const float od = __shfl_sync(FULL, dc, m2);
+              const int oi = __shfl_sync(FULL, ic, m2);
+              rank += (od < dc || (od == dc && oi < ic)) ? 1 : 0;
+            }
+            if (lane < nsel) sel_s[wl][1][rank] = make_float2(dc, __int_as_float(ic));
+            __syncwarp();
+            const int nres = min(nsel, K);
+            if (lane < nres) { const float2 v = sel_s[wl][1][lane]; L.d = v.x; L.i = __float_as_int(v.y); }
+            __syncwarp();
+            tau_d = nsel >= K ? __shfl_sync(FULL, L.d, K - 1) : INF;
+            if (a.use_radius || k.cover == INF) break;
+            if (tau_d < INF && tau_d < __fmul_rn(k.cover, k.cover)) break;
+            continue;  // not covered yet: next block size through the insertion path
+          }
+          L.init();
+        }
+      }
       for (int row0 = 0; row0 < nrows; row0 += 32) {
         // rows of the block: contiguous record ranges; flatten them with a prefix sum
         const int row = row0 + lane;
@@ -485,7 +592,7 @@ int grid_ball_query(const float* xyz, const float* new_xyz, int B, int N, int M,
   int rc = grid_build(xyz, nullptr, B, N, nsample, 1, radius, nullptr, workspace, &g, st);
   if (rc) return rc;
   GridKnnArgs k{new_xyz, nullptr, nullptr, B, M, nsample, 1, radius, nullptr, g, nullptr, idx, OUT_BALL};
-  grid_knn_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(k);
+  grid_knn_kernel<false><<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(k);
   TPG_CHECK_LAUNCH("grid_knn_kernel");
   return TPG_OK;
 }
@@ -508,7 +615,11 @@ int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes,
     return TPG_OK;
   }
   GridKnnArgs k{a.p1, qrec, a.len1, a.B, a.P1, a.K, a.use_radius, a.r, a.r_per_cloud, g, a.dists, a.idx, a.out_mode};
-  grid_knn_kernel<<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
+  // plain kNN with K <= 24 (<= 32 * GK_PER candidates in the first block at the grid's cell size): select-based kernel
+  if (a.out_mode == OUT_KNN && !a.use_radius && a.K <= 24)
+    grid_knn_kernel<true><<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
+  else
+    grid_knn_kernel<false><<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
   TPG_CHECK_LAUNCH("grid_knn_kernel");
   return TPG_OK;
 }
