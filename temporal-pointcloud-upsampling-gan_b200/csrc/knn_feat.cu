@@ -583,15 +583,15 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     __syncwarp();
     {
       const int sub = lane / lpr, ch = lane - sub * lpr;
-      for (int r0 = 0; r0 < ncand; r0 += 4 * rpi) {  // 4 independent loads in flight per lane
-        float4 v[4];
+      for (int r0 = 0; r0 < ncand; r0 += 8 * rpi) {  // 8 independent loads in flight per lane (all 32 rows at D = 32)
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int r = r0 + u * rpi + sub;
           if (r < ncand) v[u] = __ldg(reinterpret_cast<const float4*>(p2b + (size_t)wcand[r] * D) + ch);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int r = r0 + u * rpi + sub;
           if (r < ncand) *reinterpret_cast<float4*>(wtile + r * rstride + ch * 4) = v[u];
         }
