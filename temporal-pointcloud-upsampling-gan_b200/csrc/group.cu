@@ -539,11 +539,8 @@ template <typename CT>
 static int launch_csr_cluster(const int32_t* idx, const int64_t* item_len, int B, int N, int L, int Q, size_t smem,
                               int32_t* off, int32_t* items, cudaStream_t st) {
   auto kern = csr_cluster_kernel<CT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  // per call: the attribute is per device, and a process may drive several
+  TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * Q));
   cfg.blockDim = dim3(1024);

@@ -197,11 +197,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) group_bwd_staged_kernel(const S
 template <int NPT, int TCG>
 int launch_staged(const StagedArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto kern = group_bwd_staged_kernel<NPT, TCG>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM_BYTES));
-    attr_set = true;
-  }
+  // per call: the attribute is per device, and a process may drive several
+  TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM_BYTES));
   kern<<<grid, SB_THREADS, smem, st>>>(a);
   TPG_CHECK_LAUNCH("group_bwd_staged_kernel");
   return TPG_OK;
