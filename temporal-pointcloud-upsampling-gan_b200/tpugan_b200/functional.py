@@ -211,23 +211,65 @@ def inverse_index(idx, N: int) -> Tuple[torch.Tensor, torch.Tensor]:
 
 class _CsrCache:
     """Inverse indices keyed by the idx tensor they were built from.  Holding the idx
-    tensor keeps its storage alive, so (data_ptr, version) cannot alias a new tensor."""
+    tensor keeps its storage alive, so (data_ptr, version) cannot alias a new tensor.
+
+    With ``prefetch_enabled`` the grouping / gather *forward* already builds the inverse index its backward
+    will need, on a side stream that only waits for idx: the build leaves the critical path of the backward
+    pass (a chain of CSR build -> gradient per layer) and fills idle SMs during the forward.  ``get`` makes
+    the consuming stream wait for the build; ``join`` (end of a captured step) waits for builds nobody used."""
 
     def __init__(self, capacity: int = 16):
         self.capacity = capacity
         self.entries: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self.prefetch_enabled = False
+        self._pools = {}
+        self._rr = 0
+
+    @staticmethod
+    def _key(idx, N):
+        return (idx.data_ptr(), idx._version, tuple(idx.shape), N, idx.device.index)
+
+    def _insert(self, key, entry):
+        self.entries[key] = entry
+        cap = max(self.capacity, 256) if self.prefetch_enabled else self.capacity
+        while len(self.entries) > cap:
+            self.entries.popitem(last=False)
+
+    def prefetch(self, idx: torch.Tensor, N: int) -> None:
+        key = self._key(idx, N)
+        if key in self.entries:
+            return
+        dev = idx.device
+        pool = self._pools.get(dev.index)
+        if pool is None:
+            pool = self._pools[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        side = pool[self._rr % len(pool)]
+        self._rr += 1
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            off, items = inverse_index(idx, N)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._insert(key, (idx, off, items, done))
 
     def get(self, idx: torch.Tensor, N: int):
-        key = (idx.data_ptr(), idx._version, tuple(idx.shape), N, idx.device.index)
+        key = self._key(idx, N)
         hit = self.entries.get(key)
         if hit is not None:
             self.entries.move_to_end(key)
+            if hit[3] is not None:
+                torch.cuda.current_stream(idx.device).wait_event(hit[3])
             return hit[1], hit[2]
         off, items = inverse_index(idx, N)
-        self.entries[key] = (idx, off, items)
-        while len(self.entries) > self.capacity:
-            self.entries.popitem(last=False)
+        self._insert(key, (idx, off, items, None))
         return off, items
+
+    def join(self) -> None:
+        for e in self.entries.values():
+            if e[3] is not None:
+                torch.cuda.current_stream(e[0].device).wait_event(e[3])
 
     def clear(self):
         self.entries.clear()
@@ -387,6 +429,8 @@ class GroupingOperation(torch.autograd.Function):
     def forward(ctx, features, idx):
         ctx.N = features.shape[2]
         ctx.save_for_backward(idx)
+        if csr_cache.prefetch_enabled and features.requires_grad:
+            csr_cache.prefetch(idx, ctx.N)
         return group_fwd(features, idx)
 
     @staticmethod
@@ -404,6 +448,8 @@ class GatherOperation(torch.autograd.Function):
         _req(idx, "idx", torch.int32, 2)
         ctx.N = features.shape[2]
         ctx.save_for_backward(idx)
+        if csr_cache.prefetch_enabled and features.requires_grad:
+            csr_cache.prefetch(idx, ctx.N)
         return group_fwd(features, idx.unsqueeze(-1)).squeeze(-1)
 
     @staticmethod

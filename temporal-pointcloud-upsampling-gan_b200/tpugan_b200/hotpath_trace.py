@@ -302,6 +302,7 @@ class TraceReplay:
             ops.lanes_begin(2 * lanes)
         state: Dict[str, Any] = {"idx": [], "fwd": {}, "cloud": {}, "chamfer": None, "last_fps": None,
                                  "last_gather": None, "frnn": None, "csr": {}, "by_call": {}}
+        bwd_ids = self.__dict__.setdefault("_bwd_ids", {c["in"]["fwd_id"] for c in self.calls if "fwd_id" in c["in"]})
         prod: Dict[int, int] = {}   # id(tensor) -> call that produced it
         done: Dict[int, Any] = {}   # call -> completion event (multi-lane only)
         keep: List[Any] = []        # every produced tensor stays alive until the step ends (cross-stream use)
@@ -363,7 +364,7 @@ class TraceReplay:
                 used += [xyz, idx]
 
                 def run(xyz=xyz, idx=idx, i=i, n=n):
-                    out = ops.gather(ops.transpose12(xyz), idx)  # [B,3,M]
+                    out = ops.gather(ops.transpose12(xyz), idx, i["id"] in bwd_ids)  # [B,3,M]
                     new_xyz = ops.transpose12(out)
                     made(n, out, new_xyz)
                     state["last_gather"] = (xyz, new_xyz)
@@ -411,7 +412,7 @@ class TraceReplay:
                 def run(src=src, src_idx=src_idx, stride=stride, d=d, i=i, n=n):
                     idx = ops.stride_last(src_idx, stride) if stride > 1 else src_idx
                     f = ops.transpose12(src) if src is not None else d["f"]
-                    out = ops.group(f, idx)
+                    out = ops.group(f, idx, i["id"] in bwd_ids)
                     made(n, out, idx, f)
                     results.append((n, out))
                     state["fwd"][i["id"]] = idx
@@ -470,7 +471,9 @@ class TorchCudaOps:
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
     def new_step(self):
-        self._csr = {}
+        self.F.csr_cache.clear()
+        if self.F.csr_cache.capacity < 256:
+            self.F.csr_cache.capacity = 256  # a step keeps every inverse index until its backward
 
     def tick(self):
         e = self.torch.cuda.Event(enable_timing=True)
@@ -503,6 +506,7 @@ class TorchCudaOps:
     def lanes_end(self):
         t = self.torch
         t.cuda.set_stream(self._main)
+        self.F.csr_cache.join()  # prefetched inverse indices nobody consumed
         for s in self._streams[1:]:
             e = t.cuda.Event()
             e.record(s)
@@ -529,20 +533,22 @@ class TorchCudaOps:
     def fps(self, xyz, npoint):
         return self.F.fps(xyz, npoint)
 
-    def gather(self, f, idx):
+    def gather(self, f, idx, will_bwd=False):
+        if will_bwd and self.F.csr_cache.prefetch_enabled:
+            self.F.csr_cache.prefetch(idx, f.shape[2])
         return self.F.group_fwd(f, idx.unsqueeze(-1)).squeeze(-1)
 
     def ball_query(self, r, ns, xyz, new_xyz):
         return self.F.ball_query(r, ns, xyz, new_xyz)
 
-    def group(self, f, idx):
+    def group(self, f, idx, will_bwd=False):
+        if will_bwd and self.F.csr_cache.prefetch_enabled:
+            self.F.csr_cache.prefetch(idx, f.shape[2])
         return self.F.group_fwd(f, idx)
 
     def group_bwd(self, grad_out, idx, N):
-        key = (idx.data_ptr(), N)
-        if key not in self._csr:  # one inverse index per idx tensor, shared by its groupings
-            self._csr[key] = (idx,) + tuple(self.F.inverse_index(idx, N))
-        _, off, items = self._csr[key]
+        # one inverse index per idx tensor, shared by its groupings (built here unless the forward prefetched it)
+        off, items = self.F.csr_cache.get(idx, N)
         return self.F.group_bwd(grad_out, off, items, N)
 
     def chamfer(self, src, tgt, directions):
@@ -592,8 +598,8 @@ class ShimApiOps(TorchCudaOps):
     def fps(self, xyz, npoint):
         return self.pu.furthest_point_sample(xyz, npoint)
 
-    def gather(self, f, idx):
-        f = f.detach().requires_grad_(True)
+    def gather(self, f, idx, will_bwd=False):
+        f = f.detach().requires_grad_(will_bwd or not self.F.csr_cache.prefetch_enabled)
         out = self.pu.gather_operation(f, idx)
         self._fwd[idx.data_ptr()] = (f, out)
         return out.detach()
@@ -601,8 +607,8 @@ class ShimApiOps(TorchCudaOps):
     def ball_query(self, r, ns, xyz, new_xyz):
         return self.pu.ball_query(r, ns, xyz, new_xyz)
 
-    def group(self, f, idx):
-        f = f.detach().requires_grad_(True)
+    def group(self, f, idx, will_bwd=False):
+        f = f.detach().requires_grad_(will_bwd or not self.F.csr_cache.prefetch_enabled)
         out = self.pu.grouping_operation(f, idx)
         self._fwd.setdefault(("g", idx.data_ptr(), tuple(out.shape)), []).append((f, out))
         return out

@@ -566,8 +566,9 @@ def test_gather_rows(F, oracle):
     np.testing.assert_array_equal(F.gather_rows(cu(x), cu(idx)).cpu().numpy(), oracle.gather_rows(x, idx))
 
 
+@pytest.mark.parametrize("prefetch", [False, True])
 @pytest.mark.parametrize("name,batch", [("action", 2), ("fluid", 2)])
-def test_multi_stream_replay_equals_single_stream(F, name, batch):
+def test_multi_stream_replay_equals_single_stream(F, name, batch, prefetch):
     """TraceReplay.run_step(lanes=S) issues independent chains of the recorded step on S streams; every
     result (all grouping outputs / gradients and the Chamfer loss) must equal the in-order replay."""
     import os
@@ -588,7 +589,12 @@ def test_multi_stream_replay_equals_single_stream(F, name, batch):
     ops.finish = finish
     for lanes in (1, 3, 32):
         finish.__defaults__[0][0] = lanes
-        loss = rp.run_step(lanes=lanes)
+        # eager inverse-index builds at forward time (side streams) only for the multi-stream runs
+        F.csr_cache.prefetch_enabled = prefetch and lanes > 1
+        try:
+            loss = rp.run_step(lanes=lanes)
+        finally:
+            F.csr_cache.prefetch_enabled = False
         torch.cuda.synchronize()
         got[("loss", lanes)] = float(loss)
     for lanes in (3, 32):
