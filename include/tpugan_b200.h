@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 6
+#define TPG_ABI_VERSION 7
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -88,6 +88,26 @@ int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                 const int64_t* lengths2, int B, int P1, int P2, int D, int K,
                 float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,
                 tpg_stream_t stream);
+
+/* Memoised search (exact): the reference's IDGCNLayer runs three knn_points calls on bit-identical
+ * feature maps (gcn_lib/pointnet/gcn.py:258-265: K = 9, 20, 20) — each on a fresh .contiguous() copy,
+ * so only a content comparison can tell.  Everything stays on the device and capturable:
+ *   tpg_bytes_equal_and   flag[0] is cleared when the two buffers differ (caller sets it to 1 first;
+ *                         several comparisons may share one flag)
+ *   tpg_knn_cond_f32      tpg_knn_f32, except that on the tensor-core path every kernel of the call
+ *                         returns at once when *skip_flag != 0 (skip_flag may be NULL; other paths
+ *                         ignore it and compute)
+ *   tpg_knn_take_prefix   when *flag != 0: dists/idx[r, :K] = cached_dists/idx[r, :K] of a cached
+ *                         [rows, Kc] result, Kc >= K (the K nearest are a prefix of the Kc nearest
+ *                         in the canonical (d2, index) order)
+ * tpugan_b200.functional.knn_memo drives them; it never keeps anything across train steps.       */
+int tpg_bytes_equal_and(const void* a, const void* b, size_t nbytes, int32_t* flag, tpg_stream_t stream);
+int tpg_knn_cond_f32(const float* p1, const float* p2, const int64_t* lengths1,
+                     const int64_t* lengths2, int B, int P1, int P2, int D, int K,
+                     float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,
+                     const int32_t* skip_flag, tpg_stream_t stream);
+int tpg_knn_take_prefix(const int32_t* flag, const float* cached_dists, const int64_t* cached_idx, int Kc,
+                        float* dists, int64_t* idx, int K, long long rows, tpg_stream_t stream);
 
 /* ---- K3: fixed-radius nearest neighbours --------------------------------
  * replaces frnn.frnn_grid_points(points1, points2, lengths1, lengths2, K, r,

@@ -91,7 +91,7 @@ class Recorder:
     def record(self, op, inputs, outputs):
         if not self.enabled:
             return
-        inputs = {k: v for k, v in inputs.items() if not (k == "deps" and v is None)}
+        inputs = {k: v for k, v in inputs.items() if not (k in ("deps", "p1_sha", "p2_sha") and v is None)}
         if self.shapes_only:
             inputs = {k: _describe(v) for k, v in inputs.items()}
             outputs = {k: _describe(v) for k, v in outputs.items()}

@@ -10,6 +10,12 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+def _sha(t):
+    import hashlib
+
+    return hashlib.sha1(np.ascontiguousarray(_np(t)).tobytes()).hexdigest()[:16] if recorder.enabled else None
+
+
 def _out(*tensors):
     """tag freshly made output tensors with the call recorded last (dependency tracking)"""
     recorder.tag(*tensors)
@@ -25,7 +31,10 @@ def knn(p1, p2, K, lengths1=None, lengths2=None):
     deps = recorder.deps(p1=p1, p2=p2)
     d, i = oracle.knn(_np(p1), _np(p2), K, None if lengths1 is None else _np(lengths1),
                       None if lengths2 is None else _np(lengths2))
-    recorder.record("knn", dict(p1=_c(_np(p1)), p2=_c(_np(p2)), K=K, deps=deps), dict(dists=d, idx=i))
+    # content digests: calls that received bit-identical clouds (IDGCNLayer runs three searches on one feature
+    # map, gcn.py:258-265) are replayed on bit-identical inputs
+    recorder.record("knn", dict(p1=_c(_np(p1)), p2=_c(_np(p2)), K=K, deps=deps, p1_sha=_sha(p1), p2_sha=_sha(p2)),
+                    dict(dists=d, idx=i))
     return _out(torch.from_numpy(d), torch.from_numpy(i))
 
 

@@ -19,6 +19,7 @@ struct KnnArgs {
   float* dists;
   void* idx;
   int out_mode;
+  const int32_t* skip = nullptr;  // device flag: nonzero -> the tensor-core path returns without writing (memoised search)
 };
 
 // knn.cu

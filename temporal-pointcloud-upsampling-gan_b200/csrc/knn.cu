@@ -209,10 +209,73 @@ TPG_API size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K) {
   return grid_eligible(D, P2, K) ? grid_workspace_bytes(B, P2) : 0;
 }
 
+namespace tpg {
+// flag[0] &= (a == b) bytewise; nbytes % 16 == 0, 16-byte aligned
+__global__ void bytes_equal_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, size_t n16,
+                                   int32_t* __restrict__ flag) {
+  bool diff = false;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n16; e += (size_t)gridDim.x * blockDim.x) {
+    const uint4 x = __ldg(a + e), y = __ldg(b + e);
+    diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+  }
+  if (diff) *flag = 0;
+}
+// flag != 0: out[r, :K] = cached[r, :Kc][:K]
+__global__ void knn_take_prefix_kernel(const int32_t* __restrict__ flag, const float* __restrict__ cd,
+                                       const int64_t* __restrict__ ci, int Kc, float* __restrict__ od,
+                                       int64_t* __restrict__ oi, int K, long long rows) {
+  if (*flag == 0) return;
+  const long long total = rows * K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / K;
+    const int k = (int)(e - r * K);
+    od[e] = cd[r * Kc + k];
+    oi[e] = ci[r * Kc + k];
+  }
+}
+}  // namespace tpg
+
+TPG_API int tpg_bytes_equal_and(const void* a, const void* b, size_t nbytes, int32_t* flag, tpg_stream_t stream) {
+  TPG_REQUIRE(flag, TPG_EINVAL, "bytes_equal: null flag");
+  if (nbytes == 0) return TPG_OK;
+  TPG_REQUIRE(a && b, TPG_EINVAL, "bytes_equal: null pointer");
+  TPG_REQUIRE(nbytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0,
+              TPG_EUNSUPPORTED, "bytes_equal: needs 16-byte aligned buffers of a multiple of 16 bytes");
+  const size_t n16 = nbytes / 16;
+  const unsigned blocks = (unsigned)min((n16 + 255) / 256, (size_t)num_sms() * 8);
+  bytes_equal_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(a),
+                                                           reinterpret_cast<const uint4*>(b), n16, flag);
+  TPG_CHECK_LAUNCH("bytes_equal_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_knn_take_prefix(const int32_t* flag, const float* cached_dists, const int64_t* cached_idx, int Kc,
+                                float* dists, int64_t* idx, int K, long long rows, tpg_stream_t stream) {
+  TPG_REQUIRE(K >= 1 && Kc >= K && rows >= 0, TPG_EINVAL, "knn_take_prefix: bad sizes K=%d Kc=%d", K, Kc);
+  if (rows == 0) return TPG_OK;
+  TPG_REQUIRE(flag && cached_dists && cached_idx && dists && idx, TPG_EINVAL, "knn_take_prefix: null pointer");
+  const long long total = rows * K;
+  const unsigned blocks = (unsigned)min((total + 255) / 256, (long long)num_sms() * 8);
+  knn_take_prefix_kernel<<<blocks, 256, 0, as_stream(stream)>>>(flag, cached_dists, cached_idx, Kc, dists, idx, K, rows);
+  TPG_CHECK_LAUNCH("knn_take_prefix_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_knn_cond_f32(const float* p1, const float* p2, const int64_t* lengths1, const int64_t* lengths2, int B,
+                             int P1, int P2, int D, int K, float* dists, int64_t* idx, void* workspace,
+                             size_t workspace_bytes, const int32_t* skip_flag, tpg_stream_t stream);
+
 TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                         const int64_t* lengths2, int B, int P1, int P2, int D, int K,
                         float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,
                         tpg_stream_t stream) {
+  return tpg_knn_cond_f32(p1, p2, lengths1, lengths2, B, P1, P2, D, K, dists, idx, workspace, workspace_bytes, nullptr,
+                          stream);
+}
+
+TPG_API int tpg_knn_cond_f32(const float* p1, const float* p2, const int64_t* lengths1, const int64_t* lengths2, int B,
+                             int P1, int P2, int D, int K, float* dists, int64_t* idx, void* workspace,
+                             size_t workspace_bytes, const int32_t* skip_flag, tpg_stream_t stream) {
   TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0, TPG_EINVAL, "knn: negative size");
   TPG_REQUIRE(D >= 1 && D <= 256, TPG_EUNSUPPORTED, "knn: D=%d outside [1,256]", D);
   TPG_REQUIRE(K >= 1 && K <= 1024, TPG_EUNSUPPORTED, "knn: K=%d outside [1,1024]", K);
@@ -220,6 +283,7 @@ TPG_API int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths
   if (B == 0 || P1 == 0) return TPG_OK;
   TPG_REQUIRE(p1 && (p2 || P2 == 0) && dists && idx, TPG_EINVAL, "knn: null pointer");
   KnnArgs a{p1, p2, lengths1, lengths2, B, P1, P2, D, K, 0.f, nullptr, 0, dists, idx, OUT_KNN};
+  a.skip = skip_flag;  // honoured by the tensor-core path only; the other paths simply compute
   if (P2 > 0 && knn_feat_eligible(a)) return knn_feat_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   if (grid_eligible(D, P2, K)) return grid_knn_dispatch(a, workspace, workspace_bytes, as_stream(stream));
   return knn_dispatch(a, as_stream(stream));

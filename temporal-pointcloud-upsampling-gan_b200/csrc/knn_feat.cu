@@ -65,6 +65,7 @@ struct FeatArgs {
   int* fb_count;           // [1]
   int* fb_list;            // [B*P1]
   long long* dbg;          // [ctas][8] phase timestamps (tools/bench_knn_feat.py)
+  const int32_t* skip;     // nonzero -> every kernel of the call returns at once (results come from a memoised call)
 };
 
 struct FeatMaps {  // TMA descriptors: [B*P, D] fp32, box 32 floats x 128 rows, 128B swizzle
@@ -229,7 +230,8 @@ __device__ __forceinline__ float ordered_key_inv(unsigned uk) {
 
 // ---- squared norms + per-cloud max ---------------------------------------------------------
 __global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int D, float* __restrict__ nrm,
-                                 unsigned* __restrict__ nmax) {
+                                 unsigned* __restrict__ nmax, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   float s = 0.0f;
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   __shared__ float limit_s[FT_NQ];
   __shared__ int cnt_s[FT_NQ];
 
+  if (a.skip && *a.skip) return;  // (uniform) memoised call: nothing to do, nothing allocated yet
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, colgrp = warp >> 2;
   const int nq0 = colgrp * FT_QW;  // first query (column) of this warp
@@ -638,6 +641,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 template <int CH>  // CH = D / 4 float4 chunks per row (8 or 16)
 __global__ void __launch_bounds__(512) knn_feat_fallback_kernel(FeatArgs a) {
   __shared__ float2 part_s[16][32];
+  if (a.skip && *a.skip) return;
   const int total = *a.fb_count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float INF = __int_as_float(0x7f800000);
@@ -805,18 +809,18 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_CUDA(cudaMemsetAsync(w.nmax2, 0, (size_t)((char*)w.nrm1 - (char*)w.nmax2), st));  // nmax2 + fb_count
   {
     dim3 g2(ceil_div(k.P2, 128), k.B);
-    feat_norm_kernel<<<g2, 128, 0, st>>>(k.p2, k.B, k.P2, k.D, w.nrm2, w.nmax2);
+    feat_norm_kernel<<<g2, 128, 0, st>>>(k.p2, k.B, k.P2, k.D, w.nrm2, w.nmax2, k.skip);
     TPG_CHECK_LAUNCH("feat_norm_kernel");
     if (k.p1 == k.p2 && k.P1 == k.P2) {
       w.nrm1 = w.nrm2;  // self search: one norm pass
     } else {
       dim3 g1(ceil_div(k.P1, 128), k.B);
-      feat_norm_kernel<<<g1, 128, 0, st>>>(k.p1, k.B, k.P1, k.D, w.nrm1, nullptr);
+      feat_norm_kernel<<<g1, 128, 0, st>>>(k.p1, k.B, k.P1, k.D, w.nrm1, nullptr, k.skip);
       TPG_CHECK_LAUNCH("feat_norm_kernel");
     }
   }
   FeatArgs a{k.p1, k.p2, k.len1, k.len2, k.B, k.P1, k.P2, k.D, k.K, w.nrm1, w.nrm2, w.nmax2,
-             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr};
+             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr, k.skip};
   const size_t aux = max((size_t)FT_NQ * 64 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
   const size_t smem = (size_t)k.D * 512 * FT_STAGES + (size_t)k.D * 4 * FT_NQ + 1024 + aux;
   TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -86,14 +86,90 @@ def knn(p1, p2, K: int, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, tor
     P2 = p2.shape[1]
     l1 = _lengths(lengths1, B, P1, p1.device, "lengths1")
     l2 = _lengths(lengths2, B, P2, p1.device, "lengths2")
+    if knn_memo.enabled and l1 is None and l2 is None and knn_memo.eligible(p1, p2, K):
+        return knn_memo.run(p1, p2, K)
+    return _knn_raw(p1, p2, K, l1, l2)
+
+
+def _knn_raw(p1, p2, K, l1=None, l2=None, skip_flag=None):
+    B, P1, D = p1.shape
+    P2 = p2.shape[1]
     dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     with _on_device(p1.device):
         nbytes = _lib.load().tpg_knn_workspace_bytes(B, P1, P2, D, K)  # > 0: tensor-core (tcgen05) path
         ws = _ws(nbytes, p1.device) if nbytes else None
-        _lib.call("tpg_knn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, _ptr(dists), _ptr(idx),
-                  _ptr(ws), nbytes, _stream())
+        _lib.call("tpg_knn_cond_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, _ptr(dists), _ptr(idx),
+                  _ptr(ws), nbytes, _ptr(skip_flag), _stream())
     return dists, idx
+
+
+class _KnnMemo:
+    """Exact memoisation of repeated feature-space searches inside one train step (opt-in).
+
+    The reference's IDGCNLayer runs knn_points three times on bit-identical feature maps (K = 9, 20, 20;
+    gcn_lib/pointnet/gcn.py:258-265), each on a fresh ``.contiguous()`` copy.  With ``enabled`` a call on the
+    tensor-core path is compared on the device (bytes, not pointers) with the inputs of the most recent call of the
+    same shape; the search kernels of the new call return at once when the contents match, and the result is
+    the prefix of the cached list (the K nearest are a prefix of the Kc >= K nearest in the canonical order).
+    Searches with K < 20 are computed with 20 neighbours so that the following K = 20 calls can reuse them.
+    No host synchronisation, capturable; ``clear()`` at the end of a step (nothing survives a step)."""
+
+    KMIN = 20
+
+    def __init__(self, capacity: int = 4):
+        self.enabled = False
+        self.capacity = capacity
+        self.entries = []  # (p1, p2, v1, v2, Kc, dists, idx, event)
+        self._retired = []  # evicted entries stay alive until clear(): another stream may still read them
+
+    @staticmethod
+    def eligible(p1, p2, K):
+        D = p1.shape[2]
+        return D in (32, 64) and p2.shape[1] >= 1024 and K <= 24 and p1.is_contiguous() and p2.is_contiguous() \
+            and p1.data_ptr() % 16 == 0 and p2.data_ptr() % 16 == 0
+
+    def clear(self):
+        self.entries.clear()
+        self._retired.clear()
+
+    def _remember(self, p1, p2, Kc, dists, idx):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(p1.device))
+        self.entries.append((p1, p2, p1._version, p2._version, Kc, dists, idx, ev))
+        self._retired.extend(self.entries[:-self.capacity])
+        del self.entries[:-self.capacity]
+
+    def run(self, p1, p2, K):
+        dev = p1.device
+        Kc = max(K, self.KMIN)
+        hit = None
+        for e in reversed(self.entries):  # the most recent call of this shape (a layer's searches are consecutive)
+            if e[0].shape == p1.shape and e[1].shape == p2.shape and e[0].device == dev:
+                if e[4] >= Kc and e[0]._version == e[2] and e[1]._version == e[3]:
+                    hit = e
+                break
+        if hit is None:
+            dists, idx = _knn_raw(p1, p2, Kc)
+        else:
+            cp1, cp2, _, _, Kh, cd, ci, ev = hit
+            torch.cuda.current_stream(dev).wait_event(ev)
+            flag = torch.ones(1, dtype=torch.int32, device=dev)
+            with _on_device(dev):
+                _lib.call("tpg_bytes_equal_and", _ptr(p1), _ptr(cp1), p1.numel() * 4, _ptr(flag), _stream())
+                if not (p2 is p1 and cp2 is cp1):
+                    _lib.call("tpg_bytes_equal_and", _ptr(p2), _ptr(cp2), p2.numel() * 4, _ptr(flag), _stream())
+            dists, idx = _knn_raw(p1, p2, Kc, skip_flag=flag)
+            with _on_device(dev):
+                _lib.call("tpg_knn_take_prefix", _ptr(flag), _ptr(cd), _ptr(ci), Kh, _ptr(dists), _ptr(idx), Kc,
+                          p1.shape[0] * p1.shape[1], _stream())
+        self._remember(p1, p2, Kc, dists, idx)
+        if Kc == K:
+            return dists, idx
+        return dists[:, :, :K].contiguous(), idx[:, :, :K].contiguous()
+
+
+knn_memo = _KnnMemo()
 
 
 def frnn(p1, p2, K: int, r, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -608,3 +608,36 @@ def test_library_was_used(F):
     import tpugan_b200
 
     assert tpugan_b200.launch_count() > 0
+
+
+def test_knn_memo_is_exact_and_skips_only_identical_inputs(F, oracle):
+    """functional.knn_memo: repeated searches on bit-identical clouds (fresh copies) return the plain results;
+    a changed cloud of the same shape is recomputed; K < 20 is served as a prefix of a 20-neighbour search."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((2, 1024, 32)).astype(np.float32)
+    y = x.copy()
+    y[1, 500, 3] += 1e-3                      # one element differs
+    ref = {K: oracle.knn(x, x, K) for K in (9, 20)}
+    refy = oracle.knn(y, y, 20)
+    F.knn_memo.clear()
+    F.knn_memo.enabled = True
+    try:
+        launches = []
+        import tpugan_b200
+
+        for K, arr, want in [(9, x, ref[9]), (20, x, ref[20]), (20, x, ref[20]), (20, y, refy), (9, y, None), (20, x, ref[20])]:
+            t = cu(arr)                       # a fresh tensor every time, like the reference's .contiguous() copies
+            n0 = tpugan_b200.launch_count()
+            d, i = F.knn(t, t, K)
+            launches.append(tpugan_b200.launch_count() - n0)
+            assert d.is_contiguous() and i.is_contiguous() and d.shape == (2, 1024, K)
+            if want is None:
+                want = (refy[0][:, :, :9], refy[1][:, :, :9])
+            np.testing.assert_array_equal(i.cpu().numpy(), want[1])
+            np.testing.assert_array_equal(d.cpu().numpy(), want[0])
+    finally:
+        F.knn_memo.enabled = False
+        F.knn_memo.clear()
+    # plain calls afterwards are untouched
+    d, i = F.knn(cu(x), cu(x), 9)
+    np.testing.assert_array_equal(i.cpu().numpy(), ref[9][1])

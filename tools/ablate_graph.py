@@ -14,6 +14,7 @@ from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
 _lib.set_option("fps.sms_per_cloud", int(os.environ.get("FPS_SMS", "1")))
 from tpugan_b200 import functional as _Fn  # noqa: E402
 _Fn.csr_cache.prefetch_enabled = os.environ.get("CSR_PREFETCH", "1") == "1"
+_Fn.knn_memo.enabled = os.environ.get("KNN_MEMO", "0") == "1"
 _lib.set_option("fps.exclusive_sm", int(os.environ.get("FPS_EXCL", "1")))
 
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 64

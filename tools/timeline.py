@@ -19,6 +19,7 @@ lib = _lib.load()
 _lib.set_option("fps.sms_per_cloud", 1)
 from tpugan_b200 import functional as _Fn  # noqa: E402
 _Fn.csr_cache.prefetch_enabled = os.environ.get("CSR_PREFETCH", "1") == "1"
+_Fn.knn_memo.enabled = os.environ.get("KNN_MEMO", "0") == "1"
 _lib.set_option("fps.exclusive_sm", 1)
 ts_fn = lib.tpg_debug_timestamp
 ts_fn.restype = ctypes.c_int
