@@ -279,3 +279,17 @@ def test_chamfer_against_float64(oracle):
         sm[b, p, c] -= eps
         fd = (val(sp, t) - val(sm, t)) / (sp[b, p, c].astype(np.float64) - sm[b, p, c])
         np.testing.assert_allclose(gs[b, p, c], fd, rtol=2e-2, atol=1e-3)
+
+
+def test_ball_query_wrapper_equals_plain_knn():
+    """discriminator.py:24-40 (`ball_query_wrapper`): FRNN(K, r) with its -1 slots filled from kNN(K) is the kNN
+    list itself — the in-radius hits are a prefix of it in the canonical (d2, index) order."""
+    import oracle
+    import synth
+
+    rng = np.random.default_rng(3)
+    for B, P1, P2, K, r in [(2, 256, 256, 32, 0.08), (2, 300, 500, 16, 0.05), (1, 100, 20, 32, 0.2), (2, 256, 1024, 32, 0.03)]:
+        a, b = synth.fluid_cloud(rng, B, P1), synth.fluid_cloud(rng, B, P2)
+        _, fi = oracle.frnn(a, b, K, r)
+        _, ki = oracle.knn(a, b, K)
+        np.testing.assert_array_equal(np.where(fi == -1, ki, fi), ki)
