@@ -18,20 +18,22 @@
 //   * otherwise (near-duplicate features, huge norms, buffer overflow) the query goes to
 //     an exact SIMT fallback (a fraction of a percent of the queries on N(0,1) features).
 //
-// Kernel anatomy (one CTA = 128 queries of one cloud, 16 warps, one wave of CTAs):
+// Kernel anatomy (one CTA = 128 queries of one cloud, one wave of CTAs; 16 epilogue warps + one MMA-issuer warp
+// + one TMA-producer warp):
 //   MMA shape M=128 (candidates) x N=128 (queries) x K=8 per instruction, cta_group::1.
 //   Candidates are the M operand on purpose: TMEM lane == candidate, so a thread owns one
 //   candidate row of the accumulator tile and sweeps its queries without any cross-lane
-//   operation.  smem: 3-stage ring of candidate tiles (128 x D fp32, K-major, 128B-swizzled,
+//   operation.  smem: 4-stage ring of candidate tiles (128 x D fp32, K-major, 128B-swizzled,
 //   filled by TMA: cp.async.bulk.tensor.2d, one box per 32-float K-slab, complete_tx on a
 //   per-stage mbarrier; UMMA descriptors built by hand) + the query tile; TMEM: 4 x 128 columns
-//   (the issue-to-commit latency of a tile is ~2000 cycles although the tensor pipe is busy for
-//   ~180 of them, so three MMAs are kept in flight).  mbarrier pipeline, no CTA barrier in the loop:
-//     full[stage]   TMA -> MMA issuer        tile landed
-//     done[buf]     tcgen05.commit -> all     accumulator ready, smem stage free
-//     tfree[buf]    16 warps -> MMA issuer    accumulator drained (tcgen05.ld complete)
-//   Per tile u: [tid 0] wait full/tfree, issue MMA(u+3); all: wait done(u); [tid 0] TMA tile u+4;
-//   tcgen05.ld -> registers; per-lane min / predicated append; arrive tfree(u).
+//   (three MMAs in flight behind the tile being drained).  mbarrier pipeline, no CTA barrier in the loop:
+//     full[stage]   TMA -> MMA issuer            tile landed
+//     done[buf]     tcgen05.commit -> epilogue, producer   accumulator ready, smem stage free
+//     tfree[buf]    16 epilogue warps -> MMA issuer         accumulator drained (tcgen05.ld complete)
+//   issuer warp (one thread): for every tile u: wait full / tfree, issue D/8 MMAs, commit;
+//   producer warp (one thread): wait done(u), TMA tile u+4 into the stage MMA(u) read;
+//   epilogue warps: wait done(u); tcgen05.ld -> registers; per-lane min (pass 0) / predicated append
+//   (pass 1); arrive tfree(u).
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -75,10 +77,6 @@ struct FeatMaps {  // TMA descriptors: [B*P, D] fp32, box 32 floats x 128 rows, 
 // ---- PTX wrappers -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -352,7 +350,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     for (int u0 = 0; u0 < FT_STAGES && u0 < U; ++u0) load_tile(u0 % T, u0);
   }
 
-  // [tid 0] MMA(u): needs tile u in smem and TMEM buffer u&1 drained by the epilogue of u-2
+  // MMA(u): needs tile u in smem and TMEM buffer u % 4 drained by the epilogue of u - 4
   auto issue_mma = [&](int u) {
     const int s = u % FT_NBUF;  // TMEM buffer / mbarrier
     mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
@@ -490,7 +488,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         }
       }
     }
-    // this warp has drained TMEM buffer u&1 (tcgen05.wait::ld inside tmem_ld32): MMA(u+2) may overwrite it.
+    // this warp has drained TMEM buffer u % 4 (tcgen05.wait::ld inside tmem_ld32): MMA(u+4) may overwrite it.
     // No CTA-wide barrier in the loop: warps run ahead until the next MMA-done barrier.
     tc_fence_before();
     __syncwarp();

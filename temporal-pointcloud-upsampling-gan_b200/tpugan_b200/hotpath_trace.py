@@ -478,7 +478,6 @@ class TorchCudaOps:
         from . import functional as F
 
         self.torch, self.F, self.device = torch, F, torch.device(device)
-        self._csr = {}
 
     def array(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
