@@ -167,7 +167,11 @@ int tpg_fps_start_f32(const float* pts, int B, int N, int D, int k,
  * ascending (m,j) order, through an inverse index (CSR) built once per idx
  * tensor by tpg_inverse_index_build and shared by every grouping call that
  * reuses that idx.
- *   seg_offsets [B,N+1] int32, seg_items [B,L] int32 (L = M*k; item = m*k+j). */
+ *   seg_offsets [B,N+1] int32, seg_items [B,L] int32 (L = M*k; item = m*k+j).
+ *   Contract of tpg_group_bwd_f32: the items of a segment are ASCENDING (what
+ *   tpg_inverse_index_build produces) and lie in [0,L); the shared-memory-staged
+ *   kernel walks them with a cursor through chunks of the grad_out rows, so an
+ *   unsorted list would drop contributions. */
 int tpg_group_fwd_f32(const float* f, const int32_t* idx, const float* center,
                       int B, int C, int N, int M, int k, float* out,
                       tpg_stream_t stream);
