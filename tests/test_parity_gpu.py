@@ -409,7 +409,10 @@ def test_group_fwd_exact(F, oracle, B, C, N, M, k):
                                             (3, 32, 2048, 2048, 20, False), (2, 64, 256, 256, 32, True),
                                             (2, 20, 1000, 1024, 12, False), (1, 8, 3000, 2048, 16, False),
                                             (1, 130, 96, 4096, 16, True), (2, 35, 2048, 1024, 32, True),
-                                            (1, 2, 512, 30000, 20, True)])
+                                            (1, 2, 512, 30000, 20, True),
+                                            # staged variants <4,2>, <1,2>, <1,4> (points per thread, channels per item walk)
+                                            (2, 80, 3000, 2048, 8, False), (4, 40, 1000, 1024, 12, True),
+                                            (8, 40, 1000, 1024, 12, False)])
 def test_group_bwd_deterministic_and_exact(F, oracle, B, C, N, M, k, hubs):
     rng = np.random.default_rng(10)
     f, idx = make_group(rng, B, C, N, M, k, hubs)
