@@ -93,6 +93,8 @@ KNN_GRID_CASES = [
     (2, 3000, 5000, 16, "fluid"), (1, 8192, 8192, 20, "fluid"), (2, 4096, 4096, 32, "dup"), (1, 4096, 4096, 8, "dummy"),
     (1, 4913, 4913, 9, "lattice"), (2, 500, 2048, 1, "fluid"), (1, 700, 2500, 12, "outside"), (1, 300, 2048, 5, "flat"),
     (1, 64, 3000, 3, "same"),
+    # select-based kernel (K <= 24) with ties at the K-th distance / more than 32 candidates under the bound
+    (2, 4096, 4096, 20, "dup"), (1, 2197, 2197, 24, "lattice"), (1, 2048, 2048, 20, "featdup3"),
 ]
 
 
@@ -106,6 +108,10 @@ def make_grid_pair(rng, B, P1, P2, kind):
         b[..., 2] = 0.125
         a = synth.fluid_cloud(rng, B, P1)
         return a, b
+    if kind == "featdup3":  # 40 copies of each of ~51 distinct points: every K-th distance is a 40-way tie
+        base = synth.fluid_cloud(rng, B, (P2 + 39) // 40)
+        b = np.ascontiguousarray(np.repeat(base, 40, axis=1)[:, :P2])
+        return b[:, :P1].copy(), b
     if kind == "same":      # every candidate at the same place
         b = np.full((B, P2, 3), 0.25, np.float32)
         return synth.fluid_cloud(rng, B, P1), b
