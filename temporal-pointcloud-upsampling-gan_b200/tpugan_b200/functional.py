@@ -14,6 +14,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
+from .recording import log as _log
 
 _vp = ctypes.c_void_p
 
@@ -86,9 +87,14 @@ def knn(p1, p2, K: int, lengths1=None, lengths2=None) -> Tuple[torch.Tensor, tor
     P2 = p2.shape[1]
     l1 = _lengths(lengths1, B, P1, p1.device, "lengths1")
     l2 = _lengths(lengths2, B, P2, p1.device, "lengths2")
+    rec = _log.begin("knn", p1=p1, p2=p2, K=int(K), lengths1=l1, lengths2=l2) if _log.on else None
     if knn_memo.enabled and l1 is None and l2 is None and knn_memo.eligible(p1, p2, K):
-        return knn_memo.run(p1, p2, K)
-    return _knn_raw(p1, p2, K, l1, l2)
+        dists, idx = knn_memo.run(p1, p2, K)
+    else:
+        dists, idx = _knn_raw(p1, p2, K, l1, l2)
+    if rec is not None:
+        _log.end(rec, dists=dists, idx=idx)
+    return dists, idx
 
 
 def _knn_raw(p1, p2, K, l1=None, l2=None, skip_flag=None):
@@ -139,6 +145,12 @@ class _KnnMemo:
         self.entries.append((p1, p2, p1._version, p2._version, Kc, dists, idx, ev))
         self._retired.extend(self.entries[:-self.capacity])
         del self.entries[:-self.capacity]
+        # evicted entries only have to outlive the kernels that may still read them (another stream may be
+        # comparing against them): drop those whose event has completed, so that an uncaptured train loop over
+        # the drop-in packages does not accumulate every call's tensors.  Under stream capture events cannot be
+        # queried; a captured step calls clear() when it ends.
+        if self._retired and not torch.cuda.is_current_stream_capturing():
+            self._retired = [e for e in self._retired if not e[7].query()]
 
     def run(self, p1, p2, K):
         dev = p1.device
@@ -164,8 +176,10 @@ class _KnnMemo:
                 _lib.call("tpg_knn_take_prefix", _ptr(flag), _ptr(cd), _ptr(ci), Kh, _ptr(dists), _ptr(idx), Kc,
                           p1.shape[0] * p1.shape[1], _stream())
         self._remember(p1, p2, Kc, dists, idx)
+        # the caller always gets private copies: the reference edits neighbour lists in place
+        # (gcn_lib/pointnet/gcn.py:44, discriminator.py:39), which must never reach the cached result
         if Kc == K:
-            return dists, idx
+            return dists.clone(), idx.clone()
         return dists[:, :, :K].contiguous(), idx[:, :, :K].contiguous()
 
 
@@ -193,6 +207,8 @@ def frnn(p1, p2, K: int, r, lengths1=None, lengths2=None) -> Tuple[torch.Tensor,
             r_dev = r.to(device=p1.device, dtype=torch.float32).expand(B).contiguous()
     else:
         r_host = float(r)
+    rec = _log.begin("frnn", p1=p1, p2=p2, K=int(K), r=(r_dev if r_dev is not None else r_host), lengths1=l1,
+                     lengths2=l2) if _log.on else None
     dists = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     idx = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     with _on_device(p1.device):
@@ -200,6 +216,8 @@ def frnn(p1, p2, K: int, r, lengths1=None, lengths2=None) -> Tuple[torch.Tensor,
         ws = _ws(nbytes, p1.device)
         _lib.call("tpg_frnn_f32", _ptr(p1), _ptr(p2), _ptr(l1), _ptr(l2), B, P1, P2, D, K, r_host, _ptr(r_dev),
                   _ptr(dists), _ptr(idx), _ptr(ws), ws.numel(), _stream())
+    if rec is not None:
+        _log.end(rec, dists=dists, idx=idx)
     return dists, idx
 
 
@@ -211,12 +229,16 @@ def ball_query(radius: float, nsample: int, xyz, new_xyz) -> torch.Tensor:
         raise RuntimeError("ball_query expects xyz (B,N,3) and new_xyz (B,M,3)")
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
+    rec = _log.begin("ball_query", xyz=xyz, new_xyz=new_xyz, radius=float(radius), nsample=int(nsample)) \
+        if _log.on else None
     idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
     with _on_device(xyz.device):
         nbytes = _lib.load().tpg_ball_query_workspace_bytes(B, N, M, int(nsample))  # > 0: uniform-grid search
         ws = _ws(nbytes, xyz.device) if nbytes else None
         _lib.call("tpg_ball_query_f32", _ptr(xyz), _ptr(new_xyz), B, N, M, float(radius), int(nsample), _ptr(idx),
                   _ptr(ws), nbytes, _stream())
+    if rec is not None:
+        _log.end(rec, idx=idx)
     return idx
 
 
@@ -227,12 +249,15 @@ def fps(xyz, npoint: int) -> torch.Tensor:
     if xyz.shape[2] != 3:
         raise RuntimeError("furthest_point_sample expects xyz (B,N,3)")
     B, N, _ = xyz.shape
+    rec = _log.begin("fps", xyz=xyz, npoint=int(npoint)) if _log.on else None
     out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     with _on_device(xyz.device):
         nbytes = _lib.load().tpg_fps_workspace_bytes(B, N)
         ws = _ws(nbytes, xyz.device)
         _lib.call("tpg_fps_f32", _ptr(xyz), B, N, int(npoint), _ptr(out), _ptr(ws), ws.numel() if nbytes else 0,
                   _stream())
+    if rec is not None:
+        _log.end(rec, idx=out)
     return out
 
 
@@ -241,6 +266,7 @@ def fps_start(pts, k: int, start, return_rows: bool = False):
     _req(pts, "pts", torch.float32, 3)
     B, N, D = pts.shape
     start = torch.as_tensor(start, dtype=torch.int64, device=pts.device).expand(B).contiguous()
+    rec = _log.begin("fps_start", pts=pts, k=int(k), start=start) if _log.on else None
     out = torch.empty((B, k), dtype=torch.int64, device=pts.device)
     rows = torch.empty((B, k, N), dtype=torch.float32, device=pts.device) if return_rows else None
     with _on_device(pts.device):
@@ -248,11 +274,13 @@ def fps_start(pts, k: int, start, return_rows: bool = False):
         ws = _ws(nbytes, pts.device)
         _lib.call("tpg_fps_start_f32", _ptr(pts), B, N, D, int(k), _ptr(start), _ptr(out), _ptr(rows), _ptr(ws),
                   ws.numel() if nbytes else 0, _stream())
+    if rec is not None:
+        _log.end(rec, idx=out, rows=rows)
     return (out, rows) if return_rows else out
 
 
 # --------------------------------------------------------------------------- grouping
-def group_fwd(f, idx, center=None) -> torch.Tensor:
+def group_fwd(f, idx, center=None, _op: str = "group") -> torch.Tensor:
     """f [B,C,N], idx int32 [B,M,k] -> [B,C,M,k] (optionally minus center [B,C,M])."""
     _req(f, "features", torch.float32, 3)
     _req(idx, "idx", torch.int32, 3)
@@ -264,9 +292,12 @@ def group_fwd(f, idx, center=None) -> torch.Tensor:
         _req(center, "center", torch.float32, 3)
         if tuple(center.shape) != (B, C, M):
             raise RuntimeError("group_fwd: center must be [B,C,M]")
+    rec = _log.begin(_op, f=f, idx=idx, center=center) if _log.on else None
     out = torch.empty((B, C, M, k), dtype=torch.float32, device=f.device)
     with _on_device(f.device):
         _lib.call("tpg_group_fwd_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
     return out
 
 
@@ -371,11 +402,14 @@ def group_reduce_fwd(f, idx, op: int = _lib.REDUCE_MAX, want_arg: bool = True):
     _req(idx, "idx", torch.int32, 3)
     B, C, N = f.shape
     _, M, k = idx.shape
+    rec = _log.begin("group_reduce", f=f, idx=idx, op=int(op)) if _log.on else None
     out = torch.empty((B, C, M), dtype=torch.float32, device=f.device)
     arg = torch.empty((B, C, M), dtype=torch.int32, device=f.device) if (want_arg and op != _lib.REDUCE_SUM) else None
     with _on_device(f.device):
         _lib.call("tpg_group_reduce_fwd_f32", _ptr(f), _ptr(idx), B, C, N, M, k, int(op), _ptr(out), _ptr(arg),
                   _stream())
+    if rec is not None:
+        _log.end(rec, out=out, arg=arg)
     return out, arg
 
 
@@ -395,6 +429,7 @@ def three_nn(unknown, known):
     _req(known, "known", torch.float32, 3)
     B, n, _ = unknown.shape
     m = known.shape[1]
+    rec = _log.begin("three_nn", unknown=unknown, known=known) if _log.on else None
     dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
     with _on_device(unknown.device):
@@ -402,6 +437,8 @@ def three_nn(unknown, known):
         ws = _ws(nbytes, unknown.device) if nbytes else None
         _lib.call("tpg_three_nn_f32", _ptr(unknown), _ptr(known), B, n, m, _ptr(dist), _ptr(idx), _ptr(ws), nbytes,
                   _stream())
+    if rec is not None:
+        _log.end(rec, dist=dist, idx=idx)
     return dist, idx
 
 
@@ -411,9 +448,12 @@ def three_interpolate_fwd(f, idx, w):
     _req(w, "weight", torch.float32, 3)
     B, c, m = f.shape
     n = idx.shape[1]
+    rec = _log.begin("three_interpolate", f=f, idx=idx, w=w) if _log.on else None
     out = torch.empty((B, c, n), dtype=torch.float32, device=f.device)
     with _on_device(f.device):
         _lib.call("tpg_three_interpolate_fwd_f32", _ptr(f), _ptr(idx), _ptr(w), B, c, m, n, _ptr(out), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
     return out
 
 
@@ -476,12 +516,15 @@ def cubic_interp(query, field, pos, cutoff: float) -> torch.Tensor:
     P, F = field.shape[1], field.shape[2]
     if pos.shape != (S, P, 3) or query.shape[2] != 3:
         raise ValueError("cubic_interp: expected query [S,Q,3], field [S,P,F], pos [S,P,3]")
+    rec = _log.begin("cubic_interp", query=query, field=field, pos=pos, cutoff=float(cutoff)) if _log.on else None
     out = torch.empty((S, Q, F), dtype=torch.float32, device=query.device)
     with _on_device(query.device):
         nbytes = _lib.load().tpg_cubic_interp_workspace_bytes(S, Q, P)
         ws = _ws(nbytes, query.device)
         _lib.call("tpg_cubic_interp_f32", _ptr(query), _ptr(field), _ptr(pos), S, Q, P, F, float(cutoff), _ptr(out),
                   _ptr(ws), ws.numel(), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
     return out
 
 
@@ -491,9 +534,12 @@ def gather_rows(x, idx) -> torch.Tensor:
     _req(idx, "idx", torch.int64, 2)
     B, N, U = x.shape
     L = idx.shape[1]
+    rec = _log.begin("gather_rows", x=x, idx=idx) if _log.on else None
     out = torch.empty((B, L, U), dtype=torch.float32, device=x.device)
     with _on_device(x.device):
         _lib.call("tpg_gather_rows_f32", _ptr(x), _ptr(idx), B, N, U, L, _ptr(out), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
     return out
 
 
@@ -512,8 +558,13 @@ class GroupingOperation(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        rec = _log.begin("group_bwd", grad_out=grad_out, idx=idx, N=ctx.N) if _log.on else None
         off, items = csr_cache.get(idx, ctx.N)
-        return group_bwd(grad_out.contiguous(), off, items, ctx.N), None
+        gf = group_bwd(grad_out, off, items, ctx.N)
+        if rec is not None:
+            _log.end(rec, grad_f=gf)
+        return gf, None
 
 
 class GatherOperation(torch.autograd.Function):
@@ -526,13 +577,18 @@ class GatherOperation(torch.autograd.Function):
         ctx.save_for_backward(idx)
         if csr_cache.prefetch_enabled and features.requires_grad:
             csr_cache.prefetch(idx, ctx.N)
-        return group_fwd(features, idx.unsqueeze(-1)).squeeze(-1)
+        return group_fwd(features, idx.unsqueeze(-1), _op="gather").squeeze(-1)
 
     @staticmethod
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        rec = _log.begin("gather_bwd", grad_out=grad_out, idx=idx, N=ctx.N) if _log.on else None
         off, items = csr_cache.get(idx, ctx.N)
-        return group_bwd(grad_out.contiguous(), off, items, ctx.N), None
+        gf = group_bwd(grad_out, off, items, ctx.N)
+        if rec is not None:
+            _log.end(rec, grad_f=gf)
+        return gf, None
 
 
 class GroupReduce(torch.autograd.Function):
@@ -548,9 +604,13 @@ class GroupReduce(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         idx, arg = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        arg = None if ctx.op == _lib.REDUCE_SUM else arg
+        rec = _log.begin("group_reduce_bwd", grad_out=grad_out, idx=idx, arg=arg, N=ctx.N, op=ctx.op) if _log.on else None
         off, items = csr_cache.get(idx, ctx.N)
-        gf = group_reduce_bwd(grad_out.contiguous(), None if ctx.op == _lib.REDUCE_SUM else arg, off, items, ctx.N,
-                              ctx.k, ctx.op)
+        gf = group_reduce_bwd(grad_out, arg, off, items, ctx.N, ctx.k, ctx.op)
+        if rec is not None:
+            _log.end(rec, grad_f=gf)
         return gf, None, None
 
 
@@ -564,8 +624,13 @@ class ThreeInterpolate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         idx, weight = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        rec = _log.begin("three_interpolate_bwd", grad_out=grad_out, idx=idx, w=weight, m=ctx.m) if _log.on else None
         off, items = csr_cache.get(idx, ctx.m)
-        return three_interpolate_bwd(grad_out.contiguous(), weight, off, items, ctx.m), None, None
+        gf = three_interpolate_bwd(grad_out, weight, off, items, ctx.m)
+        if rec is not None:
+            _log.end(rec, grad_f=gf)
+        return gf, None, None
 
 
 class ChamferSums(torch.autograd.Function):
@@ -574,7 +639,10 @@ class ChamferSums(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, src, tgt, directions):
+        rec = _log.begin("chamfer", src=src, tgt=tgt, directions=int(directions)) if _log.on else None
         r = chamfer_fwd(src, tgt, directions)
+        if rec is not None:
+            _log.end(rec, **r)
         ctx.directions = directions
         z = torch.zeros((src.shape[0],), dtype=torch.float32, device=src.device)
         i_s = r["i_src"] if r["i_src"] is not None else torch.empty(0, dtype=torch.int32, device=src.device)
@@ -588,6 +656,11 @@ class ChamferSums(torch.autograd.Function):
         need_src, need_tgt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_src or need_tgt):
             return None, None, None
-        gs, gt = chamfer_bwd(src, tgt, i_s if i_s.numel() else None, i_t if i_t.numel() else None,
-                             g_src.contiguous(), g_tgt.contiguous(), ctx.directions, need_src, need_tgt)
+        g_src, g_tgt = g_src.contiguous(), g_tgt.contiguous()
+        i_s, i_t = (i_s if i_s.numel() else None), (i_t if i_t.numel() else None)
+        rec = _log.begin("chamfer_bwd", src=src, tgt=tgt, i_src=i_s, i_tgt=i_t, g_src=g_src, g_tgt=g_tgt,
+                         directions=int(ctx.directions)) if _log.on else None
+        gs, gt = chamfer_bwd(src, tgt, i_s, i_t, g_src, g_tgt, ctx.directions, need_src, need_tgt)
+        if rec is not None:
+            _log.end(rec, grad_src=gs, grad_tgt=gt)
         return gs, gt, None

@@ -1,0 +1,216 @@
+"""Harness that runs the reference's UNMODIFIED train step (``baseline/_ref/train_step_final.py``)
+on top of either boundary implementation:
+
+* ``backend="cuda"``   — the drop-in packages of this repo (``pytorch3d.ops``, ``frnn``,
+  ``pointnet2_ops``, ``chamferdist`` backed by libtpugan_b200.so), everything on ``cuda:0``;
+* ``backend="oracle"`` — the CPU oracle shims (``oracle/shims``), for CPU tests and as the
+  recorded-schedule source.
+
+Test / bench infrastructure: it lives outside the product package and is the only code that
+imports the reference.  The reference files are never edited: the harness only (a) puts the
+boundary packages and import-only stubs on ``sys.path``, (b) builds the reference's own models
+and optimisers, (c) feeds synthetic frames, and (d) optionally registers a
+forward hook on ``SRNet.filter_block`` that gives the mask head the *values* of a trained one
+(1 for kept points, 0 for a few percent per cloud; gradients pass straight through), because
+the GAN branch of ``tempo_gan_step`` is gated on ``masking_loss < 0.1``
+(train_step_final.py:117) which a random-init generator never reaches.  With per-cloud
+different keep counts the hard-mask path pads with (999,999,999) dummies
+(upsampling_network.py:143-150) and the discriminators' dummy re-draw runs
+(discriminator.py:115-130) — the paths a trained model exercises.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+from argparse import Namespace
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SITE = os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200")
+REF_INSTALLED = os.path.join(ROOT, "baseline", "_ref")
+REF_SOURCE = "/root/reference"
+BASE_RADIUS = 0.025  # train_utils.py:10
+_REF_MODULES = ("train_step_final", "loss", "train_utils", "gcn_lib", "gcn_lib.nn", "gcn_lib.graph_utils", "gcn_lib.gcn",
+                "gcn_lib.interpolation", "gcn_lib.pointnet", "gcn_lib.pointnet.gcn", "upsampling_network",
+                "discriminator", "sampling", "utils")
+_BOUNDARY_MODULES = ("pytorch3d", "pytorch3d.ops", "frnn", "pointnet2_ops", "pointnet2_ops.pointnet2_utils",
+                     "chamferdist", "chamferdist.chamfer", "dgl", "dgl.utils", "dgl.function", "dgl.nn", "dgl.geometry",
+                     "emd", "open3d", "tensorboardX")
+
+
+def reference_dir() -> str:
+    """The installed copy (ships to the GPU box); falls back to the read-only source tree in
+    the build container when ``tools/install_ref.py`` has not been run."""
+    if os.path.exists(os.path.join(REF_INSTALLED, "train_step_final.py")):
+        return REF_INSTALLED
+    if os.path.exists(os.path.join(REF_SOURCE, "train_step_final.py")):
+        return REF_SOURCE
+    raise FileNotFoundError("reference not installed: run `python tools/install_ref.py` in the build container "
+                            "(baseline/_ref is git-ignored and ships with gpurun)")
+
+
+def import_reference(backend: str = "cuda") -> Dict[str, Any]:
+    """Import the reference's modules over the chosen boundary implementation.  Re-importable:
+    switching backend purges the cached reference and boundary modules first."""
+    assert backend in ("cuda", "oracle")
+    for name in _REF_MODULES + _BOUNDARY_MODULES:
+        sys.modules.pop(name, None)
+    ref = reference_dir()
+    stubs = os.path.join(SITE, "import_stubs")
+    shim_dir = os.path.join(ROOT, "oracle", "shims")
+    for p in (ref, stubs, SITE, shim_dir, ROOT):
+        while p in sys.path:
+            sys.path.remove(p)
+    if backend == "cuda":
+        order = [SITE, stubs, ref]
+    else:
+        sys.path.insert(0, ROOT)
+        import oracle.shims  # noqa: F401  (test infrastructure)
+
+        order = [shim_dir, stubs, ref]
+        import torch
+
+        if not torch.cuda.is_available():
+            # the reference hard-codes .cuda() (train_step_final.py:30,156, loss.py:174)
+            torch.Tensor.cuda = lambda self, *a, **k: self
+    for p in reversed(order):
+        sys.path.insert(0, p)
+    sys.path.insert(0, ROOT)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # SyntaxWarning: `is 'concat'` (discriminator.py:242)
+        import discriminator
+        import loss
+        import train_step_final
+        import upsampling_network
+    return dict(train_step_final=train_step_final, loss=loss, discriminator=discriminator,
+                upsampling_network=upsampling_network, backend=backend, ref_dir=ref)
+
+
+# --------------------------------------------------------------------------------- synthetic data
+def fluid_frames(rng, B, n_hi, frames=3):
+    """Fluid-like window: uniform cloud at SPH spacing 0.025, centroid-centred (train_utils.py:214-221);
+    neighbouring frames = positions advected by vel*DT with vel ~ 0.5 N(0,1) (train_step_final.py:7,33-35)."""
+    L = BASE_RADIUS * (n_hi ** (1.0 / 3.0))
+    p = rng.uniform(0.0, L, size=(B, n_hi, 3)).astype(np.float32)
+    p -= p.mean(axis=1, keepdims=True).astype(np.float32)
+    vel = (0.5 * rng.standard_normal((B, n_hi, 3))).astype(np.float32)
+    out = []
+    for f in range(frames):
+        out.append(np.ascontiguousarray(p + np.float32((f - frames // 2) * 0.025) * vel, dtype=np.float32))
+    return out, vel
+
+
+def action_frames(rng, B, n_hi, frames=3):
+    """MSR-Action-like box [-.5,.5]x[-1,1]x[-.25,.25] (msr_dataset.py:81-84), small frame-to-frame motion."""
+    lo = np.array([-0.5, -1.0, -0.25], np.float32)
+    p = (rng.uniform(size=(B, n_hi, 3)).astype(np.float32) * (-2 * lo) + lo).astype(np.float32)
+    out = []
+    for f in range(frames):
+        out.append(np.ascontiguousarray(p + np.float32(0.01 * f) * rng.standard_normal((B, n_hi, 3)).astype(np.float32)))
+    return out, None
+
+
+class StepContext:
+    """Models, optimisers, frames and options of one reference train-step configuration."""
+
+    def __init__(self, domain, mods, sr_net, spatial_dis, tempo_dis, optims, lo, hi, vel_lo, vel_hi, opt, device):
+        self.domain, self.mods = domain, mods
+        self.sr_net, self.spatial_dis, self.tempo_dis = sr_net, spatial_dis, tempo_dis
+        self.optims = optims  # (G, tempo-D, spatial-D)
+        self.lo, self.hi, self.vel_lo, self.vel_hi = lo, hi, vel_lo, vel_hi
+        self.opt, self.device = opt, device
+        self.hook = None
+        self.keep = None
+
+    def networks(self):
+        return self.sr_net, self.tempo_dis, self.spatial_dis
+
+
+def build(domain: str = "fluid", B: int = 2, n_lo: int = 512, ratio: int = 4, backend: str = "cuda", device=None,
+          seed: int = 1, trained_mask: bool = True, masked_frac=(0.01, 0.06), use_vel: bool = False,
+          lr: float = 1e-4, mods: Optional[Dict[str, Any]] = None) -> StepContext:
+    """Reference models + synthetic frames.  Shapes of BASELINE configs[1]: B=8, n_lo=2048, ratio=4."""
+    import torch
+
+    mods = mods or import_reference(backend)
+    if device is None:
+        device = torch.device("cuda:0" if backend == "cuda" else "cpu")
+    device = torch.device(device)
+    torch.manual_seed(seed)  # the reference seeds np / torch / cuda with 1 (train_tempo.py:24-26)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    n_hi = n_lo * ratio
+    un, dis = mods["upsampling_network"], mods["discriminator"]
+    if domain == "fluid":
+        hi_np, vel_np = fluid_frames(rng, B, n_hi)
+        in_feats = 6 if use_vel == 6 else 3
+        g = un.SRNet(in_feats, 128, upsample_ratio=ratio)
+        sd, td = dis.FluidSpatialDis(), dis.FluidTempoDis(3)
+        opt = Namespace(use_vel=bool(use_vel), in_node_feats=in_feats, R=0.10, cutoff=0.025, w=0.5)
+    elif domain == "action":
+        hi_np, vel_np = action_frames(rng, B, n_hi)
+        g = un.NoMaskSRNet(3, 128, ratio)
+        sd, td = dis.ActionSpatialDis(), dis.ActionTempoDis(3)
+        opt = Namespace(R=2.0, w=2.0)
+    else:
+        raise ValueError(domain)
+    g, sd, td = g.to(device), sd.to(device), td.to(device)
+    hi = [torch.from_numpy(h).to(device) for h in hi_np]
+    # low-res = every ratio-th particle + N(0, 0.003^2) jitter (tempo_dataset.py:27,92; the dataset's FPS
+    # down-sampling is exercised separately, tests/test_parity_gpu.py)
+    jitter = 0.003 if domain == "fluid" else 0.0
+    lo = [(h[:, ::ratio] + jitter * torch.from_numpy(rng.standard_normal((B, n_lo, 3)).astype(np.float32)).to(device)
+           ).contiguous() for h in hi]
+    vel_hi = vel_lo = None
+    if domain == "fluid" and vel_np is not None:
+        v = torch.from_numpy(vel_np).to(device)
+        vel_hi = [v.clone() for _ in hi]
+        vel_lo = [v[:, ::ratio].contiguous() for _ in hi]
+    optims = tuple(torch.optim.Adam(m.parameters(), lr=lr) for m in (g, td, sd))
+    ctx = StepContext(domain, mods, g, sd, td, optims, lo, hi, vel_lo, vel_hi, opt, device)
+    if domain == "fluid" and trained_mask:
+        # values of a trained mask head: 1 = keep, 0 = drop; 1-6 % dropped, a different count per cloud
+        keep = np.ones((B, n_lo, 1), np.float32)
+        fr = np.linspace(masked_frac[0], masked_frac[1], B) if B > 1 else np.array([masked_frac[1]])
+        for b in range(B):
+            keep[b, rng.choice(n_lo, size=max(1, int(round(fr[b] * n_lo))), replace=False)] = 0.0
+        ctx.keep = torch.from_numpy(keep).to(device)
+
+        def trained_mask_hook(_module, _inputs, out):
+            k = ctx.keep
+            if out.shape != k.shape:
+                return out
+            return k + (out - out.detach())  # straight-through: trained values, untouched gradient path
+
+        ctx.hook = g.filter_block.register_forward_hook(trained_mask_hook)
+    return ctx
+
+
+def step(ctx: StepContext, n_iter: int = 12, freeze_D: bool = False) -> Dict[str, float]:
+    """One call of the reference's train step (G update + both D updates when n_iter is even)."""
+    tsf = ctx.mods["train_step_final"]
+    og, ot, os_ = ctx.optims
+    hi = list(ctx.hi)  # the step rebinds list entries when it draws the rotation augmentation (:172-175)
+    lo = list(ctx.lo)
+    if ctx.domain == "fluid":
+        return tsf.tempo_gan_step(ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, lo, ctx.vel_lo, hi, ctx.vel_hi, 1.0,
+                                  ctx.opt, n_iter, og, ot, os_, freeze_D=freeze_D)
+    return tsf.tempo_gan_step_no_mask(ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, lo, hi, ctx.opt, n_iter, og, ot,
+                                      os_, freeze_D=freeze_D)
+
+
+def generator_forward(ctx: StepContext):
+    """BASELINE configs[0]: SRNet.forward on the centre frame (upsampling_network.py:176-185)."""
+    import torch
+
+    with torch.no_grad():
+        if ctx.domain == "fluid":
+            return ctx.sr_net(ctx.lo[1], ctx.lo[1], hard_masking=True)
+        return ctx.sr_net(ctx.lo[1], ctx.lo[1])
+
+
+def param_counts(ctx: StepContext):
+    return tuple(sum(p.numel() for p in m.parameters() if p.requires_grad) for m in ctx.networks())
