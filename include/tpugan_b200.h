@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 7
+#define TPG_ABI_VERSION 8
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -78,12 +78,17 @@ int tpg_set_option(const char* name, long value);
  * p1 [B,P1,D], p2 [B,P2,D] -> dists [B,P1,K] (squared), idx [B,P1,K] int64.
  * Slots beyond min(K, lengths2[b]) and rows beyond lengths1[b] hold 0 / 0.
  * 1 <= D <= 256, 1 <= K <= 1024.
- * Feature-space searches (D = 32/64/128, K <= 24, P2 >= 1024) run on the tensor cores
- * (tcgen05, tf32 candidate search + exact fp32 re-rank) and 3-D searches over clouds of
+ * Feature-space searches (D = 32/64, K <= 24, P2 >= 1024) run on the tensor cores
+ * (tcgen05: centred operands split into two bf16 terms, four-product bf16 contraction with fp32
+ * accumulation as candidate search + exact fp32 re-rank on the original rows) and 3-D searches over clouds of
  * >= 2048 points (K <= 32) walk a uniform grid; both return results identical to the
  * brute-force path and need tpg_knn_workspace_bytes() bytes of workspace; for every
  * other shape that function returns 0 and workspace may be NULL.            */
 size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K);
+/* Diagnostics of the tensor-core path: byte offset, inside the workspace of a finished call, of an
+ * int32 counter = number of queries of that call that were answered by the exact SIMT fallback
+ * (candidate margin not provably complete).  Results are identical either way. */
+size_t tpg_knn_fallback_count_offset(int B);
 int tpg_knn_f32(const float* p1, const float* p2, const int64_t* lengths1,
                 const int64_t* lengths2, int B, int P1, int P2, int D, int K,
                 float* dists, int64_t* idx, void* workspace, size_t workspace_bytes,

@@ -25,9 +25,10 @@ struct KnnArgs {
 // knn.cu
 int knn_dispatch(const KnnArgs& a, cudaStream_t st);
 
-// knn_feat.cu — tcgen05 path for D in {32,64,96,128}, K <= 24 (exact results, tensor-core candidate search)
+// knn_feat.cu — tcgen05 path for D in {32,64}, K <= 24 (exact results, tensor-core candidate search)
 bool knn_feat_eligible(const KnnArgs& a);
-size_t knn_feat_workspace_bytes(int B, int P1, int P2);
+size_t knn_feat_workspace_bytes(int B, int P1, int P2, int D);
+size_t knn_feat_fallback_count_offset(int B);
 int knn_feat_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // grid.cu — uniform-grid search for 3-D clouds of >= 2048 points, K <= 32 (results identical to knn_dispatch)

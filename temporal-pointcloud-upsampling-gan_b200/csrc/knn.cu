@@ -205,9 +205,11 @@ using namespace tpg;
 TPG_API size_t tpg_knn_workspace_bytes(int B, int P1, int P2, int D, int K) {
   KnnArgs a{reinterpret_cast<const float*>(16), reinterpret_cast<const float*>(16), nullptr, nullptr, B, P1, P2, D, K,
             0.f, nullptr, 0, nullptr, nullptr, OUT_KNN};
-  if (knn_feat_eligible(a)) return knn_feat_workspace_bytes(B, P1, P2);
+  if (knn_feat_eligible(a)) return knn_feat_workspace_bytes(B, P1, P2, D);
   return grid_eligible(D, P2, K) ? grid_workspace_bytes(B, P2) : 0;
 }
+
+TPG_API size_t tpg_knn_fallback_count_offset(int B) { return knn_feat_fallback_count_offset(B); }
 
 namespace tpg {
 // flag[0] &= (a == b) bytewise; nbytes % 16 == 0, 16-byte aligned

@@ -5,10 +5,17 @@
 //
 // The distance matrix is a genuine dense contraction, so it goes to tcgen05:
 //   e[j][i] = |y_j|^2 - 2 <y_j, x_i>        (the |x_i|^2 term is constant per query)
-// with <y,x> from tcgen05.mma kind::tf32 (fp32 operands read as tf32, fp32 accumulate in
-// TMEM).  e only SELECTS candidates; the neighbours that are returned are re-ranked with
-// the canonical distance (sequential fp32, no FMA), so indices and distances are identical
-// to the brute-force kernel:
+// Operands are prepared by a pre-pass (feat_split_kernel): every cloud is CENTRED on its mean
+// (distances are translation-invariant; real network features carry a large common offset) and
+// every centred value is split into two bf16 terms, v ~ b1 + b2 (16 significand bits), stored as
+// rows [b1(0..D-1) | b2(0..D-1)] — the same bytes per row as the fp32 input.  <y,x> is then the
+// sum of the four bf16 x bf16 products b1b1 + b1b2 + b2b1 + b2b2 (tcgen05.mma kind::f16, bf16
+// inputs, exact products, fp32 accumulate in TMEM): ~2^-15 relative instead of the 2^-10 of a
+// tf32 contraction.  (Measured on the generator's real activations, tools/dump_knn_inputs.py: a
+// plain tf32 contraction sends 77-98 % of the queries to the exact fallback, centring alone
+// 15-34 %, centring + split 0.0 %.)  e only SELECTS candidates; the neighbours that are
+// returned are re-ranked with the canonical distance (sequential fp32, no FMA) on the ORIGINAL
+// rows, so indices and distances are identical to the brute-force kernel:
 //   * a first pass over the e-matrix yields, per query, a valid upper bound tau0 of the
 //     (K+8)-th smallest e; a second pass buffers every candidate with e <= tau0;
 //   * with T_K the K-th smallest buffered e and eps a rigorous bound on
@@ -20,23 +27,24 @@
 //
 // Kernel anatomy (one CTA = 128 queries of one cloud, one wave of CTAs; 16 epilogue warps + one MMA-issuer warp
 // + one TMA-producer warp):
-//   MMA shape M=128 (candidates) x N=128 (queries) x K=8 per instruction, cta_group::1.
+//   MMA shape M=128 (candidates) x N=128 (queries) x K=16 (bf16) per instruction, cta_group::1.
 //   Candidates are the M operand on purpose: TMEM lane == candidate, so a thread owns one
 //   candidate row of the accumulator tile and sweeps its queries without any cross-lane
-//   operation.  smem: 4-stage ring of candidate tiles (128 x D fp32, K-major, 128B-swizzled,
+//   operation.  smem: 4-stage ring of candidate tiles (128 x 2D bf16, K-major, 128B-swizzled,
 //   filled by TMA: cp.async.bulk.tensor.2d, one box per 32-float K-slab, complete_tx on a
 //   per-stage mbarrier; UMMA descriptors built by hand) + the query tile; TMEM: 4 x 128 columns
 //   (three MMAs in flight behind the tile being drained).  mbarrier pipeline, no CTA barrier in the loop:
 //     full[stage]   TMA -> MMA issuer            tile landed
 //     done[buf]     tcgen05.commit -> epilogue, producer   accumulator ready, smem stage free
 //     tfree[buf]    16 epilogue warps -> MMA issuer         accumulator drained (tcgen05.ld complete)
-//   issuer warp (one thread): for every tile u: wait full / tfree, issue D/8 MMAs, commit;
+//   issuer warp (one thread): for every tile u: wait full / tfree, issue 4 x D/16 MMAs, commit;
 //   producer warp (one thread): wait done(u), TMA tile u+4 into the stage MMA(u) read;
 //   epilogue warps: wait done(u); tcgen05.ld -> registers; per-lane min (pass 0) / predicated append
 //   (pass 1); arrive tfree(u).
 #include "common.cuh"
 #include "internal.cuh"
 
+#include <cuda_bf16.h>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
@@ -59,8 +67,8 @@ struct FeatArgs {
   const int64_t* len1;
   const int64_t* len2;
   int B, P1, P2, D, K;
-  const float* nrm1;       // [B,P1] squared norms of the queries
-  const float* nrm2;       // [B,P2] squared norms of the candidates
+  const float* nrm1;       // [B,P1] squared norms of the (centred, split) queries
+  const float* nrm2;       // [B,P2] squared norms of the (centred, split) candidates
   const unsigned* nmax2;   // [B]    max squared candidate norm (float bits)
   float* dists;            // [B,P1,K]
   int64_t* idx;            // [B,P1,K]
@@ -70,7 +78,8 @@ struct FeatArgs {
   const int32_t* skip;     // nonzero -> every kernel of the call returns at once (results come from a memoised call)
 };
 
-struct FeatMaps {  // TMA descriptors: [B*P, D] fp32, box 32 floats x 128 rows, 128B swizzle
+struct FeatMaps {  // TMA descriptors over the split operands: [B*P, 2D] bf16 moved as [B*P, D] 4-byte words,
+                   // box 32 words x 128 rows, 128B swizzle
   CUtensorMap cand, query;
 };
 
@@ -124,15 +133,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
-constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_NQ >> 3) << 17) |
+// instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t FT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FT_NQ >> 3) << 17) |
                               ((uint32_t)(FT_TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(FT_IDESC), "r"(accumulate)
       : "memory");
 }
@@ -165,13 +174,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// rigorous bound on |e - E| + |d_canon - d_true|:
-//   tf32 truncation of both operands + accumulation: |dot_tc - <x,y>| <= 2.1e-3 |x||y|  (x1.4 safety -> 6e-3
-//   on the factor 2); fp32 roundings of the norms, of e and of the canonical sum: (2D+16) 2^-24 (|x|+|y|)^2
+// rigorous bound on |e - (d_true - |x|^2)| + |d_canon - d_true|, with xs, ys the split
+// values (b1 + b2) of the centred rows x_c, y_c, xn = |xs|, yn = max |ys|, s = xn + yn:
+//   contraction: the 4D bf16 products are exact; fp32 accumulation inside the tensor core, taken as one
+//     truncation (2^-23) per product: |dot_tc - <xs,ys>| <= 4D 2^-23 xn yn, twice that in e;
+//   split: |xs - x_c| <= 2^-16 |x_c| per coordinate (two round-to-nearest bf16 steps), so
+//     |d(xs,ys) - d(x_c,y_c)| <= 2 s * 2^-16 s (+ second order) = 2^-15 s^2;
+//   centring (relative 2^-24 per coordinate), fp32 roundings of the norms, of e and of the canonical sum:
+//     (2D+32) 2^-24 s^2;  x1.25 safety on everything.
 __device__ __forceinline__ float feat_eps(float nq, float nmax, int D) {
   const float xn = sqrtf(nq) * 1.001f, yn = sqrtf(nmax) * 1.001f;
   const float s = xn + yn;
-  return 6e-3f * xn * yn + (float)(2 * D + 16) * 5.9604645e-8f * s * s;
+  return 1.25f * ((float)(8 * D) * 1.1920929e-7f * xn * yn + (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
 }
 
 // Upper end of the 16-bit radix bucket that holds the k-th smallest (1-based) of the values a
@@ -226,24 +240,78 @@ __device__ __forceinline__ float ordered_key_inv(unsigned uk) {
   return __int_as_float(bits);
 }
 
-// ---- squared norms + per-cloud max ---------------------------------------------------------
-__global__ void feat_norm_kernel(const float* __restrict__ p, int B, int P, int D, float* __restrict__ nrm,
-                                 unsigned* __restrict__ nmax, const int32_t* __restrict__ skip) {
+// ---- pre-pass: per-cloud mean, centred bf16 x 2 split, squared norms, per-cloud max norm ----------------------
+constexpr int FT_MEAN_CHUNKS = 16;
+
+// partial column sums of cloud b over rows [chunk * rows_per, ...) below its length: part[b][chunk][D]
+// (fixed summation order: the centre is deterministic; any centre would be CORRECT, it only sets the margins)
+__global__ void __launch_bounds__(256) feat_mean_partial_kernel(const float* __restrict__ p, const int64_t* __restrict__ len,
+                                                                int P, int D, float* __restrict__ part,
+                                                                const int32_t* __restrict__ skip) {
+  __shared__ float red_s[256];
   if (skip && *skip) return;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int n = len ? min((int)len[b], P) : P;
+  const int rows_per = (P + FT_MEAN_CHUNKS - 1) / FT_MEAN_CHUNKS;
+  const int r0 = chunk * rows_per, r1 = min(n, r0 + rows_per);
+  const int col = tid % D, sub = tid / D, nsub = 256 / D;
+  float acc = 0.0f;
+  for (int r = r0 + sub; r < r1; r += nsub) acc += __ldg(p + ((size_t)b * P + r) * D + col);
+  red_s[tid] = acc;
+  __syncthreads();
+  if (tid < D) {
+    float t = 0.0f;
+    for (int u = 0; u < nsub; ++u) t += red_s[u * D + tid];
+    part[((size_t)b * FT_MEAN_CHUNKS + chunk) * D + tid] = t;
+  }
+}
+
+// One float4 chunk per thread (LPR = D/4 lanes per row): v = x - mean; b1 = bf16_rn(v); b2 = bf16_rn(v - b1);
+// out row = [b1(0..D-1) | b2(0..D-1)] (2D bf16 = the bytes of the fp32 row); nrm = sum (b1 + b2)^2.
+__global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict__ p, const int64_t* __restrict__ len_c,
+                                                         int Pc, int P, int D, const float* __restrict__ part,
+                                                         uint2* __restrict__ split, float* __restrict__ nrm,
+                                                         unsigned* __restrict__ nmax, const int32_t* __restrict__ skip) {
+  __shared__ float mean_s[64];
+  if (skip && *skip) return;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int n = len_c ? min((int)len_c[b], Pc) : Pc;  // valid rows of the candidate cloud
+  if (tid < D) {
+    float t = 0.0f;
+    for (int c = 0; c < FT_MEAN_CHUNKS; ++c) t += part[((size_t)b * FT_MEAN_CHUNKS + c) * D + tid];
+    mean_s[tid] = n > 0 ? t / (float)n : 0.0f;
+  }
+  __syncthreads();
+  const int lpr = D >> 2, rows_per_cta = 256 / lpr;
+  const int row = blockIdx.x * rows_per_cta + tid / lpr, ch = tid % lpr;
   float s = 0.0f;
   if (row < P) {
-    const float4* r = reinterpret_cast<const float4*>(p + ((size_t)b * P + row) * D);
-    for (int c = 0; c < (D >> 2); ++c) {
-      const float4 v = __ldg(r + c);
-      s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + ((size_t)b * P + row) * D) + ch);
+    const float c[4] = {v.x - mean_s[4 * ch], v.y - mean_s[4 * ch + 1], v.z - mean_s[4 * ch + 2], v.w - mean_s[4 * ch + 3]};
+    unsigned short h1[4], h2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(c[k]);
+      const float f1 = __bfloat162float(b1);
+      const __nv_bfloat16 b2 = __float2bfloat16_rn(c[k] - f1);
+      const float xs = f1 + __bfloat162float(b2);  // exact in fp32 (<= 17 significant bits)
+      s = fmaf(xs, xs, s);
+      h1[k] = __bfloat16_as_ushort(b1);
+      h2[k] = __bfloat16_as_ushort(b2);
     }
-    nrm[(size_t)b * P + row] = s;
+    uint2* orow = split + ((size_t)b * P + row) * (size_t)(D >> 1);  // row = D/2 uint2 (2D bf16)
+    orow[ch] = make_uint2((unsigned)h1[0] | ((unsigned)h1[1] << 16), (unsigned)h1[2] | ((unsigned)h1[3] << 16));
+    orow[lpr + ch] = make_uint2((unsigned)h2[0] | ((unsigned)h2[1] << 16), (unsigned)h2[2] | ((unsigned)h2[3] << 16));
   }
+  // sum over the row's lanes (lpr = 8 or 16 consecutive lanes)
+  for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if (row < P && ch == 0) nrm[(size_t)b * P + row] = s;
   if (nmax) {
-    unsigned m = __reduce_max_sync(FULL, __float_as_uint(s));  // s >= 0: bit order == value order
-    if ((threadIdx.x & 31) == 0) atomicMax(nmax + b, m);
+    // rows beyond the cloud's length never become candidates; non-finite norms (inf / NaN inputs) must poison
+    // the bound, not vanish in the integer max: NaN -> +inf
+    const float sm = (row < n) ? ((s == s) ? s : __int_as_float(0x7f800000)) : 0.0f;
+    unsigned m = __reduce_max_sync(FULL, __float_as_uint(sm));  // s >= 0: bit order == value order
+    if ((tid & 31) == 0) atomicMax(nmax + b, m);
   }
 }
 
@@ -360,11 +428,17 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     // descriptors differ from their stage base only in the 14-bit start-address field (>> 4)
     const uint64_t ad0 = umma_desc_sw128(base + (uint32_t)(u % FT_STAGES) * stage_bytes);
     const uint64_t bd0 = umma_desc_sw128(qtile);
-    const int ksteps = D >> 3;
-    for (int kk = 0; kk < ksteps; ++kk) {
-      const uint64_t off = (uint64_t)(((uint32_t)(kk >> 2) * atomA + (uint32_t)(kk & 3) * 32u) >> 4);
-      umma_tf32(td, ad0 + off, bd0 + off, kk > 0 ? 1u : 0u);  // atomA == atomB (128 rows x 128 B)
-    }
+    // a row holds D/8 32-byte K-steps (16 bf16 each): steps [0, h) = b1, [h, 2h) = b2, h = D/16.
+    // <y,x> = sum over the four (y term, x term) pairings, all accumulated into one TMEM tile.
+    const int h = D >> 4;
+    auto koff = [&](int kk) { return (uint64_t)(((uint32_t)(kk >> 2) * atomA + (uint32_t)(kk & 3) * 32u) >> 4); };
+    uint32_t accum = 0u;
+    for (int ta = 0; ta < 2; ++ta)
+      for (int tb = 0; tb < 2; ++tb)
+        for (int kk = 0; kk < h; ++kk) {
+          umma_bf16(td, ad0 + koff(ta * h + kk), bd0 + koff(tb * h + kk), accum);  // atomA == atomB (128 rows x 128 B)
+          accum = 1u;
+        }
     umma_commit(smem_u32(&mbar_s[s]));
   };
   if (warp == FT_THREADS / 32 + 1) {
@@ -722,6 +796,9 @@ __global__ void __launch_bounds__(512) knn_feat_fallback_kernel(FeatArgs a) {
 
 // ---- host side -------------------------------------------------------------------------------------
 struct FeatWs {
+  float* part;     // [B][FT_MEAN_CHUNKS][D] partial column sums of p2
+  uint2* split1;   // [B*P1][2D bf16] centred, split queries
+  uint2* split2;   // [B*P2][2D bf16] centred, split candidates
   float* nrm1;
   float* nrm2;
   unsigned* nmax2;
@@ -731,7 +808,7 @@ struct FeatWs {
   size_t total;
 };
 
-static FeatWs feat_carve(void* base, int B, int P1, int P2) {
+static FeatWs feat_carve(void* base, int B, int P1, int P2, int D) {
   FeatWs w;
   char* p = reinterpret_cast<char*>(base);
   size_t o = 0;
@@ -740,6 +817,9 @@ static FeatWs feat_carve(void* base, int B, int P1, int P2) {
   w.nrm1 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P1, 256);
   w.nrm2 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P2, 256);
   w.fb_list = reinterpret_cast<int*>(p + o);    o += align_up(sizeof(int) * (size_t)B * P1, 256);
+  w.part = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * FT_MEAN_CHUNKS * D, 256);
+  w.split1 = reinterpret_cast<uint2*>(p + o);   o += align_up(sizeof(float) * (size_t)B * P1 * D, 1024);
+  w.split2 = reinterpret_cast<uint2*>(p + o);   o += align_up(sizeof(float) * (size_t)B * P2 * D, 1024);
   w.dbg = reinterpret_cast<long long*>(p + o);  o += align_up(sizeof(long long) * 16 * (size_t)B * (size_t)((P1 + FT_NQ - 1) / FT_NQ), 256);
   w.total = o;
   return w;
@@ -797,24 +877,35 @@ bool knn_feat_eligible(const KnnArgs& a) {
   return true;
 }
 
-size_t knn_feat_workspace_bytes(int B, int P1, int P2) { return feat_carve(nullptr, B, P1, P2).total; }
+size_t knn_feat_fallback_count_offset(int B) {
+  return (size_t)((char*)feat_carve(nullptr, B, 1, 1, 32).fb_count - (char*)nullptr);
+}
+
+size_t knn_feat_workspace_bytes(int B, int P1, int P2, int D) { return feat_carve(nullptr, B, P1, P2, D).total; }
 
 int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  TPG_REQUIRE(workspace && workspace_bytes >= knn_feat_workspace_bytes(k.B, k.P1, k.P2), TPG_EWORKSPACE,
+  TPG_REQUIRE(workspace && workspace_bytes >= knn_feat_workspace_bytes(k.B, k.P1, k.P2, k.D), TPG_EWORKSPACE,
               "knn: workspace too small for the tensor-core path (need %zu bytes)",
-              knn_feat_workspace_bytes(k.B, k.P1, k.P2));
-  FeatWs w = feat_carve(workspace, k.B, k.P1, k.P2);
+              knn_feat_workspace_bytes(k.B, k.P1, k.P2, k.D));
+  TPG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, TPG_EWORKSPACE,
+              "knn: workspace must be 256-byte aligned for the tensor-core path");
+  FeatWs w = feat_carve(workspace, k.B, k.P1, k.P2, k.D);
   TPG_CUDA(cudaMemsetAsync(w.nmax2, 0, (size_t)((char*)w.nrm1 - (char*)w.nmax2), st));  // nmax2 + fb_count
   {
-    dim3 g2(ceil_div(k.P2, 128), k.B);
-    feat_norm_kernel<<<g2, 128, 0, st>>>(k.p2, k.B, k.P2, k.D, w.nrm2, w.nmax2, k.skip);
-    TPG_CHECK_LAUNCH("feat_norm_kernel");
+    // centre = mean of the candidate cloud (rows below its length); both operands are shifted by it
+    feat_mean_partial_kernel<<<dim3(FT_MEAN_CHUNKS, k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.D, w.part, k.skip);
+    TPG_CHECK_LAUNCH("feat_mean_partial_kernel");
+    const int rows_per_cta = 256 / (k.D >> 2);
+    feat_split_kernel<<<dim3(ceil_div(k.P2, rows_per_cta), k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.P2, k.D, w.part,
+                                                                              w.split2, w.nrm2, w.nmax2, k.skip);
+    TPG_CHECK_LAUNCH("feat_split_kernel");
     if (k.p1 == k.p2 && k.P1 == k.P2) {
-      w.nrm1 = w.nrm2;  // self search: one norm pass
+      w.nrm1 = w.nrm2;  // self search: one pre-pass
+      w.split1 = w.split2;
     } else {
-      dim3 g1(ceil_div(k.P1, 128), k.B);
-      feat_norm_kernel<<<g1, 128, 0, st>>>(k.p1, k.B, k.P1, k.D, w.nrm1, nullptr, k.skip);
-      TPG_CHECK_LAUNCH("feat_norm_kernel");
+      feat_split_kernel<<<dim3(ceil_div(k.P1, rows_per_cta), k.B), 256, 0, st>>>(k.p1, k.len2, k.P2, k.P1, k.D, w.part,
+                                                                                w.split1, w.nrm1, nullptr, k.skip);
+      TPG_CHECK_LAUNCH("feat_split_kernel");
     }
   }
   FeatArgs a{k.p1, k.p2, k.len1, k.len2, k.B, k.P1, k.P2, k.D, k.K, w.nrm1, w.nrm2, w.nmax2,
@@ -824,8 +915,8 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k.P1, FT_NQ), k.B);
   FeatMaps maps;
-  TPG_REQUIRE(make_feat_map(&maps.cand, k.p2, (long long)k.B * k.P2, k.D) &&
-                  make_feat_map(&maps.query, k.p1, (long long)k.B * k.P1, k.D),
+  TPG_REQUIRE(make_feat_map(&maps.cand, reinterpret_cast<const float*>(w.split2), (long long)k.B * k.P2, k.D) &&
+                  make_feat_map(&maps.query, reinterpret_cast<const float*>(w.split1), (long long)k.B * k.P1, k.D),
               TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
   knn_feat_tc_kernel<<<grid, FT_BLOCK, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");

@@ -14,7 +14,7 @@ LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
-ABI_VERSION = 7
+ABI_VERSION = 8
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
@@ -37,6 +37,7 @@ _PROTOS = {
     "tpg_launch_count": (c_uint64, []),
     "tpg_set_option": (_I, [c_char_p, c_long]),
     "tpg_knn_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "tpg_knn_fallback_count_offset": (_Z, [_I]),
     "tpg_knn_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_knn_cond_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P, _P]),
     "tpg_bytes_equal_and": (_I, [_P, _P, _Z, _P, _P]),

@@ -1,6 +1,8 @@
 """GPU parity: every kernel, through the C ABI (ctypes), against the CPU oracle on the same
 seeded inputs.  Bar: bit-exact for indices and for values that are pure copies / single
 roundings; rtol 1e-5 for sums whose association differs (Chamfer totals, interpolation)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -650,3 +652,55 @@ def test_knn_memo_is_exact_and_skips_only_identical_inputs(F, oracle):
     # plain calls afterwards are untouched
     d, i = F.knn(cu(x), cu(x), 9)
     np.testing.assert_array_equal(i.cpu().numpy(), ref[9][1])
+
+
+# ---- K2 on REAL generator activations --------------------------------------------------------------
+# tests/golden/knn_real_features.npz: inputs of four feature-space knn_points calls recorded while the
+# reference's SRNet(3,128,4) ran on cuda:0 over this library (tools/dump_knn_inputs.py; random-init
+# weights, one cloud of 2048 points).  Real features carry a large common offset and lie near a
+# low-dimensional manifold: a plain tf32 contraction cannot separate their neighbours (the first K2
+# version sent 77-98 % of such queries to the exact fallback; tools/bench_refstep.py).
+def _knn_with_fallback_count(a, b, K):
+    import ctypes
+
+    from tpugan_b200 import _lib
+
+    lib = _lib.load()
+    B, P1, D = a.shape
+    P2 = b.shape[1]
+    nbytes = lib.tpg_knn_workspace_bytes(B, P1, P2, D, K)
+    assert nbytes > 0
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    d = torch.empty((B, P1, K), dtype=torch.float32, device="cuda")
+    i = torch.empty((B, P1, K), dtype=torch.int64, device="cuda")
+    vp = ctypes.c_void_p
+    _lib.call("tpg_knn_f32", vp(a.data_ptr()), vp(b.data_ptr()), None, None, B, P1, P2, D, K, vp(d.data_ptr()),
+              vp(i.data_ptr()), vp(ws.data_ptr()), nbytes, vp(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    off = lib.tpg_knn_fallback_count_offset(B)
+    fb = int(ws[off:off + 4].view(torch.int32).item())
+    return d, i, fb
+
+
+@pytest.mark.parametrize("key", ["c4_K20_D32", "c10_K20_D32", "c14_K12_D64", "c20_K8_D64"])
+def test_knn_tensor_core_real_generator_features(F, oracle, key):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "knn_real_features.npz"))
+    x = np.ascontiguousarray(z[key])
+    K = int(key.split("_")[1][1:])
+    od, oi = oracle.knn(x, x, K)
+    gd, gi, fb = _knn_with_fallback_count(cu(x), cu(x), K)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+    assert fb <= 0.01 * x.shape[0] * x.shape[1], f"{fb} of {x.shape[1]} queries took the exact fallback"
+
+
+def test_knn_tensor_core_offset_features_stay_on_tensor_cores(F, oracle):
+    """|mean| = 500 x the spread: centring keeps the margin narrow (was: every query to the fallback)."""
+    rng = np.random.default_rng(77)
+    off = rng.standard_normal((1, 1, 64)).astype(np.float32) * 50.0
+    x = (rng.standard_normal((2, 2048, 64)).astype(np.float32) * 0.1 + off).astype(np.float32)
+    od, oi = oracle.knn(x, x, 16)
+    gd, gi, fb = _knn_with_fallback_count(cu(x), cu(x), 16)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
+    assert fb <= 0.02 * 2 * 2048, fb
