@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — TPU-GAN point-neighbourhood hot path on B200 (BASELINE.json metric).
+"""bench.py — TPU-GAN point-neighbourhood hot path on B200 (BASELINE.json metric:
+"kNN+group queries/s & GAN train-steps/s at 1/2/4/8 B200; % HBM roofline").
 
-A "step" is one pass of the hot path of one GAN train step: the exact sequence of boundary
-calls (kNN, FRNN, ball query, FPS, gather, grouping fwd/bwd, Chamfer fwd/bwd) that the
-reference's unmodified ``tempo_gan_step`` makes (tests/golden/fluid_step_schedule.json,
-recorded by tests/golden/make_schedule.py), replayed on synthetic fluid frames of BASELINE
-config 2 (2048 -> 8192 particles, batch 8, 3-frame window).  The dense layers between the
-calls are not on the path; their outputs are seeded synthetic activations of the recorded
-shapes (see tpugan_b200/hotpath_trace.py).
+Workloads (`--workload`):
+  fluid   (default) BASELINE configs[1]: fluid G+D train step, 2048 -> 8192 particles, batch 8, 3 frames.
+          * `value` (queries/s): one pass of the HOT PATH of that step — the exact sequence of boundary calls
+            (kNN, FRNN, ball query, FPS, gather, grouping fwd/bwd, Chamfer fwd/bwd) the reference's unmodified
+            `tempo_gan_step` makes (tests/golden/fluid_step_schedule.json), replayed on synthetic frames with the
+            dense layers replaced by seeded activations (tools/hotpath_trace.py), inputs resident in HBM;
+          * `e2e`: the same pass through the drop-in packages + autograd with HOST frames (pinned) copied in and
+            the loss read back every step;
+          * `train_step`: the reference's UNMODIFIED `tempo_gan_step` (baseline/_ref, models + cuDNN + optimisers
+            included) on these kernels: GAN train-steps/s, and the hot path's share of the step's device time;
+          * `cpu_baseline`: the same schedule at the same batch on the C oracle (all host cores), the pure-torch
+            dense formulations north_star names, and BASELINE configs[0] (SRNet.forward, batch 1, CPU vs GPU).
+  action  BASELINE configs[4] shapes (MSR-Action 128 -> 2048 points, 3-frame windows); `--global-batch 64`
+          shards a fixed global batch over the ranks (strong scaling) instead of batch 8 per GPU (weak).
+  sweep   BASELINE configs[2]: per-op microbench sweep N = 2K-64K, k = 16/32, C = 64-256.
+  chamfer BASELINE configs[3]: Chamfer fwd+bwd 8192 x 32768, batch 32.
 
     python bench.py --gpus 1 --steps 10 --warmup 3            # ours, one JSON line
-    torchrun ... bench.py --gpus N ...                       # weak scaling: batch 8 per GPU
-    python bench.py --impl reference ...                     # CPU oracle arm (host cores)
-
-value   = neighbourhood queries / s with inputs resident in HBM (raw C-ABI path)
-e2e     = same metric through the drop-in packages (pytorch3d.ops / frnn / pointnet2_ops /
-          chamferdist + autograd) with the step's position frames copied from pinned HOST
-          memory each step and the loss read back to the host
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU (NCCL)
+    python bench.py --impl reference ...                     # CPU arm: the same workload on the host cores
 """
 from __future__ import annotations
 
@@ -29,7 +34,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 SITE = os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200")
-for _p in (SITE, ROOT):
+for _p in (SITE, ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -43,7 +48,8 @@ OP_KERNEL = {"knn": "knn_feat_tc_kernel", "frnn": "grid_knn_kernel", "ball_query
              "fps": "fps_reg_kernel", "gather": "group_fwd_kernel", "group": "group_fwd_kernel",
              "group_bwd": "group_bwd_staged_kernel", "gather_bwd": "group_bwd_kernel", "chamfer": "grid_nn1_kernel",
              "chamfer_bwd": "chamfer_bwd_kernel"}
-# GAN-step gradient buckets all-reduced at N > 1 (G / tempo-D / spatial-D parameters)
+HBM_OPS = ("group", "group_bwd", "gather", "gather_bwd", "chamfer_bwd")
+# parameter counts of the three networks (G / tempo-D / spatial-D) = gradient bucket sizes
 GRAD_BUCKETS = (439461, 738177, 308737)
 
 
@@ -53,16 +59,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fluid", choices=["fluid", "action"])
-    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default 8 fluid / 8 action)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--workload", default="fluid", choices=["fluid", "action", "sweep", "chamfer"])
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU (default 8)")
+    ap.add_argument("--global-batch", type=int, default=None, help="fixed global batch sharded over the ranks (strong scaling)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=None, help="clouds per step of the CPU arms (default: same batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="train_step leg at N > 1: SyncBatchNorm in the discriminators")
     ap.add_argument("--lanes", type=int, default=64, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
+    ap.add_argument("--quick", action="store_true", help="sweep / chamfer: reduced shape list")
     ap.add_argument("--per-op", action="store_true", help="print the per-op time table to stderr")
     ap.add_argument("--per-call", action="store_true", help="print every call of the schedule with its mean device time")
     return ap.parse_args()
+
+
+def batch_of(args, world=1):
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        return args.global_batch // world
+    return args.batch or 8
 
 
 # ------------------------------------------------------------------------------- CPU oracle arm
@@ -135,7 +153,7 @@ class OracleOps:
 
 def cpu_replay(workload, batch, steps, warmup):
     """Time `steps` passes of the schedule at `batch` clouds on the host cores (oracle, OpenMP)."""
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     ops = OracleOps()
     ops.o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
@@ -150,27 +168,143 @@ def cpu_replay(workload, batch, steps, warmup):
     return dict(queries=rp.queries, s_per_step=dt, cores=ops.o.num_threads(), doc=doc)
 
 
+def cpu_torch_formulations():
+    """The pure-torch dense formulations north_star names (oracle/torch_formulations.py), timed on the host cores
+    at BASELINE configs[1] shapes, one cloud each (bounded sample); the C oracle on the same inputs beside them."""
+    import torch
+
+    import oracle
+    import synth
+    from oracle import torch_formulations as tf
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(1)
+    out = {"threads": torch.get_num_threads(), "sample": "one cloud per op at BASELINE configs[1] shapes; best of 3"}
+
+    def best(fn, n=3):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3
+
+    p = synth.fluid_cloud(rng, 1, 8192)
+    lo = np.ascontiguousarray(p[:, ::4])
+    tp, tlo = torch.from_numpy(p), torch.from_numpy(lo)
+    feat = rng.standard_normal((1, 2048, 64)).astype(np.float32)
+    tfeat = torch.from_numpy(feat)
+    rows = {}
+    rows["knn D=3 2048x2048 K=20"] = (best(lambda: tf.knn(tlo, tlo, 20)), best(lambda: oracle.knn(lo, lo, 20)))
+    rows["knn D=64 2048x2048 K=12"] = (best(lambda: tf.knn(tfeat, tfeat, 12)), best(lambda: oracle.knn(feat, feat, 12)))
+    rows["knn D=3 8192x8192 K=16"] = (best(lambda: tf.knn(tp, tp, 16)), best(lambda: oracle.knn(p, p, 16)))
+    new_xyz = np.ascontiguousarray(p[:, :1024])
+    rows["ball_query 8192->1024 ns=32 r=0.1"] = (best(lambda: tf.query_ball_point(0.1, 32, tp, torch.from_numpy(new_xyz))),
+                                                best(lambda: oracle.ball_query(0.1, 32, p, new_xyz)))
+    rows["fps 8192->1024"] = (best(lambda: tf.farthest_point_sample(tp, 1024), 1), best(lambda: oracle.fps(p, 1024), 1))
+    idx = rng.integers(0, 2048, size=(1, 2048, 20)).astype(np.int32)
+    f64 = np.ascontiguousarray(feat.transpose(0, 2, 1))
+    rows["grouping C=64 N=2048 k=20"] = (best(lambda: tf.grouping(torch.from_numpy(f64), torch.from_numpy(idx))),
+                                         best(lambda: oracle.group_fwd(f64, idx)))
+    out["ms_per_call"] = {k: {"pure_torch": a, "c_oracle": b} for k, (a, b) in rows.items()}
+    return out
+
+
+def c1_generator_forward_cpu():
+    """BASELINE configs[0]: the reference's SRNet(3,128).forward on CPU, one 2048-particle frame, batch 1, over the
+    pure-torch kNN / grouping path (oracle/shims in "torch" mode).  Call AFTER every GPU leg: it re-imports the
+    reference over the CPU shims."""
+    import torch
+
+    import refstep
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ctx = refstep.build("fluid", B=1, n_lo=2048, ratio=4, backend="oracle", device="cpu")
+    from oracle.shims import _backend
+
+    _backend.IMPL["mode"] = "torch"
+    try:
+        refstep.generator_forward(ctx)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            refstep.generator_forward(ctx)
+            ts.append(time.perf_counter() - t0)
+    finally:
+        _backend.IMPL["mode"] = "c"
+    return {"ms": min(ts) * 1e3, "threads": torch.get_num_threads(),
+            "what": "reference SRNet(3,128,4).forward, 1 x 2048 particles, CPU, pure-torch square_distance+topk / index_points path"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    batch_full = args.batch or 8
-    sb = args.cpu_sample_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    batch_full = batch_of(args, world)
+    if args.workload in ("sweep", "chamfer"):
+        return run_reference_ops(args)
+    sb = args.cpu_sample_batch or batch_full
     r = cpu_replay(args.workload, sb, args.steps, args.warmup)
     v = r["queries"] / r["s_per_step"]
     sample = (f"{args.workload} GAN-step schedule at batch {sb} of {batch_full} clouds per step "
               f"({r['queries']} queries/step), C oracle with OpenMP on {r['cores']} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, r["doc"], batch_full, sample_batch=sb),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "same_config": sb == batch_full,
         "note": "reference CPU path = C restatement of the un-vendored native ops (oracle/tpg_oracle.c); the "
                 "reference's own extensions are not installable here (SURVEY.md §8c)",
     }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_reference_ops(args):
+    """CPU arm of the sweep / chamfer workloads: the C oracle on a bounded sample of the same shapes."""
+    import oracle
+    import synth
+
+    oracle.build()
+    oracle.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(1)
+    if args.workload == "chamfer":
+        Bc, P1, P2 = 1, 8192, 32768
+        tgt = synth.fluid_cloud(rng, Bc, P2)
+        src = np.ascontiguousarray(tgt[:, ::4] + 0.003 * rng.standard_normal((Bc, P1, 3)).astype(np.float32))
+        g = np.full((Bc,), 1.0, np.float32)
+
+        def step():
+            r = oracle.chamfer_fwd(src, tgt, 3)
+            oracle.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3)
+
+        units, what = Bc * (P1 + P2), f"Chamfer fwd+bwd {P1}x{P2}, batch {Bc} of 32 per step"
+    else:
+        p = synth.fluid_cloud(rng, 1, 8192)
+        f = rng.standard_normal((1, 64, 8192)).astype(np.float32)
+
+        def step():
+            _, idx = oracle.knn(p, p, 16)
+            oracle.group_fwd(f, idx.astype(np.int32))
+
+        units, what = 8192, "knn (D=3, K=16) -> int32 -> grouping (C=64) on one 8192-point cloud"
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = units / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "sample": what},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": what},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -185,6 +319,8 @@ def workload_config(args, doc, batch, sample_batch=None):
         "parallelism": f"batch-sharded x{args.gpus}",
         "l2": "L2 flushed (256 MiB write) before every timed step",
     }
+    if args.global_batch:
+        c["global_batch"] = args.global_batch
     if sample_batch is not None:
         c["cpu_sample_batch"] = sample_batch
     return c
@@ -225,15 +361,140 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------- ours
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------- real train step
+def real_step_leg(args, world, rank, dev, batch, timed):
+    """The reference's unmodified train step (baseline/_ref) on this library: GAN train-steps/s and the share of
+    the step's device time spent in hot-path kernels.  At N > 1: batch-sharded replicas, real gradient buckets
+    all-reduced before every optimiser step, branch flag agreed (tools/refstep.py DataParallel)."""
+    import torch
+
+    import refstep
+    import tpugan_b200
+    from tpugan_b200.recording import hot_path_ms, log
+
+    domain = args.workload
+    n_lo, ratio = (2048, 4) if domain == "fluid" else (128, 16)
+    ctx = refstep.build(domain, B=batch, n_lo=n_lo, ratio=ratio, backend="cuda", device=dev, seed=1 + rank)
+    dp = refstep.DataParallel(ctx, sync_bn=args.sync_bn)
+    n_iter = [12]
+
+    def one():
+        n_iter[0] += 2  # even: G update + both D updates (train_step_final.py:166)
+        return refstep.step(ctx, n_iter[0])
+
+    steps = max(1, min(args.steps, 10))
+    for _ in range(max(args.warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    l0 = tpugan_b200.launch_count()
+    dp.bytes_per_step = 0
+    ms = timed(one, steps, 0, flush=False)
+    launches = (tpugan_b200.launch_count() - l0) // steps
+    allreduce_bytes = dp.bytes_per_step // steps
+    log.start(capture=False, timing=True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    losses = one()
+    b.record()
+    calls = log.stop()
+    torch.cuda.synchronize()
+    per_op = hot_path_ms(calls)
+    hot, total = sum(per_op.values()), a.elapsed_time(b)
+    grads = [torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
+             for net in ctx.networks()]
+    if ctx.hook is not None:
+        ctx.hook.remove()
+    return {
+        "train_steps_per_s": 1e3 / ms, "global_batch": batch * world,
+        "samples_per_s": batch * world * 1e3 / ms,
+        "ms_per_step": ms, "steps": steps, "batch_per_gpu": batch,
+        "what": ("reference tempo_gan_step (train_step_final.py:69-230)" if domain == "fluid" else
+                 "reference tempo_gan_step_no_mask (train_step_final.py:233-320)") +
+                ", unmodified, from baseline/_ref; models, cuDNN layers and the three Adam steps included; eager, "
+                "single stream, with the reference's own host syncs",
+        "hot_path_ms": hot, "hot_path_share": hot / total, "instrumented_step_ms": total,
+        "hot_path_per_op_ms": dict(sorted(per_op.items(), key=lambda kv: -kv[1])),
+        "rest": "cuDNN convolutions / BatchNorm / elementwise / optimiser kernels of the reference's torch code + host launch gaps",
+        "boundary_calls_per_step": len(calls), "library_launches_per_step": int(launches),
+        "allreduce_bytes_per_step": int(allreduce_bytes), "sync_bn": bool(args.sync_bn and world > 1),
+        "losses": {k: float(v) for k, v in losses.items()},
+    }, grads
+
+
+# ------------------------------------------------------------------------------- ours: op workloads
+def run_ours_ops(args):
+    import torch
+
+    import bench_ops
+    import tpugan_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if rank != 0:  # per-op microbenchmarks do not shard: rank 0 measures, the others idle
+        return 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = tpugan_b200.launch_count()
+    t0 = time.perf_counter()
+    if args.workload == "chamfer":
+        bn, info = bench_ops.run_chamfer(args.quick, max(args.steps, 3), verbose=args.per_op)
+        us = info["us_fwd"] + info["us_bwd"]
+        units = info["B"] * (info["P1"] + info["P2"])
+        value = units / (us * 1e-6)
+        alg = 52 * units  # fused fwd 20 B + bwd 32 B per point (SURVEY.md §8d contract figure)
+        cfg = {"workload": f"Chamfer fwd+bwd {info['P1']}x{info['P2']}, batch {info['B']} (BASELINE configs[3])",
+               "l2": "L2 flushed before every call"}
+        roof = {"bound": "hbm", "kernel": "grid_nn1_kernel + chamfer_bwd_kernel", "achieved": alg / (us * 1e-6) / 1e9,
+                "peak": bn.peak, "unit": "GB/s", "frac": alg / (us * 1e-6) / 1e9 / bn.peak, "traffic": None,
+                "peak_source": bn.peak_source, "alg_bytes_per_launch": alg,
+                "note": "nearest-neighbour search through a uniform grid: compute-bound on the SIMT pipe, reported "
+                        "against HBM as the contract asks; see rows[].gpairs_per_s"}
+        ms = us * 1e-3
+    else:
+        bn = bench_ops.run_sweep(args.quick, max(args.steps, 3), verbose=args.per_op)
+        bench_ops.run_chamfer(args.quick, 3, args.per_op, bn)
+        # headline of the sweep: the kNN -> grouping pair of SURVEY.md §8d at N = 8192, k = 16, C = 64, batch 8
+        k = next(r for r in bn.rows if r["op"] == "knn (D=3)" and "N=8192 K=16" in r["shape"])
+        g = next(r for r in bn.rows if r["op"] == "group fwd" and "C=64 N=M=8192 k=16" in r["shape"])
+        us = k["us"] + g["us"]
+        value = 8 * 8192 / (us * 1e-6)
+        cfg = {"workload": "op sweep N=2K-64K, k=16/32, C=64-256 (BASELINE configs[2]); value = B*P1 / t(knn -> grouping) "
+                           "at B=8, N=8192, k=16, C=64", "l2": "L2 flushed before every call"}
+        roof = {"bound": "hbm", "kernel": "group_fwd_kernel", "achieved": g["alg_gbs"], "peak": bn.peak, "unit": "GB/s",
+                "frac": g["frac_hbm"], "traffic": None, "peak_source": bn.peak_source}
+        ms = us * 1e-3
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg, "roofline": roof, "rows": bn.rows,
+            "e2e": None, "cpu_baseline": None, "gpu_launches": int(tpugan_b200.launch_count() - l0),
+            "clocks": sampler.summary(), "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------- ours: train-step workloads
 def run_ours(args):
     # the DAG replay keeps many independent streams busy: use every hardware work queue (must precede CUDA init)
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
 
+    import hotpath_trace as ht
     import tpugan_b200
-    from tpugan_b200 import _lib, functional as Fn, hotpath_trace as ht
+    from tpugan_b200 import _lib, functional as Fn
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -244,7 +505,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    batch = args.batch or 8
+    batch = batch_of(args, world)
     doc = ht.load_schedule(os.path.join(GOLDEN, f"{args.workload}_step_schedule.json"), batch)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # one flat fp32 buffer = [loss | G grads | tempo-D grads | spatial-D grads]: a single all-reduce per step
@@ -267,13 +528,14 @@ def run_ours(args):
             return flat[0].clone()
         return loss
 
-    def timed(step_fn, steps, warmup):
+    def timed(step_fn, steps, warmup, flush=True):
         for _ in range(warmup):
             step_fn()
         barrier()
         evs = []
         for _ in range(steps):
-            flush_l2()
+            if flush:
+                flush_l2()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn()
@@ -286,10 +548,30 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / max(steps, 1)
 
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- leg 0: the reference's unmodified train step on this library (also yields REAL gradient buckets) ------
+    train_step, grad_payload = None, "zeros (train_step leg unavailable)"
+    if not args.no_train_step:
+        try:
+            train_step, grads = real_step_leg(args, world, rank, dev, batch, timed)
+            if flat is not None:
+                o = 1
+                for g in grads:  # the replay legs all-reduce the step's real gradient values, not zeros
+                    n = min(g.numel(), flat.numel() - o)
+                    flat[o:o + n].copy_(g[:n])
+                    o += n
+                grad_payload = "gradients of the three networks after one real train step (non-zero)"
+            del grads
+        except Exception as e:
+            train_step = {"unavailable": repr(e)[:300]}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
     # ---- leg 1: device-resident, raw C-ABI ------------------------------------------------
     ops = ht.TorchCudaOps(dev)
     rp = ht.TraceReplay(doc, ops, seed=1 + rank)
-    sampler = ClockSampler(local)
 
     def step_resident():
         return reduce_step(rp.run_step())
@@ -297,7 +579,6 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_resident()
     rp.timers = {}
-    sampler.start()
     l0 = tpugan_b200.launch_count()
     ms_res = timed(step_resident, args.steps, 0)
     launches = tpugan_b200.launch_count() - l0
@@ -373,27 +654,24 @@ def run_ours(args):
             Fn.csr_cache.prefetch_enabled = False
             torch.cuda.synchronize()
 
-    # per-op device time inside the timed region (events recorded around every call)
+    # per-op device time inside the timed region (events recorded around every call); per call the MEDIAN over the
+    # timed steps (a host hiccup in one step must not land in one op's roofline), scaled back to `steps`
     op_ms, op_bytes, op_calls = {}, {}, {}
     cursor = {k: 0 for k in timers}
-    call_ms = [0.0] * len(doc["calls"])
+    per_call = [[] for _ in doc["calls"]]
     for step in range(args.steps):
         for ci, c in enumerate(doc["calls"]):
             op = c["op"]
             a, b = timers[op][cursor[op]]
             cursor[op] += 1
-            call_ms[ci] += a.elapsed_time(b)
-            op_ms[op] = op_ms.get(op, 0.0) + a.elapsed_time(b)
-            op_bytes[op] = op_bytes.get(op, 0) + ht.algorithmic_bytes(c)
-            op_calls[op] = op_calls.get(op, 0) + 1
-    # split knn by point dimension (3-D search vs feature-space search are different regimes)
-    dom = max(op_ms, key=op_ms.get)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
+            per_call[ci].append(a.elapsed_time(b))
+    call_ms = [float(np.median(v)) * args.steps for v in per_call]
+    for ci, c in enumerate(doc["calls"]):
+        op = c["op"]
+        op_ms[op] = op_ms.get(op, 0.0) + call_ms[ci]
+        op_bytes[op] = op_bytes.get(op, 0) + ht.algorithmic_bytes(c) * args.steps
+        op_calls[op] = op_calls.get(op, 0) + args.steps
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = {}
     try:
@@ -401,34 +679,51 @@ def run_ours(args):
             traffic = json.load(f)
     except Exception:
         pass
-    ach = op_bytes[dom] / (op_ms[dom] * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": OP_KERNEL[dom], "op": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-        "frac": ach / peak, "traffic": (traffic.get(OP_KERNEL[dom]) or {}).get("dram_bytes_per_launch"),
-        "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of one launch of this kernel)",
-        "note": ("FPS is a chain of npoint dependent arg-max rounds: latency-bound, its algorithmic bytes are tiny; "
-                 "see roofline_hbm_op for the largest bandwidth-bound op" if dom == "fps" else None),
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-        "launches_per_step": op_calls[dom] // max(args.steps, 1),
-        "avg_launch_us": op_ms[dom] * 1e3 / op_calls[dom],
-        "alg_bytes_per_launch": op_bytes[dom] / op_calls[dom],
-        "share_of_step": op_ms[dom] / sum(op_ms.values()),
-        "per_op_ms_per_step": {k: v / args.steps for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])},
-        "per_op_gbs": {k: op_bytes[k] / (op_ms[k] * 1e-3) / 1e9 for k in op_ms},
-    }
-    hbm_ops = [k for k in ("group", "group_bwd", "gather", "gather_bwd") if k in op_ms]
-    hop = max(hbm_ops, key=lambda k: op_bytes[k]) if hbm_ops else None
-    roofline_hbm = None
-    if hop:
-        a2 = op_bytes[hop] / (op_ms[hop] * 1e-3) / 1e9
-        roofline_hbm = {"bound": "hbm", "kernel": OP_KERNEL[hop], "op": hop, "achieved": a2, "peak": peak, "unit": "GB/s",
-                        "frac": a2 / peak, "launches_per_step": op_calls[hop] // max(args.steps, 1),
-                        "avg_launch_us": op_ms[hop] * 1e3 / op_calls[hop],
-                        "alg_bytes_per_launch": op_bytes[hop] / op_calls[hop],
-                        "note": "average over every call of the step incl. small launch-bound ones; per-shape numbers: profiles/*_ops_sweep.md"}
-    # the kernel whose removal shortens the DAG-replayed step most (tools/ablate_graph.py): feature-space kNN on
-    # tcgen05 -- tensor-bound in its contraction, so report it against the measured dense bf16 peak
-    # (tf32 runs at half the bf16 rate)
+
+    def roof_of(op):
+        ach = op_bytes[op] / (op_ms[op] * 1e-3) / 1e9
+        tr = traffic.get(OP_KERNEL[op]) or {}
+        return {"bound": "hbm", "kernel": OP_KERNEL[op], "op": op, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": tr.get("dram_bytes_per_launch"),
+                "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                  "of this kernel, ncu --set full)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "launches_per_step": op_calls[op] // max(args.steps, 1),
+                "avg_launch_us": op_ms[op] * 1e3 / op_calls[op],
+                "alg_bytes_per_launch": op_bytes[op] / op_calls[op],
+                "share_of_step": op_ms[op] / sum(op_ms.values())}
+
+    # roofline = the HBM-bound op class with the largest summed device time (grouping forward / backward)
+    hbm_ops = [k for k in HBM_OPS if k in op_ms]
+    dom = max(hbm_ops, key=op_ms.get)
+    roofline = roof_of(dom)
+    roofline["note"] = ("average over every call of the step incl. small launch-bound ones (eager leg, L2 flushed per "
+                        "step); per-shape numbers: bench.py --workload sweep / profiles/*_ops_sweep.md")
+    roofline["per_op_ms_per_step"] = {k: v / args.steps for k, v in sorted(op_ms.items(), key=lambda kv: -kv[1])}
+    roofline["per_op_gbs"] = {k: op_bytes[k] / (op_ms[k] * 1e-3) / 1e9 for k in op_ms}
+    roofline["per_op_frac_of_hbm_peak"] = {k: roofline["per_op_gbs"][k] / peak for k in op_ms}
+    # latency-bound chain: FPS rounds; search ops: brute-force-equivalent pair evaluations / s (the SIMT ceiling)
+    fps_rounds = sum(int(c["in"]["npoint"]) for c in doc["calls"] if c["op"] == "fps")
+    fps_info = {"ns_per_round": op_ms.get("fps", 0.0) / args.steps * 1e6 / max(fps_rounds, 1), "rounds_per_step": fps_rounds,
+                "ms_per_step": op_ms.get("fps", 0.0) / args.steps, "note": "latency-bound chain of arg-max rounds"}
+    pairs = {}
+    for ci, c in enumerate(doc["calls"]):
+        i, op = c["in"], c["op"]
+        if op in ("knn", "frnn"):
+            s1, s2 = i["p1"]["shape"], i["p2"]["shape"]
+            key = op + (" (D=3)" if s1[2] == 3 else " (feature space)")
+            n = float(s1[0]) * s1[1] * s2[1]
+        elif op == "ball_query":
+            key, n = op, float(i["xyz"]["shape"][0]) * i["xyz"]["shape"][1] * i["new_xyz"]["shape"][1]
+        elif op == "chamfer":
+            key, n = op, 2.0 * i["src"]["shape"][0] * i["src"]["shape"][1] * i["tgt"]["shape"][1]
+        else:
+            continue
+        e = pairs.setdefault(key, [0.0, 0.0])
+        e[0] += n
+        e[1] += call_ms[ci] / args.steps
+    search_ops = {k: {"gpairs_per_s": v[0] / (v[1] * 1e-3) / 1e9, "ms_per_step": v[1]} for k, v in pairs.items() if v[1] > 0}
+    # feature-space kNN on tcgen05: tensor-bound in its contraction -> report against the measured dense bf16 peak
     roofline_tc = None
     tc_calls = [(ci, c) for ci, c in enumerate(doc["calls"])
                 if c["op"] == "knn" and c["in"]["p1"]["shape"][2] in (32, 64) and c["in"]["p2"]["shape"][1] >= 1024
@@ -437,20 +732,21 @@ def run_ours(args):
         fl = sum(2.0 * c["in"]["p1"]["shape"][0] * c["in"]["p1"]["shape"][1] * c["in"]["p2"]["shape"][1] *
                  c["in"]["p1"]["shape"][2] for _, c in tc_calls)  # algorithmic: one pass over the distance matrix
         ms_tc = sum(call_ms[ci] for ci, _ in tc_calls) / args.steps
-        pk = float(peaks.get("bf16_tflops", 1628.7)) / 2.0
+        pk = float(peaks.get("bf16_tflops", 1628.7))
         roofline_tc = {"bound": "tensor", "kernel": "knn_feat_tc_kernel", "op": "knn (D = 32 / 64)",
                        "achieved": fl / (ms_tc * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
                        "frac": fl / (ms_tc * 1e-3) / 1e12 / pk, "launches_per_step": len(tc_calls),
                        "avg_launch_us": ms_tc * 1e3 / len(tc_calls),
-                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 rate)",
-                       "note": "call = norms + tcgen05 kernel + exact-fallback launch; the kernel issues the contraction "
-                               "twice (two-pass candidate selection) and spends two thirds of its time in the SIMT "
-                               "selection / exact re-ranking that make the indices bit-exact (DESIGN.md K2)"}
+                       "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)",
+                       "note": "call = mean + split pre-pass + tcgen05 kernel + exact-fallback launch; achieved = ALGORITHMIC "
+                               "flops (2 P1 P2 D); the kernel issues 8x that in bf16 MMAs (four split products, two passes) and "
+                               "spends most of its time in the SIMT selection / exact re-ranking that make the indices "
+                               "bit-exact (DESIGN.md K2)"}
     if args.per_call and rank == 0:
         agg = {}
         for ci, c in enumerate(doc["calls"]):
             sig = c["op"] + " " + " ".join(f"{k}={tuple(v['shape']) if isinstance(v, dict) else v}" for k, v in c["in"].items()
-                                          if k not in ("id", "fwd_id"))
+                                          if k not in ("id", "fwd_id", "deps", "p1_sha", "p2_sha"))
             e = agg.setdefault(sig, [0, 0.0])
             e[0] += 1
             e[1] += call_ms[ci] / args.steps
@@ -533,13 +829,42 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- C1 on the GPU (the CPU side of it runs last, below) --------------------------------
+    c1 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "fluid":
+        try:
+            import refstep
+
+            ctx1 = refstep.build("fluid", B=1, n_lo=2048, ratio=4, backend="cuda", device=dev)
+            for _ in range(3):
+                refstep.generator_forward(ctx1)
+            ms_c1 = timed(lambda: refstep.generator_forward(ctx1), 10, 0, flush=False)
+            c1 = {"gpu_ms": ms_c1}
+            del ctx1
+        except Exception as e:
+            c1 = {"gpu_error": repr(e)[:200]}
+
+    # ---- CPU side (after every GPU leg: it re-imports the reference over the CPU shims) -------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_replay(args.workload, args.cpu_sample_batch, 6, 1)
+        sb = args.cpu_sample_batch or batch
+        r = cpu_replay(args.workload, sb, 2, 1)
         cpu_baseline = {"value": r["queries"] / r["s_per_step"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                        "sample": f"6 passes (+1 warm-up) of the {args.workload} schedule at batch {args.cpu_sample_batch} of "
+                        "same_config": sb == batch,
+                        "sample": f"2 passes (+1 warm-up) of the {args.workload} schedule at batch {sb} of "
                                   f"{batch} clouds ({r['queries']} queries and {r['s_per_step']:.2f} s per pass), "
                                   f"C oracle with OpenMP"}
+        try:
+            cpu_baseline["torch_formulations"] = cpu_torch_formulations()
+        except Exception as e:
+            cpu_baseline["torch_formulations"] = {"error": repr(e)[:200]}
+        if c1 is not None:
+            try:
+                c1.update({"cpu_" + k: v for k, v in c1_generator_forward_cpu().items()})
+                if "gpu_ms" in c1:
+                    c1["speedup"] = c1["cpu_ms"] / c1["gpu_ms"]
+            except Exception as e:
+                c1["cpu_error"] = repr(e)[:200]
 
     if rank == 0:
         # headline = the step as the product issues it: one CUDA graph over the recorded data-flow DAG when that
@@ -551,18 +876,23 @@ def run_ours(args):
             mode, ms_head = f"cuda graph, {args.lanes} streams along the recorded data dependencies", graph_lanes["ms_per_step"]
         cfg = workload_config(args, doc, batch)
         cfg["issue"] = mode
+        if world > 1:
+            cfg["allreduce"] = {"bytes_per_step": int(flat.numel() * 4), "payload": grad_payload,
+                                "what": "one flat fp32 all-reduce per step: loss + the three gradient buckets"}
         line = {
             "metric": METRIC, "value": total_queries / (ms_head * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_head, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
+            "train_step": train_step,
             "train_step_hot_path_per_s": world * 1e3 / ms_head,
             "eager": {"value": total_queries / (ms_res * 1e-3), "unit": UNIT, "ms_per_step": ms_res,
                       "note": "same calls launched one by one from Python; the per-op / roofline timings below are "
                               "CUDA events around the calls of this leg"},
             "queries_per_step": total_queries,
             "cuda_graph": graph_info, "cuda_graph_streams": graph_lanes,
-            "roofline": roofline, "roofline_hbm_op": roofline_hbm, "roofline_tensor_op": roofline_tc, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_tensor_op": roofline_tc, "fps": fps_info, "search_ops": search_ops,
+            "cpu_baseline": cpu_baseline, "c1_generator_forward": c1, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -575,6 +905,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in ("sweep", "chamfer"):
+        return run_ours_ops(args)
     return run_ours(args)
 
 

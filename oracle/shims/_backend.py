@@ -27,7 +27,16 @@ def _c(a):
     return a if recorder.shapes_only or not recorder.enabled else a
 
 
+# "c" = the C oracle (default); "torch" = the pure-torch dense formulations (oracle/torch_formulations.py) for the
+# ops the generator forward uses (kNN, grouping) -- the BASELINE configs[0] CPU leg of bench.py
+IMPL = {"mode": "c"}
+
+
 def knn(p1, p2, K, lengths1=None, lengths2=None):
+    if IMPL["mode"] == "torch" and lengths1 is None and lengths2 is None:
+        from oracle import torch_formulations as tf
+
+        return tf.knn(p1, p2, K)
     deps = recorder.deps(p1=p1, p2=p2)
     d, i = oracle.knn(_np(p1), _np(p2), K, None if lengths1 is None else _np(lengths1),
                       None if lengths2 is None else _np(lengths2))
@@ -67,6 +76,10 @@ class Grouping(torch.autograd.Function):
         ctx.N = features.shape[2]
         ctx.save_for_backward(idx)
         ctx.call_id = recorder.new_id()
+        if IMPL["mode"] == "torch":
+            from oracle import torch_formulations as tf
+
+            return tf.grouping(features, idx)
         deps = recorder.deps(f=features, idx=idx)
         out = oracle.group_fwd(_np(features), _np(idx))
         recorder.record("group", dict(f=_c(_np(features)), idx=_c(_np(idx)), id=ctx.call_id, deps=deps), dict(out=out))

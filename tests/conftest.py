@@ -5,7 +5,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SITE = os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200")
-for p in (ROOT, SITE, os.path.dirname(os.path.abspath(__file__))):
+for p in (ROOT, SITE, os.path.join(ROOT, "tools"), os.path.dirname(os.path.abspath(__file__))):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -293,3 +293,59 @@ def test_ball_query_wrapper_equals_plain_knn():
         _, fi = oracle.frnn(a, b, K, r)
         _, ki = oracle.knn(a, b, K)
         np.testing.assert_array_equal(np.where(fi == -1, ki, fi), ki)
+
+
+# ---- independent cross-check: the pure-torch dense formulations select the same neighbours -----------------
+# (a different algorithm -- expanded-form distance matrix in float64 + sort / top-k -- on tie-free data; the C
+# oracle evaluates the canonical fp32 expression on the same float32 inputs)
+def _tf():
+    from oracle import torch_formulations as tf
+
+    return tf
+
+
+@pytest.mark.parametrize("B,P1,P2,D,K", [(2, 300, 400, 3, 16), (1, 257, 513, 32, 9), (1, 128, 1024, 64, 20)])
+def test_oracle_knn_equals_torch_square_distance_topk(oracle, B, P1, P2, D, K):
+    import torch
+
+    rng = np.random.default_rng(5 + D)
+    a = rng.standard_normal((B, P1, D)).astype(np.float32)
+    b = rng.standard_normal((B, P2, D)).astype(np.float32)
+    od, oi = oracle.knn(a, b, K)
+    td, ti = _tf().knn(torch.from_numpy(a).double(), torch.from_numpy(b).double(), K)
+    np.testing.assert_array_equal(oi, ti.numpy())
+    np.testing.assert_allclose(od, td.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_ball_query_equals_torch_query_ball_point(oracle):
+    import torch
+
+    rng = np.random.default_rng(9)
+    xyz = synth.fluid_cloud(rng, 2, 1500)
+    new_xyz = np.ascontiguousarray(xyz[:, ::6])  # every centre is a cloud point: at least one hit (itself)
+    for r, ns in ((0.05, 16), (0.08, 32), (0.03, 8)):
+        o = oracle.ball_query(r, ns, xyz, new_xyz)
+        t = _tf().query_ball_point(r, ns, torch.from_numpy(xyz).double(), torch.from_numpy(new_xyz).double())
+        np.testing.assert_array_equal(o, t.numpy().astype(np.int32))
+
+
+def test_oracle_fps_equals_torch_farthest_point_sample(oracle):
+    import torch
+
+    rng = np.random.default_rng(11)
+    xyz = synth.fluid_cloud(rng, 2, 2000) + np.float32(1.0)  # away from the origin: upstream's |p|^2 <= 1e-3 skip is inert
+    t = _tf().farthest_point_sample(torch.from_numpy(xyz).double(), 200, start=0).numpy()
+    np.testing.assert_array_equal(oracle.fps(xyz, 200), t.astype(np.int32))
+    np.testing.assert_array_equal(oracle.fps_start(xyz, 200, np.zeros(2, np.int64)), t)
+
+
+def test_oracle_grouping_and_chamfer_equal_torch_formulations(oracle):
+    import torch
+
+    rng = np.random.default_rng(13)
+    f = rng.standard_normal((2, 8, 300)).astype(np.float32)
+    idx = rng.integers(0, 300, size=(2, 50, 7)).astype(np.int32)
+    np.testing.assert_array_equal(oracle.group_fwd(f, idx), _tf().grouping(torch.from_numpy(f), torch.from_numpy(idx)).numpy())
+    a, b = synth.fluid_cloud(rng, 2, 300), synth.fluid_cloud(rng, 2, 500)
+    t = float(_tf().chamfer(torch.from_numpy(a).double(), torch.from_numpy(b).double()))
+    assert abs(float(oracle.chamfer_distance(a, b, bidirectional=True)) - t) <= 1e-5 * abs(t)

@@ -585,7 +585,7 @@ def test_multi_stream_replay_equals_single_stream(F, name, batch, prefetch):
     import os
 
     import torch
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     doc = ht.load_schedule(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}_step_schedule.json"), batch)
     ops = ht.TorchCudaOps("cuda")

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 
 def test_fluid_schedule_counts():
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     doc = ht.load_schedule(os.path.join(GOLDEN, "fluid_step_schedule.json"))
     c = doc["counts"]
@@ -23,7 +23,7 @@ def test_fluid_schedule_counts():
 
 
 def test_action_schedule_counts():
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     doc = ht.load_schedule(os.path.join(GOLDEN, "action_step_schedule.json"))
     c = doc["counts"]
@@ -32,7 +32,7 @@ def test_action_schedule_counts():
 
 
 def test_batch_rescale_and_bytes():
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     d2 = ht.load_schedule(os.path.join(GOLDEN, "fluid_step_schedule.json"))
     d8 = ht.load_schedule(os.path.join(GOLDEN, "fluid_step_schedule.json"), 8)
@@ -48,7 +48,7 @@ def test_batch_rescale_and_bytes():
 def test_replay_runs_on_the_oracle_backend():
     """Small-shape replay of a truncated schedule through bench.OracleOps (CPU)."""
     import bench
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     doc = ht.load_schedule(os.path.join(GOLDEN, "action_step_schedule.json"), 1)
     rp = ht.TraceReplay(doc, bench.OracleOps(), seed=3)
@@ -96,7 +96,7 @@ def test_dependency_tracker_follows_weights_views_and_autograd():
 
 @pytest.mark.parametrize("name", ["fluid", "action"])
 def test_schedule_dependencies_form_a_dag_with_parallel_chains(name):
-    from tpugan_b200 import hotpath_trace as ht
+    import hotpath_trace as ht
 
     doc = ht.load_schedule(os.path.join(GOLDEN, f"{name}_step_schedule.json"))
     calls = doc["calls"]

@@ -9,7 +9,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
-from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
+import hotpath_trace as ht  # noqa: E402
+from tpugan_b200 import _lib  # noqa: E402
 
 _lib.set_option("fps.sms_per_cloud", int(os.environ.get("FPS_SMS", "1")))
 from tpugan_b200 import functional as _Fn  # noqa: E402

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Per-op microbench sweep on the GPU box (BASELINE configs[2] and configs[3]): device time per call
-(CUDA events, median of `reps`, L2 flushed before every call), algorithmic GB/s (SURVEY.md §8d formulas)
-and the fraction of the measured HBM peak.  Writes a markdown table.
+(CUDA events, median of `reps`, L2 flushed before every call), algorithmic GB/s (SURVEY.md §8d formulas),
+the fraction of the measured HBM peak and, for the search ops, brute-force-equivalent pair evaluations/s
+(the secondary ceiling of §8d: a search is compute-bound on the SIMT pipe unless a grid prunes it).
 
     python tools/bench_ops.py [--quick] [--out gpurun_out/ops_sweep.md]
+
+`bench.py --workload sweep|chamfer` imports `run_sweep` / `run_chamfer` from here.
 """
 import argparse
 import json
@@ -11,130 +14,173 @@ import os
 import sys
 
 import numpy as np
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import synth  # noqa: E402
-from tpugan_b200 import functional as F  # noqa: E402
-
-ap = argparse.ArgumentParser()
-ap.add_argument("--quick", action="store_true")
-ap.add_argument("--reps", type=int, default=7)
-ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ops_sweep.md"))
-args = ap.parse_args()
-try:
-    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-except Exception:
-    PEAK = 6650.0
-dev = torch.device("cuda")
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-rng = np.random.default_rng(1)
-rows = []
 
 
-def timeit(fn, reps=None):
-    reps = reps or args.reps
-    fn()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(reps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+class Bench:
+    def __init__(self, reps=7, verbose=True):
+        import torch
+
+        self.torch = torch
+        self.dev = torch.device("cuda")
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.rng = np.random.default_rng(1)
+        self.reps = reps
+        self.rows = []
+        self.peak, self.peak_source = hbm_peak()
+        self.verbose = verbose
+
+    def timeit(self, fn, reps=None):
+        torch = self.torch
+        reps = reps or self.reps
         fn()
-        b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
-    return float(np.median(ts))
+        ts = []
+        for _ in range(reps):
+            self.flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts))
 
+    def add(self, op, shape, us, alg_bytes, note="", pairs=None, queries=None):
+        gbs = alg_bytes / (us * 1e-6) / 1e9
+        row = {"op": op, "shape": shape, "us": us, "alg_mb": alg_bytes / 1e6, "alg_gbs": gbs, "frac_hbm": gbs / self.peak,
+               "note": note}
+        if pairs is not None:
+            row["gpairs_per_s"] = pairs / (us * 1e-6) / 1e9
+        if queries is not None:
+            row["mqueries_per_s"] = queries / us
+        self.rows.append(row)
+        if self.verbose:
+            extra = f" {row['gpairs_per_s']:9.1f} Gpair/s" if pairs is not None else ""
+            print(f"{op:18s} {shape:44s} {us:10.1f} us {alg_bytes / 1e6:10.1f} MB {gbs:8.1f} GB/s "
+                  f"{100 * gbs / self.peak:5.1f}%{extra}  {note}", file=sys.stderr, flush=True)
 
-def add(op, shape, us, alg_bytes, note=""):
-    gbs = alg_bytes / (us * 1e-6) / 1e9
-    rows.append((op, shape, us, alg_bytes / 1e6, gbs, gbs / PEAK, note))
-    print(f"{op:18s} {shape:44s} {us:10.1f} us {alg_bytes / 1e6:10.1f} MB {gbs:8.1f} GB/s {100 * gbs / PEAK:5.1f}%  {note}", flush=True)
+    def cloud(self, B, N):
+        import synth
 
-
-def cloud(B, N):
-    return torch.from_numpy(synth.fluid_cloud(rng, B, N)).to(dev)
+        return self.torch.from_numpy(synth.fluid_cloud(self.rng, B, N)).to(self.dev)
 
 
 def radius_for(k):  # ~2k points inside the ball at SPH spacing 0.025
     return 0.025 * (2 * k * 3 / (4 * np.pi)) ** (1 / 3)
 
 
-B = 8
-NS = [2048, 8192] if args.quick else [2048, 8192, 32768, 65536]
-for N in NS:
-    p = cloud(B, N)
-    for K in (16, 32):
-        us = timeit(lambda: F.knn(p, p, K))
-        add("knn (D=3)", f"B={B} N={N} K={K}", us, 4 * B * 3 * 2 * N + 12 * B * N * K, f"{B * N / us:.1f} Mquery/s")
-        r = radius_for(K)
-        us = timeit(lambda: F.frnn(p, p, K, r))
-        add("frnn", f"B={B} N={N} K={K} r={r:.3f}", us, 4 * B * 3 * 2 * N + 12 * B * N * K, f"{B * N / us:.1f} Mquery/s")
-        M = N // 4
-        q = p[:, :M].contiguous()
-        us = timeit(lambda: F.ball_query(r, K, p, q))
-        add("ball_query", f"B={B} N={N} M={M} ns={K}", us, 12 * B * (N + M) + 4 * B * M * K)
-    if N <= 32768:
-        npoint = N // 4
-        us = timeit(lambda: F.fps(p, npoint), reps=3)
-        add("fps", f"B={B} N={N} npoint={npoint}", us, 12 * B * N + 4 * B * npoint, f"{us / npoint * 1e3:.0f} ns/round (latency-bound)")
+def run_sweep(quick=False, reps=7, verbose=True):
+    """BASELINE configs[2]: knn / FRNN / ball_query / FPS / grouping / three_interpolate at N = 2K-64K,
+    k = 16/32, C = 64-256.  Returns the Bench (rows in .rows)."""
+    from tpugan_b200 import functional as F
 
-for N, D, K in ([(2048, 64, 16)] if args.quick else [(2048, 32, 16), (2048, 64, 16), (8192, 64, 16), (8192, 64, 24)]):
-    x = torch.randn(B, N, D, device=dev)
-    us = timeit(lambda: F.knn(x, x, K))
-    add("knn (tcgen05)", f"B={B} N={N} D={D} K={K}", us, 4 * B * D * 2 * N + 12 * B * N * K,
-        f"{2.0 * B * N * N * D * 2 / us / 1e6:.1f} TFLOP/s tf32 issued (2 passes)")
+    bn = Bench(reps, verbose)
+    torch, dev = bn.torch, bn.dev
+    B = 8
+    NS = [2048, 8192] if quick else [2048, 8192, 32768, 65536]
+    for N in NS:
+        p = bn.cloud(B, N)
+        for K in (16, 32):
+            us = bn.timeit(lambda: F.knn(p, p, K))
+            bn.add("knn (D=3)", f"B={B} N={N} K={K}", us, 4 * B * 3 * 2 * N + 12 * B * N * K, pairs=float(B) * N * N, queries=B * N)
+            r = radius_for(K)
+            us = bn.timeit(lambda: F.frnn(p, p, K, r))
+            bn.add("frnn", f"B={B} N={N} K={K} r={r:.3f}", us, 4 * B * 3 * 2 * N + 12 * B * N * K, pairs=float(B) * N * N, queries=B * N)
+            M = N // 4
+            q = p[:, :M].contiguous()
+            us = bn.timeit(lambda: F.ball_query(r, K, p, q))
+            bn.add("ball_query", f"B={B} N={N} M={M} ns={K}", us, 12 * B * (N + M) + 4 * B * M * K, pairs=float(B) * N * M, queries=B * M)
+        if N <= 32768:
+            npoint = N // 4
+            us = bn.timeit(lambda: F.fps(p, npoint), reps=3)
+            bn.add("fps", f"B={B} N={N} npoint={npoint}", us, 12 * B * N + 4 * B * npoint,
+                   f"{us / npoint * 1e3:.0f} ns/round (latency-bound)")
+    for N, D, K in ([(2048, 64, 16)] if quick else [(2048, 32, 16), (2048, 32, 20), (2048, 64, 12), (2048, 64, 16), (8192, 64, 16), (8192, 64, 24)]):
+        x = torch.randn(B, N, D, device=dev)
+        us = bn.timeit(lambda: F.knn(x, x, K))
+        bn.add("knn (tcgen05)", f"B={B} N={N} D={D} K={K}", us, 4 * B * D * 2 * N + 12 * B * N * K,
+               f"{2.0 * B * N * N * D / us / 1e6:.1f} TFLOP/s algorithmic", pairs=float(B) * N * N, queries=B * N)
+    GC = [(64, 2048, 16), (256, 2048, 32), (64, 8192, 16)] if quick else [(64, 2048, 16), (128, 2048, 32), (256, 2048, 32), (64, 8192, 16),
+                                                          (256, 8192, 32), (64, 65536, 16), (128, 65536, 32)]
+    for C, N, k in GC:
+        Bg = B if N <= 8192 else 1
+        f = torch.randn(Bg, C, N, device=dev)
+        idx = torch.randint(0, N, (Bg, N, k), device=dev, dtype=torch.int32)
+        us = bn.timeit(lambda: F.group_fwd(f, idx))
+        nbytes = 4 * Bg * (C * N + N * k + C * N * k)
+        bn.add("group fwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes)
+        us_g = us
+        us = bn.timeit(lambda: F.group_fwd(f, idx).max(-1))
+        bn.add("group fwd + max", f"B={Bg} C={C} N=M={N} k={k}", us, 4 * Bg * (C * N + N * k + 2 * C * N), "unfused: materialise [B,C,M,k], torch.max")
+        us = bn.timeit(lambda: F.group_reduce_fwd(f, idx, 0))
+        bn.add("group+max fused", f"B={Bg} C={C} N=M={N} k={k}", us, 4 * Bg * (C * N + N * k + 2 * C * N))
+        go = torch.randn(Bg, C, N, k, device=dev)
+        off, items = F.inverse_index(idx, N)
+        us = bn.timeit(lambda: F.group_bwd(go, off, items, N))
+        bn.add("group bwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes, "CSR prebuilt")
+        us = bn.timeit(lambda: F.inverse_index(idx, N))
+        bn.add("inverse index", f"B={Bg} N={N} L={N * k}", us, 4 * Bg * (2 * N * k + N))
+        del go
+    for c, n in ([(64, 8192)] if quick else [(64, 8192), (256, 8192), (128, 65536)]):
+        m = n // 4
+        Bt = B if n <= 8192 else 2
+        unk, kn = bn.cloud(Bt, n), bn.cloud(Bt, m)
+        us = bn.timeit(lambda: F.three_nn(unk, kn))
+        bn.add("three_nn", f"B={Bt} n={n} m={m}", us, 12 * Bt * (n + m) + 24 * Bt * n, pairs=float(Bt) * n * m, queries=Bt * n)
+        d, i3 = F.three_nn(unk, kn)
+        w = torch.rand(Bt, n, 3, device=dev)
+        ff = torch.randn(Bt, c, m, device=dev)
+        us = bn.timeit(lambda: F.three_interpolate_fwd(ff, i3, w))
+        bn.add("three_interpolate", f"B={Bt} c={c} m={m} n={n}", us, 4 * Bt * c * m + 24 * Bt * n + 4 * Bt * c * n)
+    return bn
 
-GC = [(64, 2048, 16), (256, 2048, 32)] if args.quick else [(64, 2048, 16), (128, 2048, 32), (256, 2048, 32), (64, 8192, 16), (256, 8192, 32),
-                                                            (64, 65536, 16), (128, 65536, 32)]
-for C, N, k in GC:
-    Bg = B if N <= 8192 else 1
-    f = torch.randn(Bg, C, N, device=dev)
-    idx = torch.randint(0, N, (Bg, N, k), device=dev, dtype=torch.int32)
-    us = timeit(lambda: F.group_fwd(f, idx))
-    nbytes = 4 * Bg * (C * N + N * k + C * N * k)
-    add("group fwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes)
-    us = timeit(lambda: F.group_reduce_fwd(f, idx, 0))
-    add("group+max fwd", f"B={Bg} C={C} N=M={N} k={k}", us, 4 * Bg * (C * N + N * k + 2 * C * N))
-    go = torch.randn(Bg, C, N, k, device=dev)
-    off, items = F.inverse_index(idx, N)
-    us = timeit(lambda: F.group_bwd(go, off, items, N))
-    add("group bwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes, "CSR prebuilt")
-    us = timeit(lambda: F.inverse_index(idx, N))
-    add("inverse index", f"B={Bg} N={N} L={N * k}", us, 4 * Bg * (2 * N * k + N))
-    del go
 
-for c, n in ([(64, 8192)] if args.quick else [(64, 8192), (256, 8192), (128, 65536)]):
-    m = n // 4
-    Bt = B if n <= 8192 else 2
-    unk, kn = cloud(Bt, n), cloud(Bt, m)
-    us = timeit(lambda: F.three_nn(unk, kn))
-    add("three_nn", f"B={Bt} n={n} m={m}", us, 12 * Bt * (n + m) + 24 * Bt * n)
-    d, i3 = F.three_nn(unk, kn)
-    w = torch.rand(Bt, n, 3, device=dev)
-    ff = torch.randn(Bt, c, m, device=dev)
-    us = timeit(lambda: F.three_interpolate_fwd(ff, i3, w))
-    add("three_interpolate", f"B={Bt} c={c} m={m} n={n}", us, 4 * Bt * c * m + 24 * Bt * n + 4 * Bt * c * n)
+def run_chamfer(quick=False, reps=5, verbose=True, bn=None):
+    """BASELINE configs[3]: Chamfer fwd + bwd, 8192 x 32768 points, batch 32 (src = subset of tgt + jitter)."""
+    from tpugan_b200 import functional as F
 
-# configs[3]: Chamfer fwd + bwd, 8192 x 32768, batch 32
-Bc, P1, P2 = (8, 8192, 32768) if args.quick else (32, 8192, 32768)
-tgt = cloud(Bc, P2)
-src = (tgt[:, ::4] + 0.003 * torch.randn(Bc, P1, 3, device=dev)).contiguous()
-g = torch.full((Bc,), 1.0 / Bc, device=dev)
-us_f = timeit(lambda: F.chamfer_fwd(src, tgt, 3), reps=3)
-add("chamfer fwd", f"B={Bc} {P1}x{P2}", us_f, 20 * Bc * (P1 + P2), f"{2.0 * Bc * P1 * P2 / us_f / 1e3:.1f} Gpair/s brute-force equivalent")
-r = F.chamfer_fwd(src, tgt, 3)
-us_b = timeit(lambda: F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3), reps=3)
-add("chamfer bwd", f"B={Bc} {P1}x{P2}", us_b, 32 * Bc * (P1 + P2))
+    bn = bn or Bench(reps, verbose)
+    torch, dev = bn.torch, bn.dev
+    Bc, P1, P2 = (8, 8192, 32768) if quick else (32, 8192, 32768)
+    tgt = bn.cloud(Bc, P2)
+    src = (tgt[:, ::4] + 0.003 * torch.randn(Bc, P1, 3, device=dev)).contiguous()
+    g = torch.full((Bc,), 1.0 / Bc, device=dev)
+    us_f = bn.timeit(lambda: F.chamfer_fwd(src, tgt, 3), reps=reps)
+    bn.add("chamfer fwd", f"B={Bc} {P1}x{P2}", us_f, 20 * Bc * (P1 + P2), pairs=2.0 * Bc * P1 * P2, queries=Bc * (P1 + P2))
+    r = F.chamfer_fwd(src, tgt, 3)
+    us_b = bn.timeit(lambda: F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3), reps=reps)
+    bn.add("chamfer bwd", f"B={Bc} {P1}x{P2}", us_b, 32 * Bc * (P1 + P2))
+    return bn, dict(B=Bc, P1=P1, P2=P2, us_fwd=us_f, us_bwd=us_b)
 
-with open(args.out, "w") as fh:
-    fh.write(f"# Op sweep (BASELINE configs[2], configs[3]) — device time per call, algorithmic bytes, % of measured HBM peak ({PEAK} GB/s)\n\n")
-    fh.write("CUDA events around single calls, median of %d, L2 flushed before every call, clocks as found.\n\n" % args.reps)
-    fh.write("| op | shape | us | alg MB | alg GB/s | % HBM peak | note |\n|---|---|---:|---:|---:|---:|---|\n")
-    for op, shape, us, mb, gbs, frac, note in rows:
-        fh.write(f"| {op} | {shape} | {us:.1f} | {mb:.1f} | {gbs:.1f} | {100 * frac:.1f}% | {note} |\n")
-print("wrote", args.out)
+
+def write_markdown(bn, path, reps):
+    with open(path, "w") as fh:
+        fh.write(f"# Op sweep (BASELINE configs[2], configs[3]) — device time per call, algorithmic bytes, % of measured HBM peak ({bn.peak} GB/s)\n\n")
+        fh.write("CUDA events around single calls, median of %d, L2 flushed before every call, clocks as found.\n\n" % reps)
+        fh.write("| op | shape | us | alg MB | alg GB/s | % HBM peak | Gpair/s | note |\n|---|---|---:|---:|---:|---:|---:|---|\n")
+        for r in bn.rows:
+            gp = f"{r['gpairs_per_s']:.1f}" if "gpairs_per_s" in r else ""
+            fh.write(f"| {r['op']} | {r['shape']} | {r['us']:.1f} | {r['alg_mb']:.1f} | {r['alg_gbs']:.1f} | {100 * r['frac_hbm']:.1f}% | {gp} | {r['note']} |\n")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ops_sweep.md"))
+    args = ap.parse_args()
+    bn = run_sweep(args.quick, args.reps)
+    run_chamfer(args.quick, 3, True, bn)
+    write_markdown(bn, args.out, args.reps)
+    print("wrote", args.out)

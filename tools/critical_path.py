@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
-from tpugan_b200 import hotpath_trace as ht  # noqa: E402
+import hotpath_trace as ht  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "fluid"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 8

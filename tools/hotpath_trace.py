@@ -475,7 +475,7 @@ class TorchCudaOps:
     def __init__(self, device="cuda"):
         import torch
 
-        from . import functional as F
+        from tpugan_b200 import functional as F
 
         self.torch, self.F, self.device = torch, F, torch.device(device)
 

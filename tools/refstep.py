@@ -214,3 +214,76 @@ def generator_forward(ctx: StepContext):
 
 def param_counts(ctx: StepContext):
     return tuple(sum(p.numel() for p in m.parameters() if p.requires_grad) for m in ctx.networks())
+
+
+# --------------------------------------------------------------------------------- data parallel
+class DataParallel:
+    """Batch-sharded replicas of the reference's train step WITHOUT touching its code:
+
+    * gradients: an optimiser pre-step hook packs the gradients of that optimiser's network into ONE flat
+      fp32 bucket, all-reduces it (NCCL over NVLink; gloo in the CPU tests) and unpacks the mean — three
+      bucket all-reduces per GAN step (G, tempo-D, spatial-D; train_step_final.py:161-163,188-190,214-216);
+    * branch flag: `tpugan_sr_loss` is wrapped so the masking loss that gates the GAN branch
+      (train_step_final.py:117) is the mean over ranks — every rank takes the same branch;
+    * BatchNorm statistics (discriminator.py:74-75,357-361): `sync_bn=True` converts the discriminators'
+      BatchNorm layers to torch's SyncBatchNorm (exact single-process statistics, CUDA only); otherwise
+      statistics stay per-rank like torch DDP's default (documented divergence).
+    """
+
+    def __init__(self, ctx: StepContext, sync_bn: bool = False):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.dist, self.torch = ctx, dist, torch
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.buckets = []
+        self.bytes_per_step = 0
+        if self.world == 1:
+            return
+        if sync_bn:
+            ctx.spatial_dis = torch.nn.SyncBatchNorm.convert_sync_batchnorm(ctx.spatial_dis)
+            ctx.tempo_dis = torch.nn.SyncBatchNorm.convert_sync_batchnorm(ctx.tempo_dis)
+        for net in ctx.networks():  # identical replicas: rank 0's initial weights everywhere
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t.data, src=0)
+        for net, optim in zip(ctx.networks(), ctx.optims):
+            params = [p for p in net.parameters() if p.requires_grad]
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=ctx.device)
+            self.buckets.append(flat)
+            optim.register_step_pre_hook(self._make_hook(params, flat))
+        tsf = ctx.mods["train_step_final"]
+        orig = tsf.tpugan_sr_loss
+        world = self.world
+
+        def agreed_sr_loss(*a, **k):
+            loss, cd, ml = orig(*a, **k)
+            ml_all = ml.detach().clone().float().reshape(-1)
+            dist.all_reduce(ml_all, op=dist.ReduceOp.SUM)
+            # value agreed over ranks (same branch everywhere), gradient of the local term untouched
+            return loss, cd, ml + (ml_all.reshape(ml.shape) / world - ml.detach())
+
+        tsf.tpugan_sr_loss = agreed_sr_loss
+
+    def _make_hook(self, params, flat):
+        dist, world, torch = self.dist, self.world, self.torch
+
+        def hook(_optim, _args, _kwargs):
+            o = 0
+            for p in params:
+                n = p.numel()
+                if p.grad is not None:
+                    flat[o:o + n].copy_(p.grad.reshape(-1))
+                else:
+                    flat[o:o + n].zero_()
+                o += n
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(world)
+            o = 0
+            for p in params:
+                n = p.numel()
+                if p.grad is not None:
+                    p.grad.copy_(flat[o:o + n].view_as(p.grad))
+                o += n
+            self.bytes_per_step += flat.numel() * 4
+
+        return hook

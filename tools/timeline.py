@@ -12,7 +12,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "temporal-pointcloud-upsampling-gan_b200"))
-from tpugan_b200 import _lib, hotpath_trace as ht  # noqa: E402
+import hotpath_trace as ht  # noqa: E402
+from tpugan_b200 import _lib  # noqa: E402
 
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib = _lib.load()
