@@ -11,7 +11,9 @@
  *   - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers
  *     unless a parameter is documented as a host scalar.
  *   - the caller owns every buffer (inputs, outputs, workspace); the library
- *     never allocates or frees device memory and keeps no state between calls.
+ *     never allocates or frees device memory.  No data state survives a call; the
+ *     only process-global state is the two scheduling hints of tpg_set_option()
+ *     (they never change a result) and the launch counter.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
  *     no call synchronises the device or reads anything back to the host.
  *   - return value: TPG_OK (0) or a negative TPG_E* code; the message of the
@@ -273,6 +275,27 @@ int tpg_cubic_interp_f32(const float* query, const float* field,
  * as Python negative indexing does.                                        */
 int tpg_gather_rows_f32(const float* x, const int64_t* idx, int B, int N, int U,
                         int L, float* out, tpg_stream_t stream);
+/* backward of tpg_gather_rows_f32 (= pytorch3d knn_gather backward): grad_x [B,N,U] = sum of
+ * grad_out[b,l,:] over the positions l with idx[b,l] == n, in ascending l (deterministic, no
+ * atomics), through the inverse index (tpg_inverse_index_build) of the int32 copy of idx with
+ * negative entries clamped to 0; `idx` (the original int64 tensor, may be NULL) lets the kernel skip
+ * positions whose index is negative (FRNN padding).                                          */
+int tpg_gather_rows_bwd_f32(const float* grad_out, const int64_t* idx,
+                            const int32_t* seg_offsets, const int32_t* seg_items, int B,
+                            int N, int U, int L, float* grad_x, tpg_stream_t stream);
+
+/* ---- backward of the distances of tpg_knn_f32 / tpg_frnn_f32 -----------------------------------
+ * replaces the autograd backward of pytorch3d.ops.knn_points / frnn.frnn_grid_points (never
+ * taken on the reference's train step: no caller consumes `dists` — gcn_lib/pointnet/gcn.py:91,258,
+ * discriminator.py:33 — but part of the drop-in surface, and what chamferdist is built on).
+ * grad_p1[b,i,:] = sum_k 2 g[b,i,k] (p1[b,i] - p2[b,idx[b,i,k]]); grad_p2 = the scattered negative,
+ * summed in ascending (i,k) through the inverse index of idx (keys clamped to >= 0, L = P1*K).
+ * Slots k >= min(K, lengths2[b]), rows i >= lengths1[b] and negative indices carry no gradient.
+ * Either gradient pointer may be NULL.                                                        */
+int tpg_knn_bwd_f32(const float* p1, const float* p2, const int64_t* idx,
+                    const float* grad_dists, const int64_t* lengths1, const int64_t* lengths2,
+                    const int32_t* seg_offsets, const int32_t* seg_items, int B, int P1, int P2,
+                    int D, int K, float* grad_p1, float* grad_p2, tpg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,78 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* _
   }
 }
 
+// backward of gather_rows / knn_gather: grad_x[b,n,:] = sum of grad_out[b,l,:] over the positions l of segment n
+// (ascending l: deterministic, no atomics)
+__global__ void gather_rows_bwd_kernel(const float* __restrict__ go, const int32_t* __restrict__ off,
+                                       const int32_t* __restrict__ items, const int64_t* __restrict__ idx_valid, int B, int N,
+                                       int U, int L, float* __restrict__ gx) {
+  const long long total = (long long)B * N * U;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(e % U);
+    const long long row = e / U;
+    const int n = (int)(row % N), b = (int)(row / N);
+    const int s0 = off[(size_t)b * (N + 1) + n], s1 = off[(size_t)b * (N + 1) + n + 1];
+    float acc = 0.0f;
+    for (int s = s0; s < s1; ++s) {
+      const int l = items[(size_t)b * L + s];
+      if (idx_valid && idx_valid[(size_t)b * L + l] < 0) continue;  // padded slot (-1) clamped to key 0
+      acc += go[((size_t)b * L + l) * U + u];
+    }
+    gx[e] = acc;
+  }
+}
+
+// backward of knn_points / frnn_grid_points distances: d/dp1 and d/dp2 of sum g[b,i,k] * |p1[b,i] - p2[b,idx[b,i,k]]|^2.
+// Slots k >= min(K, lengths2[b]) (zero padding) and slots with idx < 0 (FRNN padding) carry no gradient.
+__global__ void knn_bwd_p1_kernel(const float* __restrict__ p1, const float* __restrict__ p2, const int64_t* __restrict__ idx,
+                                  const float* __restrict__ g, const int64_t* __restrict__ len1,
+                                  const int64_t* __restrict__ len2, int B, int P1, int P2, int D, int K,
+                                  float* __restrict__ gp1) {
+  const long long total = (long long)B * P1 * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const long long row = e / D;
+    const int i = (int)(row % P1), b = (int)(row / P1);
+    const int n1 = len1 ? (int)min((long long)len1[b], (long long)P1) : P1;
+    const int kv = min(K, len2 ? (int)min((long long)len2[b], (long long)P2) : P2);
+    float acc = 0.0f;
+    if (i < n1) {
+      const float x = p1[e];
+      for (int k = 0; k < kv; ++k) {
+        const long long j = idx[((size_t)b * P1 + i) * K + k];
+        if (j < 0) continue;
+        acc += 2.0f * g[((size_t)b * P1 + i) * K + k] * (x - p2[((size_t)b * P2 + (size_t)j) * D + d]);
+      }
+    }
+    gp1[e] = acc;
+  }
+}
+__global__ void knn_bwd_p2_kernel(const float* __restrict__ p1, const float* __restrict__ p2, const int64_t* __restrict__ idx,
+                                  const float* __restrict__ g, const int64_t* __restrict__ len1,
+                                  const int64_t* __restrict__ len2, const int32_t* __restrict__ off,
+                                  const int32_t* __restrict__ items, int B, int P1, int P2, int D, int K,
+                                  float* __restrict__ gp2) {
+  const long long total = (long long)B * P2 * D;
+  const int L = P1 * K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const long long row = e / D;
+    const int j = (int)(row % P2), b = (int)(row / P2);
+    const int n1 = len1 ? (int)min((long long)len1[b], (long long)P1) : P1;
+    const int kv = min(K, len2 ? (int)min((long long)len2[b], (long long)P2) : P2);
+    const int s0 = off[(size_t)b * (P2 + 1) + j], s1 = off[(size_t)b * (P2 + 1) + j + 1];
+    const float y = p2[e];
+    float acc = 0.0f;
+    for (int s = s0; s < s1; ++s) {  // ascending (i, k): deterministic
+      const int pos = items[(size_t)b * L + s];
+      const int i = pos / K, k = pos - i * K;
+      if (i >= n1 || k >= kv || idx[(size_t)b * L + pos] < 0) continue;
+      acc -= 2.0f * g[(size_t)b * L + pos] * (p1[((size_t)b * P1 + i) * D + d] - y);
+    }
+    gp2[e] = acc;
+  }
+}
+
 }  // namespace tpg
 
 using namespace tpg;
@@ -107,5 +179,44 @@ TPG_API int tpg_gather_rows_f32(const float* x, const int64_t* idx, int B, int N
   if (blocks > cap) blocks = cap;
   gather_rows_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(x, idx, B, N, U, L, out);
   TPG_CHECK_LAUNCH("gather_rows_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_gather_rows_bwd_f32(const float* grad_out, const int64_t* idx, const int32_t* seg_offsets,
+                                    const int32_t* seg_items, int B, int N, int U, int L, float* grad_x,
+                                    tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && N >= 0 && U >= 0 && L >= 0, TPG_EINVAL, "gather_rows_bwd: bad size");
+  const long long total = (long long)B * N * U;
+  if (total == 0) return TPG_OK;
+  TPG_REQUIRE(grad_x && seg_offsets && (L == 0 || (grad_out && seg_items)), TPG_EINVAL, "gather_rows_bwd: null pointer");
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_rows_bwd_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(grad_out, seg_offsets, seg_items, idx, B, N, U, L, grad_x);
+  TPG_CHECK_LAUNCH("gather_rows_bwd_kernel");
+  return TPG_OK;
+}
+
+TPG_API int tpg_knn_bwd_f32(const float* p1, const float* p2, const int64_t* idx, const float* grad_dists,
+                            const int64_t* lengths1, const int64_t* lengths2, const int32_t* seg_offsets,
+                            const int32_t* seg_items, int B, int P1, int P2, int D, int K, float* grad_p1,
+                            float* grad_p2, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 0 && D >= 1 && K >= 1, TPG_EINVAL, "knn_bwd: bad size");
+  if (B == 0) return TPG_OK;
+  TPG_REQUIRE((P1 == 0 || (p1 && idx && grad_dists)) && (P2 == 0 || p2), TPG_EINVAL, "knn_bwd: null pointer");
+  const int threads = 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (grad_p1 && P1 > 0) {
+    long long blocks = min(((long long)B * P1 * D + threads - 1) / threads, cap);
+    knn_bwd_p1_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(p1, p2, idx, grad_dists, lengths1, lengths2, B, P1, P2, D, K, grad_p1);
+    TPG_CHECK_LAUNCH("knn_bwd_p1_kernel");
+  }
+  if (grad_p2 && P2 > 0) {
+    TPG_REQUIRE(seg_offsets && (P1 == 0 || seg_items), TPG_EINVAL, "knn_bwd: the gradient of p2 needs the inverse index of idx");
+    long long blocks = min(((long long)B * P2 * D + threads - 1) / threads, cap);
+    knn_bwd_p2_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(p1, p2, idx, grad_dists, lengths1, lengths2, seg_offsets, seg_items, B, P1, P2, D, K, grad_p2);
+    TPG_CHECK_LAUNCH("knn_bwd_p2_kernel");
+  }
   return TPG_OK;
 }

@@ -14,7 +14,9 @@ def frnn_gather(x: torch.Tensor, idxs: torch.Tensor, lengths: Optional[torch.Ten
     N, P1, K = idxs.shape
     valid = idxs >= 0
     safe = torch.where(valid, idxs, torch.zeros_like(idxs)).contiguous()
-    out = F.gather_rows(x.contiguous(), safe.reshape(N, P1 * K)).reshape(N, P1, K, x.shape[2])
+    # differentiable w.r.t. x (upstream's frnn_gather is); padded slots give zero rows and take no gradient
+    out = F.GatherRows.apply(x.contiguous(), torch.where(valid, safe, torch.full_like(safe, -1)).reshape(N, P1 * K))
+    out = out.reshape(N, P1, K, x.shape[2])
     return out * valid.unsqueeze(-1).to(out.dtype)
 
 
@@ -49,7 +51,9 @@ def frnn_grid_points(
         raise ValueError("K must be a positive integer")
     if not isinstance(r, torch.Tensor) and r <= 0:
         raise ValueError("r must be positive")
-    dists, idxs = F.frnn(points1.contiguous().float(), points2.contiguous().float(), int(K), r, lengths1, lengths2)
+    # dists are differentiable w.r.t. both clouds like upstream's (padded slots carry no gradient)
+    dists, idxs = F.NeighbourDists.apply(points1.contiguous().float(), points2.contiguous().float(), lengths1, lengths2,
+                                         int(K), r)
     nn = frnn_gather(points2, idxs, lengths2) if return_nn else None
     return dists, idxs, nn, None
 

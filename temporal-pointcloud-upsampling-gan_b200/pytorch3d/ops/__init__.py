@@ -12,31 +12,6 @@ from tpugan_b200 import functional as F
 _KNN = namedtuple("KNN", "dists idx knn")
 
 
-class _KnnDists(torch.autograd.Function):
-    """dists/idx from the sm_100a kernel; gradient of dists w.r.t. both clouds
-    (2 g (p1 - p2[idx]) and its scatter), never taken on the reference's train step
-    because no caller consumes `dists` (gcn.py:91,258; discriminator.py:33)."""
-
-    @staticmethod
-    def forward(ctx, p1, p2, lengths1, lengths2, K):
-        dists, idx = F.knn(p1, p2, K, lengths1, lengths2)
-        ctx.save_for_backward(p1, p2, idx)
-        ctx.mark_non_differentiable(idx)
-        return dists, idx
-
-    @staticmethod
-    def backward(ctx, grad_dists, _grad_idx):
-        p1, p2, idx = ctx.saved_tensors
-        B, P1, K = idx.shape
-        D = p1.shape[2]
-        nbr = F.gather_rows(p2, idx.reshape(B, P1 * K)).reshape(B, P1, K, D)
-        diff = (p1.unsqueeze(2) - nbr) * (2.0 * grad_dists).unsqueeze(-1)  # [B,P1,K,D]
-        grad_p1 = diff.sum(2)
-        grad_p2 = torch.zeros_like(p2)
-        grad_p2.scatter_add_(1, idx.reshape(B, P1 * K, 1).expand(B, P1 * K, D), -diff.reshape(B, P1 * K, D))
-        return grad_p1, grad_p2, None, None, None
-
-
 def knn_points(
     p1: torch.Tensor,
     p2: torch.Tensor,
@@ -63,29 +38,11 @@ def knn_points(
                          "tpugan_b200 knn_points implements norm=2 only (the reference never passes norm)")
     p1 = p1.contiguous()
     p2 = p2.contiguous()
-    dists, idx = _KnnDists.apply(p1, p2, lengths1, lengths2, int(K))
+    dists, idx = F.NeighbourDists.apply(p1, p2, lengths1, lengths2, int(K), None)
     nn = None
     if return_nn:
         nn = knn_gather(p2, idx, lengths2)
     return _KNN(dists=dists, idx=idx, knn=nn)
-
-
-class _KnnGather(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, idx):
-        N, L, K = idx.shape
-        ctx.save_for_backward(idx)
-        ctx.M = x.shape[1]
-        return F.gather_rows(x, idx.reshape(N, L * K)).reshape(N, L, K, x.shape[2])
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        (idx,) = ctx.saved_tensors
-        N, L, K = idx.shape
-        U = grad_out.shape[-1]
-        gx = torch.zeros((N, ctx.M, U), dtype=grad_out.dtype, device=grad_out.device)
-        gx.scatter_add_(1, idx.reshape(N, L * K, 1).expand(N, L * K, U), grad_out.reshape(N, L * K, U))
-        return gx, None
 
 
 def knn_gather(x: torch.Tensor, idx: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -95,7 +52,7 @@ def knn_gather(x: torch.Tensor, idx: torch.Tensor, lengths: Optional[torch.Tenso
     _N, L, K = idx.shape
     if N != _N:
         raise ValueError("x and idx must have same batch dimension.")
-    out = _KnnGather.apply(x.contiguous(), idx.contiguous())
+    out = F.GatherRows.apply(x.contiguous(), idx.reshape(N, L * K).contiguous()).reshape(N, L, K, U)
     if lengths is None:
         if M >= K:
             return out  # nothing to mask, and no host sync

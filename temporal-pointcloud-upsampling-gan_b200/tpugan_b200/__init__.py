@@ -36,6 +36,14 @@ def activate(import_stubs: bool = False) -> str:
     return SITE_DIR
 
 
+def patch_reference(mods=None, **kw):
+    """Rebind the reference's thin wrappers (ball_query_wrapper, IDGCN gather+max, cubic_interpolation,
+    interpolate_vel_lst) to the fused / batched kernels; see tpugan_b200.reference_patches."""
+    from .reference_patches import patch_reference as _patch
+
+    return _patch(mods, **kw)
+
+
 def library_path() -> str:
     return _lib.LIB_PATH
 

@@ -66,6 +66,8 @@ _PROTOS = {
     "tpg_cubic_interp_workspace_bytes": (_Z, [_I, _I, _I]),
     "tpg_cubic_interp_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
     "tpg_gather_rows_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "tpg_gather_rows_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "tpg_knn_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

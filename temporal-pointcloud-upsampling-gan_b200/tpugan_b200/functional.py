@@ -543,7 +543,92 @@ def gather_rows(x, idx) -> torch.Tensor:
     return out
 
 
+def _csr_of_rows(idx: torch.Tensor, N: int):
+    """inverse index of an int64 row-index tensor idx [B,L] (negative = padding, clamped to key 0 and skipped by the
+    consuming kernel)"""
+    idx32 = idx.clamp_min(0).to(torch.int32).contiguous()
+    return inverse_index(idx32, N)
+
+
+def gather_rows_bwd(grad_out, idx, N: int) -> torch.Tensor:
+    """backward of gather_rows: grad_out [B,L,U], idx int64 [B,L] -> grad_x [B,N,U] (ascending-l sums, no atomics)"""
+    _req(grad_out, "grad_out", torch.float32, 3)
+    _req(idx, "idx", torch.int64, 2)
+    B, L, U = grad_out.shape
+    rec = _log.begin("gather_rows_bwd", grad_out=grad_out, idx=idx, N=int(N)) if _log.on else None
+    off, items = _csr_of_rows(idx, N)
+    gx = torch.empty((B, N, U), dtype=torch.float32, device=grad_out.device)
+    with _on_device(grad_out.device):
+        _lib.call("tpg_gather_rows_bwd_f32", _ptr(grad_out), _ptr(idx), _ptr(off), _ptr(items), B, N, U, L, _ptr(gx),
+                  _stream())
+    if rec is not None:
+        _log.end(rec, grad_x=gx)
+    return gx
+
+
+def knn_bwd(p1, p2, idx, grad_dists, lengths1=None, lengths2=None, need_p1=True, need_p2=True):
+    """backward of the kNN / FRNN distances: (grad_p1 [B,P1,D] | None, grad_p2 [B,P2,D] | None)"""
+    _req(p1, "p1", torch.float32, 3)
+    _req(p2, "p2", torch.float32, 3)
+    _req(idx, "idx", torch.int64, 3)
+    _req(grad_dists, "grad_dists", torch.float32, 3)
+    B, P1, D = p1.shape
+    P2, K = p2.shape[1], idx.shape[2]
+    rec = _log.begin("knn_bwd", p1=p1, p2=p2, idx=idx, grad_dists=grad_dists, lengths1=lengths1, lengths2=lengths2) \
+        if _log.on else None
+    gp1 = torch.empty_like(p1) if need_p1 else None
+    gp2 = torch.empty_like(p2) if need_p2 else None
+    off = items = None
+    if need_p2:
+        off, items = _csr_of_rows(idx.reshape(B, P1 * K), P2)
+    with _on_device(p1.device):
+        _lib.call("tpg_knn_bwd_f32", _ptr(p1), _ptr(p2), _ptr(idx), _ptr(grad_dists), _ptr(lengths1), _ptr(lengths2),
+                  _ptr(off), _ptr(items), B, P1, P2, D, K, _ptr(gp1), _ptr(gp2), _stream())
+    if rec is not None:
+        _log.end(rec, grad_p1=gp1, grad_p2=gp2)
+    return gp1, gp2
+
+
 # =========================================================================== autograd
+class NeighbourDists(torch.autograd.Function):
+    """dists / idx of knn_points (r is None) or frnn_grid_points; gradient of dists w.r.t. both clouds through
+    tpg_knn_bwd_f32.  Never taken on the reference's train step (no caller consumes `dists`: gcn.py:91,258;
+    discriminator.py:33) but part of the drop-in surface."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, lengths1, lengths2, K, r):
+        dists, idx = knn(p1, p2, K, lengths1, lengths2) if r is None else frnn(p1, p2, K, r, lengths1, lengths2)
+        B, P1, _ = p1.shape
+        ctx.l1 = _lengths(lengths1, B, P1, p1.device, "lengths1")
+        ctx.l2 = _lengths(lengths2, B, p2.shape[1], p1.device, "lengths2")
+        ctx.save_for_backward(p1, p2, idx)
+        ctx.mark_non_differentiable(idx)
+        return dists, idx
+
+    @staticmethod
+    def backward(ctx, grad_dists, _grad_idx):
+        p1, p2, idx = ctx.saved_tensors
+        gp1, gp2 = knn_bwd(p1, p2, idx, grad_dists.contiguous(), ctx.l1, ctx.l2, ctx.needs_input_grad[0],
+                           ctx.needs_input_grad[1])
+        return gp1, gp2, None, None, None, None
+
+
+class GatherRows(torch.autograd.Function):
+    """x [B,N,U], idx int64 [B,L] (negative = padding -> zero row) -> [B,L,U]; knn_gather / frnn_gather."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.N = x.shape[1]
+        ctx.save_for_backward(idx)
+        ctx.has_pad = None
+        return gather_rows(x, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return gather_rows_bwd(grad_out.contiguous(), idx, ctx.N), None
+
+
 class GroupingOperation(torch.autograd.Function):
     """pointnet2_utils.GroupingOperation (gcn_lib/pointnet/gcn.py:207)."""
 

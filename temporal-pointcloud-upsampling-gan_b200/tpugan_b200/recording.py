@@ -52,11 +52,11 @@ class CallLog:
         return calls
 
     # -- used by functional.py -------------------------------------------------------------
-    def begin(self, op: str, **inputs) -> Optional[Call]:
+    def begin(self, _name: str, **inputs) -> Optional[Call]:
         """Called before the kernels of a boundary call are launched."""
         if not self.on:
             return None
-        c = Call(op)
+        c = Call(_name)
         if self.capture:
             c.inputs = {k: _keep(v) for k, v in inputs.items()}
         if self.timing:

@@ -110,6 +110,34 @@ def check_call(oracle, c) -> str:
     if op == "gather_rows":
         assert np.array_equal(o["out"], oracle.gather_rows(i["x"], i["idx"])), "gather_rows"
         return "values exact"
+    if op == "gather_rows_bwd":
+        go, idx = i["grad_out"], i["idx"]
+        ref = np.zeros((go.shape[0], i["N"], go.shape[2]), np.float64)
+        for b in range(go.shape[0]):
+            v = idx[b] >= 0
+            np.add.at(ref[b], idx[b][v], go[b][v].astype(np.float64))
+        _close(o["grad_x"], ref, op)
+        return "grad 1e-5"
+    if op == "knn_bwd":
+        p1, p2, idx, g = (i[k].astype(np.float64) if k != "idx" else i[k] for k in ("p1", "p2", "idx", "grad_dists"))
+        B, P1, K = idx.shape
+        g = g.copy()
+        g[idx < 0] = 0
+        for b in range(B):
+            kv = K if i.get("lengths2") is None else min(K, int(i["lengths2"][b]))
+            g[b, :, kv:] = 0
+            if i.get("lengths1") is not None:
+                g[b, int(i["lengths1"][b]):] = 0
+        nb = p2[np.arange(B)[:, None, None], np.maximum(idx, 0)]
+        diff = 2.0 * g[..., None] * (p1[:, :, None, :] - nb)
+        if o.get("grad_p1") is not None:
+            _close(o["grad_p1"], diff.sum(2), "knn_bwd grad_p1")
+        if o.get("grad_p2") is not None:
+            ref = np.zeros_like(p2)
+            for b in range(B):
+                np.add.at(ref[b], np.maximum(idx[b], 0).reshape(-1), -diff[b].reshape(P1 * K, -1))
+            _close(o["grad_p2"], ref, "knn_bwd grad_p2")
+        return "grads 1e-5"
     raise AssertionError(f"no checker for op {op!r}")
 
 
