@@ -15,9 +15,10 @@
 // shared-memory exchange with a single __syncthreads (double-buffered) -> two more
 // REDUX -> the winner's coordinates come back through L1 (the cloud was loaded
 // through L1 by this CTA and stays resident).
-// Clouds of more than 2048 points are split over a thread-block cluster of 8 CTAs (DSMEM
-// exchange of the local winners, one cluster barrier per round); beyond 65536 points the
-// running min-dist moves to a caller-provided global workspace.
+// Clouds of more than 2048 points are split over a thread-block cluster of 4 (<= 8192 points) or 8 CTAs;
+// the local winners are exchanged ONE-WAY through DSMEM (st.async completing bytes on the receiver's
+// mbarrier: no cluster barrier in the round); beyond 65536 points the running min-dist moves to a
+// caller-provided global workspace.
 #include <atomic>
 #include <cstdlib>
 
@@ -81,10 +82,49 @@ __device__ __forceinline__ unsigned long long fps_pack(unsigned key, unsigned j)
   return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - j);
 }
 
-template <int PPT, int CL, bool MODEB>
+// ---- one-way cluster exchange (replaces one cluster.sync() per round) -------------------------------------
+// Every CTA pushes {key, xyz} of its local winner into every peer's slot with st.async: the store itself
+// completes transaction bytes on the RECEIVER's mbarrier, so a round costs one DSMEM store latency plus an
+// mbarrier wake-up instead of store + full cluster barrier (arrive.release / wait.acquire, which also
+// flushes L1D).  Slots and barriers are double-buffered by round parity; a sender can only be two rounds
+// ahead of a receiver after having received that receiver's message of the round in between, which the
+// receiver sent after reading the slots being overwritten — so no slot is overwritten while still in use.
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void fps_st_async_v4(uint32_t raddr, uint32_t rbar, unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr),
+               "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void fps_st_async_v2(uint32_t raddr, uint32_t rbar, unsigned a0, unsigned a1) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n" ::"r"(raddr), "r"(a0),
+               "r"(a1), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {  // bounded: a protocol bug must trap, not hang the GPU
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+template <int PPT, int CL, bool MODEB, bool ONEWAY = false>
 __global__ void __launch_bounds__(1024) fps_reg_kernel(FpsArgs a) {
   __shared__ unsigned long long s_key[2][32];
   __shared__ FpsSlot xchg[2][CL];
+  __shared__ __align__(8) unsigned long long xbar[2];
   extern __shared__ float pts_s[];  // this CTA's slice of the cloud, xyz interleaved (winner lookup)
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int nwarps = T >> 5;
@@ -114,6 +154,14 @@ __global__ void __launch_bounds__(1024) fps_reg_kernel(FpsArgs a) {
   int cur = MODEB ? (int)a.start[b] : 0;
   float cx, cy, cz;
   load_point(p + (size_t)cur * a.D, a.D, cx, cy, cz);
+  if (CL > 1 && ONEWAY) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(fps_smem_u32(&xbar[0])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(fps_smem_u32(&xbar[1])) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    cooperative_groups::this_cluster().sync();  // every peer's barriers exist before the first remote complete_tx
+  }
   __syncthreads();
   for (int it = 0; it < a.npoint; ++it) {
     if (tid == 0 && rank == 0) {
@@ -165,11 +213,21 @@ __global__ void __launch_bounds__(1024) fps_reg_kernel(FpsArgs a) {
           const int jl = (int)(0xffffffffu - (unsigned)best) - lo;
           v.x = pts_s[3 * jl]; v.y = pts_s[3 * jl + 1]; v.z = pts_s[3 * jl + 2];
         }
-        FpsSlot* dst = cluster.map_shared_rank(&xchg[buf][rank], lane);
-        reinterpret_cast<uint4*>(dst)[0] = make_uint4((unsigned)v.key, (unsigned)(v.key >> 32), __float_as_uint(v.x), __float_as_uint(v.y));
-        reinterpret_cast<float*>(dst)[4] = v.z;
+        if (ONEWAY) {
+          const uint32_t rslot = fps_mapa(fps_smem_u32(&xchg[buf][rank]), (uint32_t)lane);
+          const uint32_t rbar = fps_mapa(fps_smem_u32(&xbar[buf]), (uint32_t)lane);
+          if (lane == 0)  // this CTA's own barrier: one arrival + the bytes of all CL senders (24 each)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fps_smem_u32(&xbar[buf])), "r"(CL * 24) : "memory");
+          fps_st_async_v4(rslot, rbar, (unsigned)v.key, (unsigned)(v.key >> 32), __float_as_uint(v.x), __float_as_uint(v.y));
+          fps_st_async_v2(rslot + 16, rbar, __float_as_uint(v.z), 0u);
+        } else {
+          FpsSlot* dst = cluster.map_shared_rank(&xchg[buf][rank], lane);
+          reinterpret_cast<uint4*>(dst)[0] = make_uint4((unsigned)v.key, (unsigned)(v.key >> 32), __float_as_uint(v.x), __float_as_uint(v.y));
+          reinterpret_cast<float*>(dst)[4] = v.z;
+        }
       }
-      cluster.sync();
+      if (ONEWAY) fps_mbar_wait_cluster(fps_smem_u32(&xbar[buf]), (uint32_t)((it >> 1) & 1));
+      else cluster.sync();
       unsigned long long g = xchg[buf][0].key;
       int src = 0;
 #pragma unroll
@@ -227,9 +285,9 @@ __global__ void __launch_bounds__(1024) fps_mem_kernel(FpsArgs a) {
 
 std::atomic<int>& fps_exclusive_option();
 
-template <int PPT, int CL, bool MODEB>
+template <int PPT, int CL, bool MODEB, bool ONEWAY = (CL > 1)>
 static int fps_launch(const FpsArgs& a, int threads, cudaStream_t st) {
-  auto kern = fps_reg_kernel<PPT, CL, MODEB>;
+  auto kern = fps_reg_kernel<PPT, CL, MODEB, ONEWAY>;
   const int ppc = CL == 1 ? a.N : (ceil_div(a.N, CL) + 31) & ~31;
   size_t smem = sizeof(float) * 3 * (size_t)ppc;
   // option "fps.exclusive_sm": a single-CTA-per-cloud launch asks for (nearly) all shared memory of its SM, so no
@@ -291,8 +349,14 @@ static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
     return t4 <= 1024 ? fps_launch<4, 4, MODEB>(a, t4, st) : fps_launch<8, 4, MODEB>(a, t8, st);
   }
   if (N <= FPS_REG_MAX) {
+    // measured (tools/bench_fps.py, one-way exchange): a round is cheapest with 8 points per thread and as few
+    // CTAs per cloud as keep a CTA at <= 256 threads: 4 CTAs up to 8192 points (677 vs 867 ns/round with the
+    // former 8 x 256 x 4 layout), 8 beyond
+    if (N <= 8192) {
+      const int ppc = (ceil_div(N, 4) + 31) & ~31;
+      return fps_launch<8, 4, MODEB>(a, (ceil_div(ppc, 8) + 31) & ~31, st);
+    }
     const int ppc = (ceil_div(N, FPS_CL) + 31) & ~31;
-    if (ppc <= 4096) return fps_launch<4, FPS_CL, MODEB>(a, (ceil_div(ppc, 4) + 31) & ~31, st);
     return fps_launch<8, FPS_CL, MODEB>(a, (ceil_div(ppc, 8) + 31) & ~31, st);
   }
   TPG_REQUIRE(a.temp_ws != nullptr, TPG_EWORKSPACE, "fps: N=%d > %d needs a [B,N] float workspace", N, FPS_REG_MAX);
@@ -324,7 +388,8 @@ TPG_API int tpg_debug_fps_variant(const float* xyz, int B, int N, int npoint, in
                                   int threads, int flags, tpg_stream_t stream) {
   FpsArgs a{xyz, B, N, 3, npoint, nullptr, idx, nullptr, nullptr, flags};
   cudaStream_t st = as_stream(stream);
-#define V(P, C) if (ppt == P && cl == C) return fps_launch<P, C, false>(a, threads, st)
+  // flags bit 1: cluster variants with the per-round cluster.sync() (the pre-one-way exchange), for comparison
+#define V(P, C) if (ppt == P && cl == C) return (flags & 2) ? fps_launch<P, C, false, false>(a, threads, st) : fps_launch<P, C, false>(a, threads, st)
   V(1, 1); V(2, 1); V(4, 1); V(8, 1); V(16, 1);
   V(1, 8); V(2, 8); V(4, 8); V(8, 8);
   V(2, 4); V(4, 4); V(8, 4); V(4, 2); V(8, 2); V(16, 2);
