@@ -102,6 +102,94 @@ struct ReduceFwdArgs {
   int32_t* arg;        // [B,C,M] or null
 };
 
+// Fused gather + reduce, shared-memory version (K7 v2).  A CTA owns (cloud b, TC channels, a range of output
+// points).  The TC feature rows sit in shared memory CHANNEL-QUAD INTERLEAVED — [TC/4][N][4] — so one LDS.128
+// fetches four channels of a neighbour: random point indices then cost ~2.2 bank-conflict cycles per 8-lane phase
+// for 128 useful words instead of ~3.5 per 32 words with scalar gathers.  Every thread reduces ONE output point over
+// its k neighbours for all TC channels; its neighbour list is read straight from global memory with 16-byte loads
+// (a thread's list is contiguous, neighbouring threads' lists share cache lines), so each index is read once and
+// serves TC gathers; outputs are written coalesced along m.  (The first version read the indices with scalar loads
+// at stride 4k bytes across the warp, served at most 8 channels per pass and gathered 4 bytes per LDS.)
+constexpr int RT_THREADS = 512;
+constexpr size_t RT_SMEM_MAX = 200 * 1024;
+
+template <int TC>  // 4, 8 or 16 channels per tile (rows beyond C are zero-filled)
+__global__ void __launch_bounds__(RT_THREADS, 1) group_reduce_fwd_smem_kernel(ReduceFwdArgs a) {
+  extern __shared__ __align__(16) float rows_s[];  // [TC/4][N][4]
+  constexpr int Q = TC / 4;
+  const int b = blockIdx.z, c0 = blockIdx.y * TC, tid = threadIdx.x;
+  const int tc = min(TC, a.C - c0);
+  {
+    // four coalesced row loads (one per channel of the quad) -> one conflict-free STS.128 per point
+    const float* fb = a.f + ((size_t)b * a.C + c0) * a.N;
+    float4* dst = reinterpret_cast<float4*>(rows_s);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float* r0 = fb + (size_t)(4 * q) * a.N;
+      const bool h0 = 4 * q < tc, h1 = 4 * q + 1 < tc, h2 = 4 * q + 2 < tc, h3 = 4 * q + 3 < tc;
+      for (int n = tid; n < a.N; n += RT_THREADS) {
+        float4 v;
+        v.x = h0 ? __ldg(r0 + n) : 0.0f;
+        v.y = h1 ? __ldg(r0 + a.N + n) : 0.0f;
+        v.z = h2 ? __ldg(r0 + 2 * (size_t)a.N + n) : 0.0f;
+        v.w = h3 ? __ldg(r0 + 3 * (size_t)a.N + n) : 0.0f;
+        dst[(size_t)q * a.N + n] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const float4* rows4 = reinterpret_cast<const float4*>(rows_s);
+  const int m_lo = blockIdx.x * a.MT, m_hi = min(a.M, m_lo + a.MT);
+  const bool vec = ((a.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.idx) & 15) == 0);
+  for (int m = m_lo + tid; m < m_hi; m += RT_THREADS) {
+    const int32_t* im = a.idx + ((size_t)b * a.M + m) * a.k;
+    const float* wm = a.w ? a.w + ((size_t)b * a.M + m) * a.k : nullptr;
+    float acc[TC];
+    int best[TC];
+    auto take = [&](int j, int i) {
+      float4 v[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) v[q] = rows4[(size_t)q * a.N + i];
+      const float* vf = reinterpret_cast<const float*>(v);
+      if (j == 0) {
+        const float w0 = wm ? __ldg(wm) : 1.0f;
+#pragma unroll
+        for (int c = 0; c < TC; ++c) { acc[c] = wm ? __fmul_rn(w0, vf[c]) : vf[c]; best[c] = 0; }
+      } else if (wm) {
+        const float wj = __ldg(wm + j);
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(wj, vf[c]));
+      } else if (a.op == TPG_REDUCE_MAX) {
+#pragma unroll
+        for (int c = 0; c < TC; ++c) if (vf[c] > acc[c]) { acc[c] = vf[c]; best[c] = j; }
+      } else if (a.op == TPG_REDUCE_MIN) {
+#pragma unroll
+        for (int c = 0; c < TC; ++c) if (vf[c] < acc[c]) { acc[c] = vf[c]; best[c] = j; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[c] = __fadd_rn(acc[c], vf[c]);
+      }
+    };
+    if (vec) {
+      const int4* im4 = reinterpret_cast<const int4*>(im);
+      for (int j4 = 0; j4 < (a.k >> 2); ++j4) {
+        const int4 ii = __ldg(im4 + j4);
+        take(4 * j4, ii.x); take(4 * j4 + 1, ii.y); take(4 * j4 + 2, ii.z); take(4 * j4 + 3, ii.w);
+      }
+    } else {
+      for (int j = 0; j < a.k; ++j) take(j, __ldg(im + j));
+    }
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      if (c < tc) {
+        const size_t o = ((size_t)b * a.C + c0 + c) * a.M + m;
+        a.out[o] = acc[c];
+        if (a.arg) a.arg[o] = best[c];
+      }
+    }
+  }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(GRP_THREADS) group_reduce_fwd_kernel(ReduceFwdArgs a) {
   extern __shared__ float rows_s[];
@@ -663,27 +751,41 @@ TPG_API int tpg_group_fwd_f32(const float* f, const int32_t* idx, const float* c
   return TPG_OK;
 }
 
-static int launch_reduce_fwd(ReduceFwdArgs a, cudaStream_t st) {
-  const int max_tc = (int)(GRP_SMEM_MAX / ((size_t)a.N * sizeof(float)));
-  const bool smem = max_tc >= 1;
+template <int TC>
+static int launch_reduce_smem(ReduceFwdArgs a, size_t sm, cudaStream_t st) {
+  auto kern = group_reduce_fwd_smem_kernel<TC>;
+  a.TC = TC;
   const int target = 2 * num_sms();
-  // every index is re-read once per channel tile, every feature row once per m tile: take the widest
-  // channel tile that fits and split M only as far as needed to fill the machine
+  int mt = max(1, ceil_div(target, a.B * ceil_div(a.C, TC)));
+  mt = min(mt, max(1, a.M / RT_THREADS));  // every range re-stages the TC rows: keep ranges >= one tile
+  a.MT = ceil_div(ceil_div(a.M, mt), RT_THREADS) * RT_THREADS;
+  dim3 grid(ceil_div(a.M, a.MT), ceil_div(a.C, TC), a.B);
+  if (sm > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<grid, RT_THREADS, sm, st>>>(a);
+  TPG_CHECK_LAUNCH("group_reduce_fwd_smem_kernel");
+  return TPG_OK;
+}
+
+static int launch_reduce_fwd(ReduceFwdArgs a, cudaStream_t st) {
+  // shared-memory version: the widest channel tile (16 / 8 / 4) whose interleaved rows fit
+  for (int TC = 16; TC >= 4; TC >>= 1) {
+    if (TC > 4 && TC >= 2 * a.C) continue;  // do not stage (zero) rows that do not exist
+    const size_t sm = (size_t)TC * a.N * sizeof(float);
+    if (sm > RT_SMEM_MAX || ceil_div(a.C, TC) > 65535) continue;
+    if (TC == 16) return launch_reduce_smem<16>(a, sm, st);
+    if (TC == 8) return launch_reduce_smem<8>(a, sm, st);
+    return launch_reduce_smem<4>(a, sm, st);
+  }
+  // rows too long for shared memory: read-only global gathers
+  const int target = 2 * num_sms();
   int TC = 8;
-  while (TC > 1 && (TC > a.C || (smem && TC > max_tc))) TC >>= 1;
+  while (TC > 1 && TC > a.C) TC >>= 1;
   a.TC = TC;
   int mt = max(1, ceil_div(target, a.B * ceil_div(a.C, TC)));
   mt = min(mt, max(1, a.M / GRP_THREADS));
   a.MT = ceil_div(ceil_div(a.M, mt), GRP_THREADS) * GRP_THREADS;
   dim3 grid(ceil_div(a.M, a.MT), ceil_div(a.C, TC), a.B);
-  const size_t sm = smem ? (size_t)TC * a.N * sizeof(float) : 0;
-  if (smem) {
-    auto kern = group_reduce_fwd_kernel<true>;
-    if (sm > 48 * 1024) TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, GRP_THREADS, sm, st>>>(a);
-  } else {
-    group_reduce_fwd_kernel<false><<<grid, GRP_THREADS, 0, st>>>(a);
-  }
+  group_reduce_fwd_kernel<false><<<grid, GRP_THREADS, 0, st>>>(a);
   TPG_CHECK_LAUNCH("group_reduce_fwd_kernel");
   return TPG_OK;
 }

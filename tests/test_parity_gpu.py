@@ -457,7 +457,14 @@ def test_grouping_autograd_matches_oracle(F, oracle):
 
 
 @pytest.mark.parametrize("op", [0, 1, 2])
-@pytest.mark.parametrize("B,C,N,M,k", [(2, 32, 256, 256, 9), (1, 7, 100, 33, 4), (2, 3, 3000, 500, 16)])
+@pytest.mark.parametrize("B,C,N,M,k", [
+    (2, 32, 256, 256, 9), (1, 7, 100, 33, 4), (2, 3, 3000, 500, 16),
+    (2, 64, 2048, 2048, 16),   # 16-channel tiles, several output ranges per tile
+    (1, 40, 8192, 1000, 32),   # long rows: 4-channel tiles, even k (padded list stride), ragged last tile
+    (1, 130, 1024, 1500, 7),   # C not a multiple of the tile, odd k, M not a multiple of 512
+    (2, 33, 300, 513, 1),      # k = 1
+    (1, 5, 60000, 700, 8),     # rows do not fit shared memory: global-gather path
+])
 def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
     rng = np.random.default_rng(12)
     f, idx = make_group(rng, B, C, N, M, k)

@@ -135,7 +135,8 @@ def run_sweep(quick=False, reps=7, verbose=True):
     for c, n in ([(64, 8192)] if quick else [(64, 8192), (256, 8192), (128, 65536)]):
         m = n // 4
         Bt = B if n <= 8192 else 2
-        unk, kn = bn.cloud(Bt, n), bn.cloud(Bt, m)
+        unk = bn.cloud(Bt, n)
+        kn = unk[:, ::4].contiguous()  # feature propagation: the known points are a subset of the unknown cloud
         us = bn.timeit(lambda: F.three_nn(unk, kn))
         bn.add("three_nn", f"B={Bt} n={n} m={m}", us, 12 * Bt * (n + m) + 24 * Bt * n, pairs=float(Bt) * n * m, queries=Bt * n)
         d, i3 = F.three_nn(unk, kn)
@@ -159,8 +160,11 @@ def run_chamfer(quick=False, reps=5, verbose=True, bn=None):
     us_f = bn.timeit(lambda: F.chamfer_fwd(src, tgt, 3), reps=reps)
     bn.add("chamfer fwd", f"B={Bc} {P1}x{P2}", us_f, 20 * Bc * (P1 + P2), pairs=2.0 * Bc * P1 * P2, queries=Bc * (P1 + P2))
     r = F.chamfer_fwd(src, tgt, 3)
-    us_b = bn.timeit(lambda: F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3), reps=reps)
-    bn.add("chamfer bwd", f"B={Bc} {P1}x{P2}", us_b, 32 * Bc * (P1 + P2))
+    # gradient w.r.t. src (the prediction); the target cloud has no gradient (loss.py:176-181)
+    us_b = bn.timeit(lambda: F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3, need_src=True, need_tgt=False), reps=reps)
+    bn.add("chamfer bwd (src)", f"B={Bc} {P1}x{P2}", us_b, 32 * Bc * (P1 + P2))
+    us_b2 = bn.timeit(lambda: F.chamfer_bwd(src, tgt, r["i_src"], r["i_tgt"], g, g, 3), reps=reps)
+    bn.add("chamfer bwd (both)", f"B={Bc} {P1}x{P2}", us_b2, 32 * Bc * (P1 + P2) + 12 * Bc * P2)
     return bn, dict(B=Bc, P1=P1, P2=P2, us_fwd=us_f, us_bwd=us_b)
 
 
