@@ -191,6 +191,17 @@ int tpg_group_bwd_f32(const float* grad_out, const int32_t* seg_offsets,
                       const int32_t* seg_items, int B, int C, int N, int L,
                       float* grad_f, tpg_stream_t stream);
 
+/* Long rows (L = M*k > 65536 positions, N <= 8192 source points): the shared-memory-staged backward keeps
+ * 16-bit row positions, so the row is processed in S segments of L/S positions, each continuing the
+ * sequential sums of the one before (same summation order as one pass: results stay bit-identical).
+ *   tpg_group_bwd_segments   S for this shape (0 or 1: use tpg_group_bwd_f32 with the plain inverse index)
+ *   tpg_group_bwd_segmented_f32  seg_offsets [B*S, N+1], seg_items [B*S, L/S] = the inverse index of idx
+ *                            viewed as [B*S, L/S] (tpg_inverse_index_build(idx, B*S, N, L/S, ...)).        */
+int tpg_group_bwd_segments(int B, int C, int N, int L);
+int tpg_group_bwd_segmented_f32(const float* grad_out, const int32_t* seg_offsets,
+                                const int32_t* seg_items, int B, int C, int N, int L, int S,
+                                float* grad_f, tpg_stream_t stream);
+
 /* ---- K7: fused gather + reduce over the k neighbours ---------------------
  * replaces grouping_operation followed by torch.max(dim=-1) —
  *   gcn_lib/pointnet/gcn.py:261-263 — without materialising [B,C,M,k].

@@ -902,6 +902,16 @@ TPG_API int tpg_group_bwd_f32(const float* grad_out, const int32_t* seg_offsets,
   return launch_bwd(a, as_stream(stream));
 }
 
+TPG_API int tpg_group_bwd_segments(int B, int C, int N, int L) { return tpg::group_bwd_staged_segments(B, C, N, L); }
+
+TPG_API int tpg_group_bwd_segmented_f32(const float* grad_out, const int32_t* seg_offsets, const int32_t* seg_items,
+                                        int B, int C, int N, int L, int S, float* grad_f, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 1 && L >= 1 && S >= 1, TPG_EINVAL, "group_bwd_segmented: bad size");
+  if (B == 0 || C == 0) return TPG_OK;
+  TPG_REQUIRE(grad_f && seg_offsets && grad_out && seg_items, TPG_EINVAL, "group_bwd_segmented: null pointer");
+  return tpg::group_bwd_staged_segmented(grad_out, seg_offsets, seg_items, B, C, N, L, S, grad_f, as_stream(stream));
+}
+
 // tuning hook (tools/bench_group_bwd.py; not part of the ABI): variant 0 = plain CSR gather, 1/2/4 = staged kernel
 // with that many channels per thread, -1 = the dispatch of tpg_group_bwd_f32
 TPG_API int tpg_debug_group_bwd_variant(const float* grad_out, const int32_t* seg_offsets, const int32_t* seg_items,

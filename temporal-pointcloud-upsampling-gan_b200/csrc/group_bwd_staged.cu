@@ -42,7 +42,9 @@ struct StagedArgs {
   const int32_t* off;    // [B, N + 1]
   const int32_t* items;  // [B, L], ascending inside a segment
   float* gf;             // [B, C, N]
-  int B, C, N, L;
+  int B, C, N, L;        // L = positions of the segment being processed
+  int Ltot, seg, NSEG;   // row length of grad_out, segment index, segments per cloud (1: the whole row)
+  int init;              // 1: accumulators start from grad_f (the partial sums of the segments before this one)
   int G, NPs;            // thread groups per CTA and their stride in threads
   int TC, Lc, nch;       // channels per stage, chunk length (floats), chunks per row
   int S, items_bytes;    // ring stages; bytes reserved in front of the ring for the 16-bit item list
@@ -115,7 +117,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) group_bwd_staged_kernel(const S
     __syncwarp();
     if (lane < vc)
       sb_bulk_load(sb_smem_u32(ring + (size_t)st * stage_floats + (size_t)lane * a.Lc),
-                   a.go + ((size_t)b * a.C + c0 + lane) * a.L + (size_t)j * a.Lc, (uint32_t)len * 4u, bar);
+                   a.go + ((size_t)b * a.C + c0 + lane) * a.Ltot + (size_t)a.seg * a.L + (size_t)j * a.Lc,
+                   (uint32_t)len * 4u, bar);
   };
   if (warp == 0)
     for (int q = 0; q < S - 1 && q < my_chunks; ++q) issue(q);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) group_bwd_staged_kernel(const S
     const int b = tile / a.ctiles, c0 = (tile % a.ctiles) * a.TC;
     if (b != items_b) {  // (uniform over the CTA) 32-bit CSR items -> 16-bit row positions in shared memory
       __syncthreads();   // nobody still walks the previous list
-      const int4* src = reinterpret_cast<const int4*>(a.items + (size_t)b * a.L);
+      const int4* src = reinterpret_cast<const int4*>(a.items + ((size_t)b * a.NSEG + a.seg) * a.L);
       uint2* dst = reinterpret_cast<uint2*>(items_s);
       for (int e = tid; e < (a.L >> 2); e += SB_THREADS) {
         const int4 v = __ldg(src + e);
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) group_bwd_staged_kernel(const S
       items_b = b;
       __syncthreads();
     }
-    const int32_t* ob = a.off + (size_t)b * (a.N + 1);
+    const int32_t* ob = a.off + ((size_t)b * a.NSEG + a.seg) * (a.N + 1);
     int cur[NPT], end[NPT], nxt[NPT];
     float acc[NPT][TCG];
 #pragma unroll
@@ -152,7 +155,11 @@ __global__ void __launch_bounds__(SB_THREADS, 1) group_bwd_staged_kernel(const S
       }
       nxt[p] = cur[p] < end[p] ? (int)items_s[cur[p]] : INT_MAX;
 #pragma unroll
-      for (int c = 0; c < TCG; ++c) acc[p][c] = 0.0f;
+      for (int c = 0; c < TCG; ++c) {
+        acc[p][c] = 0.0f;
+        // later segments continue the sequential sum of the earlier ones: same order as one pass over the row
+        if (a.init && active && n < a.N && c0 + ch0 + c < a.C) acc[p][c] = a.gf[((size_t)b * a.C + c0 + ch0 + c) * a.N + n];
+      }
     }
     for (int j = 0; j < a.nch; ++j, ++q) {
       if (warp == 0 && q + S - 1 < my_chunks) {
@@ -206,6 +213,17 @@ int launch_staged(const StagedArgs& a, int grid, size_t smem, cudaStream_t st) {
 
 }  // namespace
 
+// segments the staged kernel needs for rows of L positions: 1 (whole row) up to L = 65536 (16-bit row positions in
+// shared memory), else the smallest S with L % (4 S) == 0 and L / S <= 65536; 0 = not eligible
+int group_bwd_staged_segments(int B, int C, int N, int L) {
+  if (N < 1 || N > 8 * SB_THREADS || (L & 3) || L < 1024) return 0;
+  if ((long long)B * C * L < (1LL << 18)) return 0;  // tiny: one launch of the plain kernel is cheaper
+  if (L <= 65536) return N <= 4 * SB_THREADS ? 1 : 0;  // (N > 4096 with short rows: the plain kernel)
+  for (int S = 2; S <= 16; ++S)
+    if (L % (4 * S) == 0 && L / S <= 65536) return S;
+  return 0;
+}
+
 bool group_bwd_staged_eligible(const float* go, const int32_t* items, int B, int C, int N, int L) {
   if (N < 1 || N > 4 * SB_THREADS || (L & 3) || L < 1024 || L > 65536) return false;  // 16-bit row positions
   if (((reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(items)) & 15) != 0) return false;
@@ -214,12 +232,36 @@ bool group_bwd_staged_eligible(const float* go, const int32_t* items, int B, int
 }
 
 // force: 0 = heuristic, else 10 * stages + channels per thread
+static int group_bwd_staged_seg(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L,
+                                int Ltot, int seg, int S_seg, float* gf, int force, cudaStream_t st);
+
 int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L, float* gf,
                      int force, cudaStream_t st) {
+  return group_bwd_staged_seg(go, off, items, B, C, N, L, L, 0, 1, gf, force, st);
+}
+
+// rows longer than 65536 positions: S launches, one per segment of L / S positions, each continuing the sums of the
+// previous one (off / items: the inverse index of idx viewed as [B*S, L/S], positions relative to the segment)
+int group_bwd_staged_segmented(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L,
+                               int S, float* gf, cudaStream_t st) {
+  TPG_REQUIRE(S >= 1 && L % (4 * S) == 0 && L / S <= 65536 && N <= 8 * SB_THREADS, TPG_EUNSUPPORTED,
+              "group_bwd_segmented: unsupported (N=%d L=%d S=%d)", N, L, S);
+  TPG_REQUIRE(((reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(items)) & 15) == 0, TPG_EUNSUPPORTED,
+              "group_bwd_segmented: grad_out / items must be 16-byte aligned");
+  for (int s = 0; s < S; ++s) {
+    const int rc = group_bwd_staged_seg(go, off, items, B, C, N, L / S, L, s, S, gf, 0, st);
+    if (rc) return rc;
+  }
+  return TPG_OK;
+}
+
+static int group_bwd_staged_seg(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L,
+                                int Ltot, int seg, int S_seg, float* gf, int force, cudaStream_t st) {
   StagedArgs a{};
   a.go = go; a.off = off; a.items = items; a.gf = gf;
   a.B = B; a.C = C; a.N = N; a.L = L;
-  const int NPT = N <= SB_THREADS ? 1 : (N <= 2 * SB_THREADS ? 2 : 4);
+  a.Ltot = Ltot; a.seg = seg; a.NSEG = S_seg; a.init = seg > 0 ? 1 : 0;
+  const int NPT = N <= SB_THREADS ? 1 : (N <= 2 * SB_THREADS ? 2 : (N <= 4 * SB_THREADS ? 4 : 8));
   a.NPs = N >= SB_THREADS ? SB_THREADS : ((N + 31) & ~31);
   a.G = SB_THREADS / a.NPs;
   a.items_bytes = (int)align_up((size_t)2 * L + 2, 128);  // + the one-past-the-end peek
@@ -228,7 +270,7 @@ int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, 
   // of >= 4096 floats (or whole rows).  min_tiles is half a wave: the step replays many groupings concurrently,
   // so SM-time matters more than the latency of one call.
   int TCG = 1;
-  const int max_tcg = NPT <= 2 ? 4 : (NPT == 4 ? 2 : 1);
+  const int max_tcg = NPT <= 2 ? 4 : (NPT == 4 ? 2 : 1);  // NPT = 8: one channel per item walk (registers)
   const int min_tiles = num_sms() / 2;
   for (int t = max_tcg; t >= 2; t >>= 1) {
     const long long TC = (long long)a.G * t;
@@ -264,6 +306,7 @@ int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, 
     case 24: return launch_staged<2, 4>(a, grid, smem, st);
     case 41: return launch_staged<4, 1>(a, grid, smem, st);
     case 42: return launch_staged<4, 2>(a, grid, smem, st);
+    case 81: return launch_staged<8, 1>(a, grid, smem, st);
   }
   set_error("group_bwd_staged: no variant for NPT=%d TCG=%d", NPT, TCG);
   return TPG_EUNSUPPORTED;

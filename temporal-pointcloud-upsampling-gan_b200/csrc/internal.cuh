@@ -53,6 +53,9 @@ int build_csr(const int32_t* idx, const int64_t* item_len, int B, int N, int L, 
 bool group_bwd_staged_eligible(const float* go, const int32_t* items, int B, int C, int N, int L);
 int group_bwd_staged(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L, float* gf,
                      int force_tcg, cudaStream_t st);
+int group_bwd_staged_segments(int B, int C, int N, int L);
+int group_bwd_staged_segmented(const float* go, const int32_t* off, const int32_t* items, int B, int C, int N, int L,
+                               int S, float* gf, cudaStream_t st);
 // fps.cu: CTAs (SMs) per cloud for 2048 < N <= 65536 (tpg_set_option "fps.sms_per_cloud")
 std::atomic<int>& fps_cluster_option();
 std::atomic<int>& fps_exclusive_option();

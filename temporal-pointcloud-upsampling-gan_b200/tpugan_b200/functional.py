@@ -333,8 +333,8 @@ class _CsrCache:
         self._rr = 0
 
     @staticmethod
-    def _key(idx, N):
-        return (idx.data_ptr(), idx._version, tuple(idx.shape), N, idx.device.index)
+    def _key(idx, N, segments=1):
+        return (idx.data_ptr(), idx._version, tuple(idx.shape), N, idx.device.index, segments)
 
     def _insert(self, key, entry):
         self.entries[key] = entry
@@ -361,15 +361,17 @@ class _CsrCache:
             done.record(side)
         self._insert(key, (idx, off, items, done))
 
-    def get(self, idx: torch.Tensor, N: int):
-        key = self._key(idx, N)
+    def get(self, idx: torch.Tensor, N: int, segments: int = 1):
+        """(seg_offsets, seg_items) of idx; segments > 1: the inverse index of idx viewed as [B*segments, L/segments]
+        (layout of tpg_group_bwd_segmented_f32)."""
+        key = self._key(idx, N, segments)
         hit = self.entries.get(key)
         if hit is not None:
             self.entries.move_to_end(key)
             if hit[3] is not None:
                 torch.cuda.current_stream(idx.device).wait_event(hit[3])
             return hit[1], hit[2]
-        off, items = inverse_index(idx, N)
+        off, items = inverse_index(idx if segments == 1 else idx.reshape(idx.shape[0] * segments, -1), N)
         self._insert(key, (idx, off, items, None))
         return off, items
 
@@ -393,6 +395,24 @@ def group_bwd(grad_out, off, items, N: int) -> torch.Tensor:
     gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
     with _on_device(grad_out.device):
         _lib.call("tpg_group_bwd_f32", _ptr(grad_out), _ptr(off), _ptr(items), B, C, N, L, _ptr(gf), _stream())
+    return gf
+
+
+def group_bwd_auto(grad_out, idx, N: int) -> torch.Tensor:
+    """Grouping backward from the index tensor: grad_out [B,C,M,k], idx int32 [B,M,k] -> grad_f [B,C,N].  Picks the
+    inverse-index layout the kernels want (whole rows, or S segments for rows of more than 65536 positions) and
+    shares it through csr_cache."""
+    B, C = grad_out.shape[0], grad_out.shape[1]
+    L = grad_out.numel() // max(B * C, 1)
+    S = _lib.load().tpg_group_bwd_segments(B, C, N, L) if grad_out.is_cuda else 0
+    if S <= 1:
+        off, items = csr_cache.get(idx, N)
+        return group_bwd(grad_out, off, items, N)
+    off, items = csr_cache.get(idx, N, segments=S)
+    _req(grad_out, "grad_out", torch.float32)
+    gf = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
+    with _on_device(grad_out.device):
+        _lib.call("tpg_group_bwd_segmented_f32", _ptr(grad_out), _ptr(off), _ptr(items), B, C, N, L, S, _ptr(gf), _stream())
     return gf
 
 
@@ -645,8 +665,7 @@ class GroupingOperation(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         rec = _log.begin("group_bwd", grad_out=grad_out, idx=idx, N=ctx.N) if _log.on else None
-        off, items = csr_cache.get(idx, ctx.N)
-        gf = group_bwd(grad_out, off, items, ctx.N)
+        gf = group_bwd_auto(grad_out, idx, ctx.N)
         if rec is not None:
             _log.end(rec, grad_f=gf)
         return gf, None

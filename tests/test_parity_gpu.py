@@ -456,6 +456,27 @@ def test_grouping_autograd_matches_oracle(F, oracle):
     np.testing.assert_array_equal(ft2.grad.cpu().numpy(), oracle.group_bwd(g2[..., None], gi[:, :, None], 200))
 
 
+@pytest.mark.parametrize("B,C,N,M,k,S", [
+    (1, 8, 8192, 8192, 16, 2),    # L = 131072: two segments of 65536 positions, 8 source points per thread
+    (2, 5, 5000, 6000, 24, 3),    # L = 144000: three segments, ragged N
+    (1, 40, 3000, 4500, 32, 3),   # N <= 4096 with a long row
+    (1, 4, 8192, 2048, 16, 0),    # N > 4096 with a short row: plain inverse-index kernel
+])
+def test_group_bwd_long_rows_segmented_bit_exact(F, oracle, B, C, N, M, k, S):
+    from tpugan_b200 import _lib
+
+    assert _lib.load().tpg_group_bwd_segments(B, C, N, M * k) == S
+    rng = np.random.default_rng(M + k)
+    idx = rng.integers(0, N, size=(B, M, k)).astype(np.int32)
+    idx[:, : M // 7] = 3  # one very long segment
+    go = rng.standard_normal((B, C, M, k)).astype(np.float32)
+    f = cu(rng.standard_normal((B, C, N)).astype(np.float32)).requires_grad_(True)
+    out = F.GroupingOperation.apply(f, cu(idx))
+    out.backward(cu(go))
+    np.testing.assert_array_equal(f.grad.cpu().numpy(), oracle.group_bwd(go, idx, N))  # same summation order
+    F.csr_cache.clear()
+
+
 @pytest.mark.parametrize("op", [0, 1, 2])
 @pytest.mark.parametrize("B,C,N,M,k", [
     (2, 32, 256, 256, 9), (1, 7, 100, 33, 4), (2, 3, 3000, 500, 16),

@@ -126,9 +126,8 @@ def run_sweep(quick=False, reps=7, verbose=True):
         us = bn.timeit(lambda: F.group_reduce_fwd(f, idx, 0))
         bn.add("group+max fused", f"B={Bg} C={C} N=M={N} k={k}", us, 4 * Bg * (C * N + N * k + 2 * C * N))
         go = torch.randn(Bg, C, N, k, device=dev)
-        off, items = F.inverse_index(idx, N)
-        us = bn.timeit(lambda: F.group_bwd(go, off, items, N))
-        bn.add("group bwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes, "CSR prebuilt")
+        us = bn.timeit(lambda: F.group_bwd_auto(go, idx, N))
+        bn.add("group bwd", f"B={Bg} C={C} N=M={N} k={k}", us, nbytes, "inverse index cached")
         us = bn.timeit(lambda: F.inverse_index(idx, N))
         bn.add("inverse index", f"B={Bg} N={N} L={N * k}", us, 4 * Bg * (2 * N * k + N))
         del go
