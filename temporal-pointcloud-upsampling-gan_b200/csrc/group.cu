@@ -650,7 +650,9 @@ static int csr_stable_warps(int N, int L, bool* wide) {
   *wide = false;
   for (int W = 32; W >= 4; W >>= 1) {
     const long long chunk = ((long long)(L + W - 1) / W + 127) & ~127LL;
-    const bool w32 = chunk > 65535;
+    // the kernel overwrites a warp's per-key counter with the exclusive prefix over ALL warps, which can reach the
+    // whole row (one key repeated L times): 16-bit counters only when that total fits
+    const bool w32 = (long long)W * chunk > 65535;
     const size_t bytes = sizeof(int32_t) * (size_t)((N + 1 + 3) & ~3) + (size_t)W * N * (w32 ? 5 : 3);
     if (bytes <= 220 * 1024) { *wide = w32; return W; }
   }

@@ -456,6 +456,21 @@ def test_grouping_autograd_matches_oracle(F, oracle):
     np.testing.assert_array_equal(ft2.grad.cpu().numpy(), oracle.group_bwd(g2[..., None], gi[:, :, None], 200))
 
 
+def test_inverse_index_one_key_repeated_more_than_65535_times(F, oracle):
+    """a key that occurs > 65535 times in one cloud (all-zero padded / no-hit index lists) at N just above 2048:
+    the single-CTA stable build must not wrap its per-key prefix (16-bit counters)"""
+    N, M, k = 2100, 4400, 16  # L = 70400
+    rng = np.random.default_rng(99)
+    idx = np.zeros((1, M, k), np.int32)
+    idx[0, ::50] = rng.integers(0, N, size=(len(range(0, M, 50)), k))
+    go = rng.standard_normal((1, 2, M, k)).astype(np.float32)
+    off, items = F.inverse_index(cu(idx), N)
+    gf = F.group_bwd(cu(go), off, items, N)
+    np.testing.assert_array_equal(gf.cpu().numpy(), oracle.group_bwd(go, idx, N))
+    o = off.cpu().numpy()[0]
+    assert o[1] - o[0] > 65535 and o[-1] == M * k
+
+
 @pytest.mark.parametrize("B,C,N,M,k,S", [
     (1, 8, 8192, 8192, 16, 2),    # L = 131072: two segments of 65536 positions, 8 source points per thread
     (2, 5, 5000, 6000, 24, 3),    # L = 144000: three segments, ragged N
