@@ -410,7 +410,38 @@ def real_step_leg(args, world, rank, dev, batch, timed):
     hot, total = sum(per_op.values()), a.elapsed_time(b)
     grads = [torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
              for net in ctx.networks()]
-    if ctx.hook is not None:
+    graphed = None
+    if domain == "fluid" and world == 1:
+        # the same step with the host round trips removed and captured as two CUDA graphs (tpugan_b200.graph_step: the
+        # reference's own networks; labels / permutations / rotations drawn on the host in the reference's order and
+        # copied in; one host read per step).  Fresh context: capturable Adam.
+        try:
+            del ctx
+            torch.cuda.empty_cache()
+            ctx2 = refstep.build(domain, B=batch, n_lo=n_lo, ratio=ratio, backend="cuda", device=dev, seed=1 + rank, capturable=True)
+            gs = refstep.graphed_step(ctx2, capture=True)
+            it = [12]
+
+            def one_g():
+                it[0] += 2
+                return gs.step(it[0])
+
+            for _ in range(3):
+                one_g()
+            ms_g = timed(one_g, steps, 0, flush=False)
+            gl = one_g()
+            graphed = {"train_steps_per_s": 1e3 / ms_g, "ms_per_step": ms_g, "samples_per_s": batch * 1e3 / ms_g,
+                       "what": "tpugan_b200.graph_step.GraphedFluidStep: generator phase and discriminator phase as two CUDA "
+                               "graphs over the reference's unmodified networks; equal to the reference step for equal seeds "
+                               "(tests/test_graph_step_gpu.py)",
+                       "host_syncs_per_step": 1, "losses": {k: float(v) for k, v in gl.items()}}
+            if ctx2.hook is not None:
+                ctx2.hook.remove()
+            del gs, ctx2
+        except Exception as e:
+            graphed = {"unavailable": repr(e)[:300]}
+        ctx = None
+    if ctx is not None and ctx.hook is not None:
         ctx.hook.remove()
     return {
         "train_steps_per_s": 1e3 / ms, "global_batch": batch * world,
@@ -426,6 +457,7 @@ def real_step_leg(args, world, rank, dev, batch, timed):
         "boundary_calls_per_step": len(calls), "library_launches_per_step": int(launches),
         "allreduce_bytes_per_step": int(allreduce_bytes), "sync_bn": bool(args.sync_bn and world > 1),
         "losses": {k: float(v) for k, v in losses.items()},
+        "graphed": graphed,
     }, grads
 
 

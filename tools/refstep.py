@@ -131,7 +131,7 @@ class StepContext:
 
 def build(domain: str = "fluid", B: int = 2, n_lo: int = 512, ratio: int = 4, backend: str = "cuda", device=None,
           seed: int = 1, trained_mask: bool = True, masked_frac=(0.01, 0.06), use_vel: bool = False,
-          lr: float = 1e-4, mods: Optional[Dict[str, Any]] = None) -> StepContext:
+          lr: float = 1e-4, mods: Optional[Dict[str, Any]] = None, capturable: bool = False) -> StepContext:
     """Reference models + synthetic frames.  Shapes of BASELINE configs[1]: B=8, n_lo=2048, ratio=4."""
     import torch
 
@@ -169,14 +169,16 @@ def build(domain: str = "fluid", B: int = 2, n_lo: int = 512, ratio: int = 4, ba
         v = torch.from_numpy(vel_np).to(device)
         vel_hi = [v.clone() for _ in hi]
         vel_lo = [v[:, ::ratio].contiguous() for _ in hi]
-    optims = tuple(torch.optim.Adam(m.parameters(), lr=lr) for m in (g, td, sd))
+    # capturable: Adam keeps its step count on the device (required inside CUDA-graph capture; same update rule)
+    optims = tuple(torch.optim.Adam(m.parameters(), lr=lr, capturable=capturable) for m in (g, td, sd))
     ctx = StepContext(domain, mods, g, sd, td, optims, lo, hi, vel_lo, vel_hi, opt, device)
     if domain == "fluid" and trained_mask:
         # values of a trained mask head: 1 = keep, 0 = drop; 1-6 % dropped, a different count per cloud
         keep = np.ones((B, n_lo, 1), np.float32)
-        fr = np.linspace(masked_frac[0], masked_frac[1], B) if B > 1 else np.array([masked_frac[1]])
-        for b in range(B):
-            keep[b, rng.choice(n_lo, size=max(1, int(round(fr[b] * n_lo))), replace=False)] = 0.0
+        if masked_frac is not None:  # None: every point kept (no dummy padding anywhere in the step)
+            fr = np.linspace(masked_frac[0], masked_frac[1], B) if B > 1 else np.array([masked_frac[1]])
+            for b in range(B):
+                keep[b, rng.choice(n_lo, size=max(1, int(round(fr[b] * n_lo))), replace=False)] = 0.0
         ctx.keep = torch.from_numpy(keep).to(device)
 
         def trained_mask_hook(_module, _inputs, out):
@@ -200,6 +202,47 @@ def step(ctx: StepContext, n_iter: int = 12, freeze_D: bool = False) -> Dict[str
                                   ctx.opt, n_iter, og, ot, os_, freeze_D=freeze_D)
     return tsf.tempo_gan_step_no_mask(ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, lo, hi, ctx.opt, n_iter, og, ot,
                                       os_, freeze_D=freeze_D)
+
+
+def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3):
+    """The graph-capturable form of the fluid step (tpugan_b200.graph_step) over this context's networks, frames and
+    (capturable) optimisers."""
+    from tpugan_b200.graph_step import GraphedFluidStep
+
+    assert ctx.domain == "fluid"
+    og, ot, os_ = ctx.optims
+    return GraphedFluidStep(ctx.mods, ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, ctx.lo, ctx.hi, ctx.opt, (og, ot, os_),
+                            furthest_distance=1.0, warmup=warmup, capture=capture)
+
+
+def snapshot(ctx: StepContext):
+    """Deep copy of every parameter / buffer / optimiser-state tensor (restore() copies back IN PLACE, so CUDA graphs
+    captured over these tensors stay valid)."""
+    import torch
+
+    nets = [{k: v.detach().clone() for k, v in net.state_dict().items()} for net in ctx.networks()]
+    opts = [[{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()} for st in o.state.values()]
+            for o in ctx.optims]
+    return nets, opts
+
+
+def restore(ctx: StepContext, snap, zero_new_optimizer_state: bool = True):
+    import torch
+
+    nets, opts = snap
+    with torch.no_grad():
+        for net, st in zip(ctx.networks(), nets):
+            cur = net.state_dict()
+            for k, v in st.items():
+                cur[k].copy_(v)
+        for o, saved in zip(ctx.optims, opts):
+            for i, st in enumerate(o.state.values()):
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if i < len(saved) and k in saved[i]:
+                            v.copy_(saved[i][k])
+                        elif zero_new_optimizer_state:
+                            v.zero_()
 
 
 def generator_forward(ctx: StepContext):
