@@ -334,3 +334,45 @@ def test_patch_reference_equals_unpatched(oracle):
     finally:
         h.unpatch()
     assert dis.ball_query_wrapper is not None and gcn.IDGCNLayer.forward.__name__ == "forward"
+
+
+# ---------------------------------------------------------------------------------------- f4: GPU data pipeline
+def test_gpu_data_pipeline_matches_reference_functions():
+    """tpugan_b200.data_pipeline vs the reference's own CPU code (train_utils.sample_patch_with_fps with scipy's KD-tree
+    and the numba FPS of sampling.py), fed the same random choices."""
+    import refstep
+    from tpugan_b200 import data_pipeline as dp
+
+    refstep.import_reference("cuda")
+    import train_utils  # the reference's module (baseline/_ref)
+
+    rng = np.random.default_rng(21)
+    N = 12000
+    frames = []
+    base = (rng.uniform(0, 0.6, size=(N, 3)) + np.array([3.0, -1.0, 0.5])).astype(np.float32)
+    for t in range(3):
+        frames.append({"pos": (base + 0.01 * t * rng.standard_normal((N, 3))).astype(np.float32),
+                       "vel": rng.standard_normal((N, 3)).astype(np.float32)})
+    center, _, _ = train_utils.normalize_point_cloud(frames[1]["pos"].copy())
+    np.random.seed(5)
+    ref, patch, fps_idx = train_utils.sample_patch_with_fps(center, 1.0, sample_num=4096, return_free_surface_particles=False,
+                                                            return_patch_and_fps_idx=True)
+    np.random.seed(5)
+    seed_idx = int(np.random.choice(N))
+    start = int(np.random.randint(4096))
+    gp, gf = dp.sample_patch_with_fps(cu(center), 4096, seed_idx=seed_idx, fps_start=start)
+    assert np.array_equal(np.sort(gp.cpu().numpy()), np.sort(patch))      # same patch (the KD-tree orders ties freely)
+    assert np.array_equal(gp.cpu().numpy(), patch)                          # and, on tie-free data, the same order
+    assert np.array_equal(gf.cpu().numpy(), fps_idx) and len(fps_idx) == 512
+    win = dp.fluid_window([{k: cu(v) for k, v in f.items()} for f in frames], sample_num=4096, jitter=0.0,
+                          seed_idx=seed_idx, fps_start=start)
+    # the centroid is a float32 mean of 12 000 coordinates near 3.0: NumPy's and the GPU's summation orders differ by ~5e-6
+    assert np.allclose(win["highres_pos"].cpu().numpy(), ref["patch_pos"], atol=3e-5)
+    assert np.allclose(win["lowres_pos"].cpu().numpy(), ref["ds_pos"], atol=3e-5)
+    assert np.array_equal(win["patch_idx"].cpu().numpy(), patch) and np.array_equal(win["fps_idx"].cpu().numpy(), fps_idx)
+    assert win["highres_pos_left"].shape == (4096, 3) and win["lowres_pos_right"].shape == (512, 3)
+    assert torch.equal(win["lowres_vel"], cu(frames[1]["vel"])[win["fps_idx"]])
+    j = dp.fluid_window([{k: cu(v) for k, v in f.items()} for f in frames], sample_num=4096, jitter=0.003,
+                        seed_idx=seed_idx, fps_start=start)
+    d = (j["lowres_pos"] - win["lowres_pos"]).std().item()
+    assert 0.002 < d < 0.004

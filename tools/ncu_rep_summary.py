@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Summarise one .ncu-rep holding several kernels (tools/prof_kernels.py under ncu --set full) into markdown and
+update profiles/ncu_traffic.json (DRAM read + write bytes AND L2 bytes per launch).
+    python tools/ncu_rep_summary.py gpurun_out/prof_r02a.ncu-rep r02a
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from ncu_summary import KEYS  # noqa: E402
+
+rep, tag = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+h, units, data = rows[0], rows[1], rows[2:]
+ki = h.index("Kernel Name")
+seen = {}
+for r in data:  # keep the LAST launch of every kernel name (the one after the warm-up and the L2 flush)
+    seen[r[ki].split("(")[0].replace("void ", "")] = r
+out = [f"# ncu --set full — {tag}", "",
+       "`ncu --set full --clock-control none --import-source on -k regex:tpg -c 60 python tools/prof_kernels.py`: one launch of every "
+       "hot kernel at a BASELINE configs[1] shape (second launch, L2 flushed before it; K2 on real generator activations).", ""]
+traffic = {"_source": f"{tag}: dram__bytes_read.sum + dram__bytes_write.sum and lts__t_bytes.sum of one launch per kernel "
+                      "(ncu --set full --clock-control none, L2 flushed before the launch; tools/prof_kernels.py)"}
+for name, r in seen.items():
+    out += [f"## `{name[:100]}`", "", "| metric | unit | value |", "|---|---|---:|"]
+    for k in KEYS:
+        if k in h:
+            out.append(f"| {k} | {units[h.index(k)]} | {r[h.index(k)]} |")
+    out.append("")
+
+    def val(k):
+        if k not in h:
+            return None
+        v, u = float(r[h.index(k)].replace(",", "")), units[h.index(k)]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+    rd, wr, l2 = val("dram__bytes_read.sum"), val("dram__bytes_write.sum"), val("lts__t_bytes.sum")
+    short = name.split("<")[0].replace("tpg::", "")
+    traffic[short] = {"dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_read": rd, "dram_write": wr, "l2_bytes_per_launch": l2,
+                      "duration_us": (val("gpu__time_duration.sum") or 0) / 1e3 if units[h.index("gpu__time_duration.sum")] == "ns" else val("gpu__time_duration.sum"),
+                      "launch": name[:120]}
+open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.md"), "w").write("\n".join(out) + "\n")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+print("kernels:", list(seen))
