@@ -652,7 +652,7 @@ def run_ours(args):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             # overlapped calls: an FPS call should hold 8 SMs, not a 64-SM cluster, for its whole duration
-            _lib.set_option("fps.sms_per_cloud", 1)
+            _lib.set_option("fps.sms_per_cloud", int(os.environ.get("TPG_BENCH_FPS_SMS", "1")))
             _lib.set_option("fps.exclusive_sm", 1)  # ... and keeps those SMs to itself (latency-bound rounds)
             Fn.csr_cache.prefetch_enabled = True     # inverse indices are built off the backward's critical path
             with torch.cuda.stream(side):
@@ -717,6 +717,9 @@ def run_ours(args):
         tr = traffic.get(OP_KERNEL[op]) or {}
         return {"bound": "hbm", "kernel": OP_KERNEL[op], "op": op, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": tr.get("dram_bytes_per_launch"),
+                "traffic_launch": {"kernel": tr.get("launch"), "alg_bytes": tr.get("alg_bytes_of_this_launch"),
+                                   "dram_read": tr.get("dram_read"), "dram_write": tr.get("dram_write"),
+                                   "note": "one profiled launch (tools/prof_kernels.py shape), not the step average"},
                 "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch "
                                   "of this kernel, ncu --set full)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

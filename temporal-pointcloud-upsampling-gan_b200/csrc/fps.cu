@@ -341,12 +341,11 @@ static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
   // option "fps.sms_per_cloud" = 1|2|4: fewer SMs per cloud.  A round gets slower, but a call that overlaps with
   // other work (multi-stream replay) then holds 8/16/32 SMs instead of 64 for its whole duration.
   const int cl_env = fps_cluster_option().load(std::memory_order_relaxed);
-  if (cl_env != FPS_CL && N <= 8192 * cl_env && (cl_env == 1 || cl_env == 2 || cl_env == 4)) {
+  if (cl_env < 4 && N <= 8192 * cl_env && (cl_env == 1 || cl_env == 2)) {
     const int ppc = (ceil_div(N, cl_env) + 31) & ~31;
-    const int t8 = (ceil_div(ppc, 8) + 31) & ~31, t4 = (ceil_div(ppc, 4) + 31) & ~31;
+    const int t8 = (ceil_div(ppc, 8) + 31) & ~31;
     if (cl_env == 1) return fps_launch<8, 1, MODEB>(a, t8, st);
-    if (cl_env == 2) return t4 <= 1024 ? fps_launch<4, 2, MODEB>(a, t4, st) : fps_launch<8, 2, MODEB>(a, t8, st);
-    return t4 <= 1024 ? fps_launch<4, 4, MODEB>(a, t4, st) : fps_launch<8, 4, MODEB>(a, t8, st);
+    return fps_launch<8, 2, MODEB>(a, t8, st);
   }
   if (N <= FPS_REG_MAX) {
     // measured (tools/bench_fps.py, one-way exchange): a round is cheapest with 8 points per thread and as few

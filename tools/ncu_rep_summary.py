@@ -24,6 +24,13 @@ for r in data:  # keep the LAST launch of every kernel name (the one after the w
 out = [f"# ncu --set full — {tag}", "",
        "`ncu --set full --clock-control none --import-source on -k regex:tpg -c 60 python tools/prof_kernels.py`: one launch of every "
        "hot kernel at a BASELINE configs[1] shape (second launch, L2 flushed before it; K2 on real generator activations).", ""]
+# algorithmic bytes (SURVEY.md §8d formulas) of the shapes tools/prof_kernels.py launches
+B_ = 8
+ALG = {"group_bwd_staged_kernel": 4 * B_ * (64 * 32768 + 32768 + 64 * 2048), "group_fwd_kernel": 4 * B_ * (64 * 2048 + 32768 + 64 * 32768),
+       "group_reduce_fwd_smem_kernel": 4 * B_ * (64 * 2048 + 32768 + 2 * 64 * 2048), "knn_feat_tc_kernel": 4 * B_ * 64 * 4096 + 12 * B_ * 2048 * 12,
+       "fps_reg_kernel": 12 * B_ * 2048 + 4 * B_ * 512, "ball_query_kernel": 12 * B_ * (8192 + 1024) + 4 * B_ * 1024 * 32,
+       "grid_knn_kernel": 4 * B_ * 3 * 2 * 8192 + 12 * B_ * 8192 * 16, "grid_nn1_kernel": 20 * B_ * 2 * 8192,
+       "csr_cluster_kernel": 4 * B_ * (2 * 32768 + 2048)}
 traffic = {"_source": f"{tag}: dram__bytes_read.sum + dram__bytes_write.sum and lts__t_bytes.sum of one launch per kernel "
                       "(ncu --set full --clock-control none, L2 flushed before the launch; tools/prof_kernels.py)"}
 for name, r in seen.items():
@@ -40,10 +47,12 @@ for name, r in seen.items():
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 
     rd, wr, l2 = val("dram__bytes_read.sum"), val("dram__bytes_write.sum"), val("lts__t_bytes.sum")
-    short = name.split("<")[0].replace("tpg::", "")
+    import re
+
+    short = re.sub(r"<[^<>]*>$", "", name.replace("<unnamed>::", "").replace("unnamed>::", "").replace("tpg::", "")).strip()
     traffic[short] = {"dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_read": rd, "dram_write": wr, "l2_bytes_per_launch": l2,
                       "duration_us": (val("gpu__time_duration.sum") or 0) / 1e3 if units[h.index("gpu__time_duration.sum")] == "ns" else val("gpu__time_duration.sum"),
-                      "launch": name[:120]}
+                      "launch": name[:120], "alg_bytes_of_this_launch": ALG.get(short)}
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.md"), "w").write("\n".join(out) + "\n")
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 print("kernels:", list(seen))
