@@ -215,11 +215,23 @@ class static_model_methods:
 
 # ------------------------------------------------------------------------------------------ the step, host-sync free
 def generator_phase(mods, sr_net, spatial_dis, tempo_dis, lowres_pos_lst, highres_pos_lst, furthest_distance, opt, n_iter,
-                    sr_net_optim, rnd: StepRandoms):
+                    sr_net_optim, rnd: StepRandoms, side_streams=None):
     """train_step_final.py:92-163 (position-only inputs) without host synchronisation.  Returns the loss tensors and
-    the detached fake frames the discriminator phase consumes."""
+    the detached fake frames the discriminator phase consumes.  `side_streams` (one per neighbouring frame): the
+    generator passes of the neighbouring frames (:128-142) are independent of the centre frame's pass, loss and spatial
+    discriminator pass, so they are issued on their own streams (autograd runs their backward there too) and joined
+    before the temporal discriminator — same arithmetic, overlapping kernels."""
     tpugan_sr_loss = mods["train_step_final"].tpugan_sr_loss
     lowres = lowres_pos_lst[1]
+    others = [0] + list(range(2, len(highres_pos_lst)))
+    side = {}
+    cur = torch.cuda.current_stream()
+    if side_streams:
+        for frame, st in zip(others, side_streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                _, _, p = sr_net(lowres_pos_lst[frame], lowres_pos_lst[frame], hard_masking=True)
+                side[frame] = (p, p[:, rnd.perms[frame]])
     pred_pos, pred_mask, padded = sr_net(lowres, lowres, hard_masking=True)
     position_loss, cd, ml = tpugan_sr_loss(100., highres_pos_lst[1], pred_pos, lowres, pred_mask,
                                            opt.cutoff / furthest_distance, n_iter)
@@ -229,10 +241,17 @@ def generator_phase(mods, sr_net, spatial_dis, tempo_dis, lowres_pos_lst, highre
     pred_lst = [None] * len(highres_pos_lst)
     pred_lst[1] = padded
     last_padded = padded
-    for frame in [0] + list(range(2, len(highres_pos_lst))):
-        _, _, p = sr_net(lowres_pos_lst[frame], lowres_pos_lst[frame], hard_masking=True)
+    for k, frame in enumerate(others):
+        if side_streams:
+            cur.wait_stream(side_streams[k])
+            p, permuted = side[frame]
+            p.record_stream(cur)
+            permuted.record_stream(cur)
+        else:
+            _, _, p = sr_net(lowres_pos_lst[frame], lowres_pos_lst[frame], hard_masking=True)
+            permuted = p[:, rnd.perms[frame]]
         last_padded = p
-        pred_lst[frame] = p[:, rnd.perms[frame]]
+        pred_lst[frame] = permuted
     fake_label = tempo_dis(pred_lst, opt.R)
     tempo_loss = (0.5 * (fake_label - rnd.scalars[3]) ** 2).mean()
     sr_loss = gate * (tempo_loss + spatial_loss) + opt.w * position_loss
@@ -279,7 +298,7 @@ class GraphedFluidStep:
     Optimisers must be capturable (``torch.optim.Adam(..., capturable=True)``)."""
 
     def __init__(self, mods, sr_net, spatial_dis, tempo_dis, lowres_pos_lst, highres_pos_lst, opt, optims,
-                 furthest_distance: float = 1.0, warmup: int = 3, capture: bool = True):
+                 furthest_distance: float = 1.0, warmup: int = 3, capture: bool = True, overlap_frames: bool = False):
         self.mods, self.nets = mods, (sr_net, spatial_dis, tempo_dis)
         self.lowres = [t.clone() for t in lowres_pos_lst]
         self.highres = [t.clone() for t in highres_pos_lst]
@@ -293,6 +312,7 @@ class GraphedFluidStep:
         self.rnd = randoms_like(self._host, dev)
         self.rnd.copy_from(self._host)
         self.captured = False
+        self.side_streams = [torch.cuda.Stream() for _ in range(self.frames - 1)] if overlap_frames else None
         self.g_out = self.d_out = None
         self._patch = static_model_methods(mods)
         self.graph_g = self.graph_d = None
@@ -302,7 +322,7 @@ class GraphedFluidStep:
     # the two phases on the static buffers
     def _run_g(self):
         out, self.fakes, self.last_padded = generator_phase(self.mods, *self.nets, self.lowres, self.highres, self.fd, self.opt,
-                                                            self.n_iter_capture, self.og, self.rnd)
+                                                            self.n_iter_capture, self.og, self.rnd, self.side_streams)
         return out
 
     def _run_d(self):

@@ -204,7 +204,7 @@ def step(ctx: StepContext, n_iter: int = 12, freeze_D: bool = False) -> Dict[str
                                       os_, freeze_D=freeze_D)
 
 
-def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3):
+def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3, overlap_frames: bool = False):
     """The graph-capturable form of the fluid step (tpugan_b200.graph_step) over this context's networks, frames and
     (capturable) optimisers."""
     from tpugan_b200.graph_step import GraphedFluidStep
@@ -212,7 +212,7 @@ def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3):
     assert ctx.domain == "fluid"
     og, ot, os_ = ctx.optims
     return GraphedFluidStep(ctx.mods, ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, ctx.lo, ctx.hi, ctx.opt, (og, ot, os_),
-                            furthest_distance=1.0, warmup=warmup, capture=capture)
+                            furthest_distance=1.0, warmup=warmup, capture=capture, overlap_frames=overlap_frames)
 
 
 def snapshot(ctx: StepContext):
