@@ -50,6 +50,8 @@ _PROTOS = {
     "tpg_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),
     "tpg_fps_start_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "tpg_group_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "tpg_group_fwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "tpg_group_fwd_ws_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "tpg_inverse_index_workspace_bytes": (_Z, [_I, _I, _I]),
     "tpg_inverse_index_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_group_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),

@@ -295,7 +295,13 @@ def group_fwd(f, idx, center=None, _op: str = "group") -> torch.Tensor:
     rec = _log.begin(_op, f=f, idx=idx, center=center) if _log.on else None
     out = torch.empty((B, C, M, k), dtype=torch.float32, device=f.device)
     with _on_device(f.device):
-        _lib.call("tpg_group_fwd_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _stream())
+        nbytes = _lib.load().tpg_group_fwd_workspace_bytes(B, C, N, M, k)  # > 0: rows too long for shared memory
+        if nbytes:
+            ws = _ws(nbytes, f.device)
+            _lib.call("tpg_group_fwd_ws_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _ptr(ws), nbytes,
+                      _stream())
+        else:
+            _lib.call("tpg_group_fwd_f32", _ptr(f), _ptr(idx), _ptr(center), B, C, N, M, k, _ptr(out), _stream())
     if rec is not None:
         _log.end(rec, out=out)
     return out

@@ -456,6 +456,21 @@ def test_grouping_autograd_matches_oracle(F, oracle):
     np.testing.assert_array_equal(ft2.grad.cpu().numpy(), oracle.group_bwd(g2[..., None], gi[:, :, None], 200))
 
 
+@pytest.mark.parametrize("B,C,N,M,k,center", [(1, 64, 30000, 3000, 16, False), (2, 40, 25000, 1111, 7, True),
+                                               (1, 130, 65536, 700, 4, False), (1, 8, 40000, 500, 8, False)])
+def test_group_fwd_long_rows_point_major(F, oracle, B, C, N, M, k, center):
+    """rows that do not fit shared memory: point-major copy + contiguous channel-row gathers (C >= 16), else L2 gathers"""
+    from tpugan_b200 import _lib
+
+    assert (_lib.load().tpg_group_fwd_workspace_bytes(B, C, N, M, k) > 0) == (C >= 16)
+    rng = np.random.default_rng(N + k)
+    f = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, size=(B, M, k)).astype(np.int32)
+    cen = rng.standard_normal((B, C, M)).astype(np.float32) if center else None
+    out = F.group_fwd(cu(f), cu(idx), cu(cen) if center else None)
+    np.testing.assert_array_equal(out.cpu().numpy(), oracle.group_fwd(f, idx, cen))
+
+
 def test_inverse_index_one_key_repeated_more_than_65535_times(F, oracle):
     """a key that occurs > 65535 times in one cloud (all-zero padded / no-hit index lists) at N just above 2048:
     the single-CTA stable build must not wrap its per-key prefix (16-bit counters)"""
