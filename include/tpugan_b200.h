@@ -218,6 +218,13 @@ int tpg_group_bwd_segmented_f32(const float* grad_out, const int32_t* seg_offset
 int tpg_group_reduce_fwd_f32(const float* f, const int32_t* idx, int B, int C,
                              int N, int M, int k, int op, float* out,
                              int32_t* arg, tpg_stream_t stream);
+/* Rows that do not fit shared memory (N > 12800, C >= 8): with tpg_group_reduce_workspace_bytes() bytes of
+ * workspace the features are copied point-major and every neighbour is one coalesced channel-row read.
+ * `w` != NULL computes the weighted sum of three_interpolate (k = 3) instead of `op`.  Same results. */
+size_t tpg_group_reduce_workspace_bytes(int B, int C, int N);
+int tpg_group_reduce_fwd_ws_f32(const float* f, const int32_t* idx, const float* w, int B, int C,
+                                int N, int M, int k, int op, float* out, int32_t* arg,
+                                void* workspace, size_t workspace_bytes, tpg_stream_t stream);
 int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg,
                              const int32_t* seg_offsets,
                              const int32_t* seg_items, int B, int C, int N,

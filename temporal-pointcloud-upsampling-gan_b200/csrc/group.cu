@@ -260,6 +260,80 @@ __global__ void __launch_bounds__(RT_THREADS, 1) group_reduce_fwd_smem_kernel(Re
   }
 }
 
+// Fused gather + reduce for rows that do not fit shared memory (N > 12800): point-major features [B,N,C] (the
+// transposed copy of transpose_cn_kernel); one warp per output point, lanes over channels, so every neighbour costs one
+// or two coalesced 128-byte row reads; results of 32 points are staged in a [64][33] tile and written along m.
+struct ReduceFwdTArgs {
+  const float* ft;     // [B,N,C]
+  const int32_t* idx;  // [B,M,k]
+  const float* w;      // [B,M,k] or null
+  int B, C, N, M, k, op;
+  float* out;          // [B,C,M]
+  int32_t* arg;        // [B,C,M] or null
+};
+
+__global__ void __launch_bounds__(256) group_reduce_pointmajor_kernel(ReduceFwdTArgs a) {
+  __shared__ float tile_v[64][33];
+  __shared__ int tile_a[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, m0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ct = min(64, a.C - c0), mt = min(32, a.M - m0);
+  const float* fb = a.ft + (size_t)b * a.N * a.C + c0;
+  const bool h0 = lane < ct, h1 = lane + 32 < ct;
+  for (int p = warp * 4; p < warp * 4 + 4; ++p) {
+    if (p >= mt) break;  // (warp-uniform)
+    const int32_t* im = a.idx + ((size_t)b * a.M + m0 + p) * a.k;
+    const float* wm = a.w ? a.w + ((size_t)b * a.M + m0 + p) * a.k : nullptr;
+    float acc0 = 0.f, acc1 = 0.f;
+    int b0 = 0, b1 = 0;
+    for (int j0 = 0; j0 < a.k; j0 += 8) {
+      float v0[8], v1[8], wj[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        v0[u] = v1[u] = 0.f; wj[u] = 1.f;
+        if (j < a.k) {
+          const float* r = fb + (size_t)__ldg(im + j) * a.C;
+          if (h0) v0[u] = __ldg(r + lane);
+          if (h1) v1[u] = __ldg(r + lane + 32);
+          if (wm) wj[u] = __ldg(wm + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j >= a.k) break;
+        if (wm) {
+          const float t0 = __fmul_rn(wj[u], v0[u]), t1 = __fmul_rn(wj[u], v1[u]);
+          acc0 = j == 0 ? t0 : __fadd_rn(acc0, t0);
+          acc1 = j == 0 ? t1 : __fadd_rn(acc1, t1);
+        } else if (j == 0) {
+          acc0 = v0[u]; acc1 = v1[u];
+        } else if (a.op == TPG_REDUCE_MAX) {
+          if (v0[u] > acc0) { acc0 = v0[u]; b0 = j; }
+          if (v1[u] > acc1) { acc1 = v1[u]; b1 = j; }
+        } else if (a.op == TPG_REDUCE_MIN) {
+          if (v0[u] < acc0) { acc0 = v0[u]; b0 = j; }
+          if (v1[u] < acc1) { acc1 = v1[u]; b1 = j; }
+        } else {
+          acc0 = __fadd_rn(acc0, v0[u]); acc1 = __fadd_rn(acc1, v1[u]);
+        }
+      }
+    }
+    tile_v[lane][p] = acc0; tile_v[lane + 32][p] = acc1;
+    tile_a[lane][p] = b0; tile_a[lane + 32][p] = b1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ct * 32; e += 256) {
+    const int c = e >> 5, p = e & 31;
+    if (p < mt) {
+      const size_t o = ((size_t)b * a.C + c0 + c) * a.M + m0 + p;
+      a.out[o] = tile_v[c][p];
+      if (a.arg) a.arg[o] = tile_a[c][p];
+    }
+  }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(GRP_THREADS) group_reduce_fwd_kernel(ReduceFwdArgs a) {
   extern __shared__ float rows_s[];
@@ -886,6 +960,40 @@ static int launch_reduce_fwd(ReduceFwdArgs a, cudaStream_t st) {
   group_reduce_fwd_kernel<false><<<grid, GRP_THREADS, 0, st>>>(a);
   TPG_CHECK_LAUNCH("group_reduce_fwd_kernel");
   return TPG_OK;
+}
+
+// long rows: the widest shared-memory tile (4 channels) does not fit -> point-major gathers
+static bool reduce_wants_pointmajor(int C, int N) { return (size_t)4 * N * sizeof(float) > RT_SMEM_MAX && C >= 8; }
+
+static int launch_reduce_pointmajor(const float* f, const int32_t* idx, const float* w, int B, int C, int N, int M, int k,
+                                    int op, float* out, int32_t* arg, void* workspace, cudaStream_t st) {
+  TPG_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, TPG_EUNSUPPORTED, "group_reduce: B or C too large");
+  float* ft = reinterpret_cast<float*>(workspace);
+  transpose_cn_kernel<<<dim3(ceil_div(N, 32), ceil_div(C, 32), B), 256, 0, st>>>(f, C, N, ft);
+  TPG_CHECK_LAUNCH("transpose_cn_kernel");
+  ReduceFwdTArgs a{ft, idx, w, B, C, N, M, k, op, out, arg};
+  group_reduce_pointmajor_kernel<<<dim3(ceil_div(M, 32), ceil_div(C, 64), B), 256, 0, st>>>(a);
+  TPG_CHECK_LAUNCH("group_reduce_pointmajor_kernel");
+  return TPG_OK;
+}
+
+TPG_API size_t tpg_group_reduce_workspace_bytes(int B, int C, int N) {
+  return reduce_wants_pointmajor(C, N) ? sizeof(float) * (size_t)B * (size_t)C * (size_t)N : 0;
+}
+
+TPG_API int tpg_group_reduce_fwd_ws_f32(const float* f, const int32_t* idx, const float* w, int B, int C, int N, int M,
+                                        int k, int op, float* out, int32_t* arg, void* workspace,
+                                        size_t workspace_bytes, tpg_stream_t stream) {
+  TPG_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0 && k >= 1, TPG_EINVAL, "group_reduce_fwd: bad size");
+  TPG_REQUIRE(op >= 0 && op <= 2, TPG_EINVAL, "group_reduce_fwd: bad op %d", op);
+  if (B == 0 || C == 0 || M == 0) return TPG_OK;
+  TPG_REQUIRE(f && idx && out, TPG_EINVAL, "group_reduce_fwd: null pointer");
+  const size_t need = tpg_group_reduce_workspace_bytes(B, C, N);
+  if (need && workspace && workspace_bytes >= need)
+    return launch_reduce_pointmajor(f, idx, w, B, C, N, M, k, w ? TPG_REDUCE_SUM : op, out, (w || op == TPG_REDUCE_SUM) ? nullptr : arg,
+                                    workspace, as_stream(stream));
+  if (w) return tpg_three_interpolate_fwd_f32(f, idx, w, B, C, N, M, out, stream);
+  return tpg_group_reduce_fwd_f32(f, idx, B, C, N, M, k, op, out, arg, stream);
 }
 
 TPG_API int tpg_group_reduce_fwd_f32(const float* f, const int32_t* idx, int B, int C, int N, int M, int k,

@@ -58,6 +58,8 @@ _PROTOS = {
     "tpg_group_bwd_segments": (_I, [_I, _I, _I, _I]),
     "tpg_group_bwd_segmented_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "tpg_group_reduce_fwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "tpg_group_reduce_workspace_bytes": (_Z, [_I, _I, _I]),
+    "tpg_group_reduce_fwd_ws_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_group_reduce_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "tpg_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
     "tpg_three_nn_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),

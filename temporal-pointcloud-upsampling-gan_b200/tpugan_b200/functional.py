@@ -432,8 +432,10 @@ def group_reduce_fwd(f, idx, op: int = _lib.REDUCE_MAX, want_arg: bool = True):
     out = torch.empty((B, C, M), dtype=torch.float32, device=f.device)
     arg = torch.empty((B, C, M), dtype=torch.int32, device=f.device) if (want_arg and op != _lib.REDUCE_SUM) else None
     with _on_device(f.device):
-        _lib.call("tpg_group_reduce_fwd_f32", _ptr(f), _ptr(idx), B, C, N, M, k, int(op), _ptr(out), _ptr(arg),
-                  _stream())
+        nbytes = _lib.load().tpg_group_reduce_workspace_bytes(B, C, N)  # > 0: rows too long for shared memory
+        ws = _ws(nbytes, f.device) if nbytes else None
+        _lib.call("tpg_group_reduce_fwd_ws_f32", _ptr(f), _ptr(idx), None, B, C, N, M, k, int(op), _ptr(out), _ptr(arg),
+                  _ptr(ws), nbytes, _stream())
     if rec is not None:
         _log.end(rec, out=out, arg=arg)
     return out, arg
@@ -477,7 +479,10 @@ def three_interpolate_fwd(f, idx, w):
     rec = _log.begin("three_interpolate", f=f, idx=idx, w=w) if _log.on else None
     out = torch.empty((B, c, n), dtype=torch.float32, device=f.device)
     with _on_device(f.device):
-        _lib.call("tpg_three_interpolate_fwd_f32", _ptr(f), _ptr(idx), _ptr(w), B, c, m, n, _ptr(out), _stream())
+        nbytes = _lib.load().tpg_group_reduce_workspace_bytes(B, c, m)
+        ws = _ws(nbytes, f.device) if nbytes else None
+        _lib.call("tpg_group_reduce_fwd_ws_f32", _ptr(f), _ptr(idx), _ptr(w), B, c, m, n, 3, _lib.REDUCE_SUM, _ptr(out), None,
+                  _ptr(ws), nbytes, _stream())
     if rec is not None:
         _log.end(rec, out=out)
     return out

@@ -514,7 +514,9 @@ def test_group_bwd_long_rows_segmented_bit_exact(F, oracle, B, C, N, M, k, S):
     (1, 40, 8192, 1000, 32),   # long rows: 4-channel tiles, even k (padded list stride), ragged last tile
     (1, 130, 1024, 1500, 7),   # C not a multiple of the tile, odd k, M not a multiple of 512
     (2, 33, 300, 513, 1),      # k = 1
-    (1, 5, 60000, 700, 8),     # rows do not fit shared memory: global-gather path
+    (1, 5, 60000, 700, 8),     # rows do not fit shared memory, few channels: global-gather path
+    (1, 40, 20000, 900, 16),   # rows do not fit shared memory: point-major copy + coalesced channel-row reads
+    (1, 130, 65536, 300, 5),   # ... three channel tiles, ragged
 ])
 def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
     rng = np.random.default_rng(12)
@@ -533,7 +535,8 @@ def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
 
 
 # ----------------------------------------------------------------------------- three_nn / interpolate
-@pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2), (2, 3000, 2048), (1, 8192, 4096)])
+@pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2), (2, 3000, 2048), (1, 8192, 4096),
+                                   (1, 3000, 20000)])
 def test_three_nn_and_interpolate(F, oracle, B, n, m):
     rng = np.random.default_rng(13)
     unknown = synth.fluid_cloud(rng, B, n)
