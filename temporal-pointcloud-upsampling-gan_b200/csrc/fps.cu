@@ -349,8 +349,12 @@ static int fps_dispatch(const FpsArgs& a, cudaStream_t st) {
   }
   if (N <= FPS_REG_MAX) {
     // measured (tools/bench_fps.py, one-way exchange): a round is cheapest with 8 points per thread and as few
-    // CTAs per cloud as keep a CTA at <= 256 threads: 4 CTAs up to 8192 points (677 vs 867 ns/round with the
-    // former 8 x 256 x 4 layout), 8 beyond
+    // CTAs per cloud as keep a CTA at <= 256 threads (2048 points): 2 CTAs up to 4096 points, 4 up to 8192 (677 vs
+    // 867 ns/round with the former 8 x 256 x 4 layout), 8 beyond
+    if (N <= 4096) {  // 2 CTAs x 2048 points: 653 vs 726 ns/round with 4 CTAs
+      const int ppc = (ceil_div(N, 2) + 31) & ~31;
+      return fps_launch<8, 2, MODEB>(a, (ceil_div(ppc, 8) + 31) & ~31, st);
+    }
     if (N <= 8192) {
       const int ppc = (ceil_div(N, 4) + 31) & ~31;
       return fps_launch<8, 4, MODEB>(a, (ceil_div(ppc, 8) + 31) & ~31, st);
@@ -391,7 +395,7 @@ TPG_API int tpg_debug_fps_variant(const float* xyz, int B, int N, int npoint, in
 #define V(P, C) if (ppt == P && cl == C) return (flags & 2) ? fps_launch<P, C, false, false>(a, threads, st) : fps_launch<P, C, false>(a, threads, st)
   V(1, 1); V(2, 1); V(4, 1); V(8, 1); V(16, 1);
   V(1, 8); V(2, 8); V(4, 8); V(8, 8);
-  V(2, 4); V(4, 4); V(8, 4); V(4, 2); V(8, 2); V(16, 2);
+  V(2, 4); V(4, 4); V(8, 4); V(16, 4); V(4, 2); V(8, 2); V(16, 2); V(16, 8);
 #undef V
   set_error("fps variant ppt=%d cl=%d not built", ppt, cl);
   return TPG_EUNSUPPORTED;
