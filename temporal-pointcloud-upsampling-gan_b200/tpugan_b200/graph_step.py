@@ -26,7 +26,8 @@ unmodified networks** (``SRNet``, ``FluidSpatialDis``, ``FluidTempoDis`` and the
   instead, which changes tensor shapes and cannot be captured),
   ``_PointnetSAModuleBase.forward`` -> device-side dummy re-draw (stable compaction of the surviving FPS
   centres + a random draw without replacement from the allowed indices, all fixed-shape tensor ops with
-  the device generator), ``discriminator.ball_query_wrapper`` -> one kNN search (see reference_patches).
+  the device generator), ``discriminator.ball_query_wrapper`` -> one kNN search, ``IDGCNLayer.forward`` -> one
+  neighbour search per layer instead of three + fused gather+max (see reference_patches; identical results).
 
 Equality with the reference step (same seeds, no dummy points in the batch, so that the only random
 stream that cannot be shared — NumPy inside the re-draw loop — stays unused) is tested in
@@ -188,8 +189,9 @@ def index_points_static(points, idx):
 class static_model_methods:
     """Context manager: rebinds the synchronising functions / methods of the reference's modules."""
 
-    def __init__(self, mods: Optional[Dict[str, Any]] = None):
+    def __init__(self, mods: Optional[Dict[str, Any]] = None, fused_idgcn: bool = True):
         self.mods = mods or {}
+        self.fused_idgcn = fused_idgcn
         self._undo: List = []
 
     def _mod(self, name):
@@ -204,6 +206,13 @@ class static_model_methods:
                                (loss, "index_points", index_points_static)):
             self._undo.append((obj, name, getattr(obj, name)))
             setattr(obj, name, new)
+        if self.fused_idgcn:  # one kNN search per IDGCN layer instead of three + fused gather+max (identical results)
+            from .reference_patches import _idgcn_forward_fused
+
+            gcn = sys.modules.get("gcn_lib.pointnet.gcn")
+            if gcn is not None:
+                self._undo.append((gcn.IDGCNLayer, "forward", gcn.IDGCNLayer.forward))
+                gcn.IDGCNLayer.forward = _idgcn_forward_fused
         return self
 
     def __exit__(self, *exc):
@@ -298,7 +307,8 @@ class GraphedFluidStep:
     Optimisers must be capturable (``torch.optim.Adam(..., capturable=True)``)."""
 
     def __init__(self, mods, sr_net, spatial_dis, tempo_dis, lowres_pos_lst, highres_pos_lst, opt, optims,
-                 furthest_distance: float = 1.0, warmup: int = 3, capture: bool = True, overlap_frames: bool = False):
+                 furthest_distance: float = 1.0, warmup: int = 3, capture: bool = True, overlap_frames: bool = False,
+                 fused_idgcn: bool = True):
         self.mods, self.nets = mods, (sr_net, spatial_dis, tempo_dis)
         self.lowres = [t.clone() for t in lowres_pos_lst]
         self.highres = [t.clone() for t in highres_pos_lst]
@@ -314,7 +324,7 @@ class GraphedFluidStep:
         self.captured = False
         self.side_streams = [torch.cuda.Stream() for _ in range(self.frames - 1)] if overlap_frames else None
         self.g_out = self.d_out = None
-        self._patch = static_model_methods(mods)
+        self._patch = static_model_methods(mods, fused_idgcn=fused_idgcn)
         self.graph_g = self.graph_d = None
         if capture:
             self._capture(warmup)

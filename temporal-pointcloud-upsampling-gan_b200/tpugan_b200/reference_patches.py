@@ -11,9 +11,10 @@ reference site                                    rebound to
 ``discriminator.ball_query_wrapper`` (:24-40)     ``gcn_dense.ball_query_wrapper``: ONE kNN search —
   FRNN + kNN + boolean-mask fill                  the FRNN hits are a prefix of the kNN list in the
                                                   canonical order, so the filled list IS the kNN list
-``IDGCNLayer.forward`` (gcn.py:253-279)           same layer with the bottleneck's
-  grouping_operation + torch.max                  ``grouping -> max`` done by the fused gather+max
-                                                  kernel (K7; [B,C,N,9] never materialised)
+``IDGCNLayer.forward`` (gcn.py:253-279)           same layer with ONE kNN search (K = 20) instead of
+  three kNN searches on the same features,        three (K = 9 is its prefix, the dilated list every
+  grouping_operation + torch.max                  2nd entry) and the bottleneck's ``grouping -> max``
+                                                  done by the fused gather+max kernel (K7)
 ``gcn_lib.cubic_interpolation`` (:103-123)        ``interpolation.cubic_interpolation`` (K10; the
   FRNN x2 + DGL graph + SpMM per sample           reference's needs ``dgl``)
 ``train_step_final.interpolate_vel_lst`` (:51)    ``interpolation.interpolate_vel_lst``: one batched
@@ -33,22 +34,40 @@ import torch
 from . import gcn_dense, interpolation
 
 
+def _edgeconv_with_idx(conv, feat, knn_idx):
+    """EdgeConv.forward (gcn_lib/pointnet/gcn.py:195-212) on a neighbour list that was searched already: feat [B,C,N],
+    knn_idx int64 [B,N,k] (already dilated).  Same ops in the same order as the reference from the cast on."""
+    from pointnet2_ops.pointnet2_utils import grouping_operation
+
+    knn_idx = knn_idx.type(torch.int32).contiguous()
+    center_feat = feat.unsqueeze(-1)
+    grouped = grouping_operation(feat, knn_idx)
+    edge_feat = grouped - center_feat
+    out = conv.node_affine(grouped) + conv.edge_affine(edge_feat)
+    return conv.aggregate_fn(conv.mlp(out))
+
+
 def _idgcn_forward_fused(self, feature):
-    """IDGCNLayer.forward (gcn_lib/pointnet/gcn.py:253-279) with `grouping_operation` + `torch.max` of the
-    bottleneck branch replaced by the fused gather+max kernel.  Everything else is the layer's own code path."""
+    """IDGCNLayer.forward (gcn_lib/pointnet/gcn.py:253-279) with (a) ONE neighbour search instead of three — the layer
+    searches the same bottleneck features with K = 9 (:258), K = 20 (GCN1) and K = 20 dilated by 2 (GCN2, :264-265); in
+    the canonical (distance, index) order the K = 9 list is the prefix of the K = 20 list and the dilated list is every
+    second entry of it — and (b) `grouping_operation` + `torch.max` of the bottleneck branch done by the fused gather+max
+    kernel.  Everything else is the layer's own code path; results are identical."""
     from pytorch3d.ops import knn_points
 
     if self.residual:
         skip_connection = self.skip_layer(feature.clone())
     feature = self.btn(feature)
-    _, local_knn_idx, _ = knn_points(feature.squeeze(-1).permute(0, 2, 1).contiguous(),
-                                     feature.squeeze(-1).permute(0, 2, 1).contiguous(), K=9, return_nn=False,
-                                     return_sorted=True)
+    pts = feature.squeeze(-1).permute(0, 2, 1).contiguous()
+    k1, d1 = self.GCN1.dilated_knn_graph.k, self.GCN1.dilated_knn_graph.dilation
+    k2, d2 = self.GCN2.dilated_knn_graph.k, self.GCN2.dilated_knn_graph.dilation
+    kmax = max(9, k1, k2)
+    _, idx_all, _ = knn_points(pts, pts, K=kmax, return_nn=False, return_sorted=True)
     feature = feature.squeeze(-1).contiguous()
-    local_knn_idx = local_knn_idx.type(torch.int32).contiguous()
+    local_knn_idx = idx_all[:, :, :9].type(torch.int32).contiguous()
     local_max = gcn_dense.group_max(feature, local_knn_idx)  # [B, C//4, N, 1]
-    feat1 = self.GCN1(feature.squeeze(-1))
-    feat2 = self.GCN2(feature.squeeze(-1))
+    feat1 = _edgeconv_with_idx(self.GCN1, feature, idx_all[:, :, :k1][:, :, ::d1])
+    feat2 = _edgeconv_with_idx(self.GCN2, feature, idx_all[:, :, :k2][:, :, ::d2])
     feature = torch.cat([local_max, feat1, feat2], dim=1)
     feature = self.decoder(feature)
     if self.use_layernorm:

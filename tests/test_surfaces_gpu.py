@@ -316,7 +316,8 @@ def test_patch_reference_equals_unpatched(oracle):
         y2 = layer(x2)
         calls = log.stop()
         assert torch.equal(y2, y1)  # max over neighbours is exact: same values, no [B,C,N,9] tensor
-        assert verify_calls.counts(calls).get("group_reduce", 0) == 1
+        cnt = verify_calls.counts(calls)
+        assert cnt.get("group_reduce", 0) == 1 and cnt.get("knn", 0) == 1 and cnt.get("group", 0) == 2, cnt  # one search, not three
         verify_calls.check_log(oracle, calls)
         y2.square().sum().backward()
         close(x2.grad, x1.grad.cpu().numpy(), rtol=1e-4)
@@ -330,6 +331,7 @@ def test_patch_reference_equals_unpatched(oracle):
         assert all(np.isfinite(v) for v in losses.values())
         cnt = verify_calls.counts(calls)
         assert cnt["frnn"] == 2 and cnt["group_reduce"] == 6 and cnt["group_reduce_bwd"] == 6 and cnt["group"] == 99, cnt
+        assert cnt["knn"] == 42 - 12, cnt  # 2 IDGCN layers x 3 frames x 2 repeated searches saved
         verify_calls.check_log(oracle, calls)
     finally:
         h.unpatch()
