@@ -78,3 +78,60 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+# ---- the data-parallel harness of the reference's train step (tools/refstep.py::DataParallel) over gloo ---------------
+def _dp_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import refstep
+
+        torch.set_num_threads(2)
+        # different data per rank (seed), identical initial weights after the harness's broadcast
+        ctx = refstep.build("action", B=2, n_lo=64, ratio=16, backend="oracle", device="cpu", seed=1 + rank)
+        dp = refstep.DataParallel(ctx, sync_bn=False)
+        seen = {}
+        for name, net, optim in zip(("G", "tempoD", "spatialD"), ctx.networks(), ctx.optims):
+            params = [p for p in net.parameters() if p.requires_grad]
+            optim.register_step_pre_hook(lambda _o, _a, _k, name=name, params=params: seen.__setitem__(
+                name, torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None]).clone()))
+        np.random.seed(3)
+        torch.manual_seed(3)
+        losses = refstep.step(ctx, 12)
+        assert all(np.isfinite(v) for v in losses.values())
+        assert dp.bytes_per_step == 4 * sum(refstep.param_counts(ctx)), (dp.bytes_per_step, refstep.param_counts(ctx))
+        # every rank stepped its optimisers on the SAME (averaged) gradients and ends with the SAME weights
+        for name in ("G", "tempoD", "spatialD"):
+            g = seen[name]
+            gathered = [torch.empty_like(g) for _ in range(world)]
+            dist.all_gather(gathered, g)
+            assert all(torch.equal(gathered[0], x) for x in gathered), name
+        w = torch.cat([p.detach().reshape(-1) for p in ctx.sr_net.parameters()])
+        gathered = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(gathered, w)
+        assert torch.equal(gathered[0], gathered[1])
+        q.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+
+        q.put((rank, repr(e) + traceback.format_exc()[-800:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(ROOT, "baseline", "_ref", "train_step_final.py")) or
+                         os.path.isdir("/root/reference")), reason="reference not installed")
+def test_data_parallel_reference_step_over_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
