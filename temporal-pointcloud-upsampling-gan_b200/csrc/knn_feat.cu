@@ -9,8 +9,8 @@
 // (distances are translation-invariant; real network features carry a large common offset) and
 // every centred value is split into two bf16 terms, v ~ b1 + b2 (16 significand bits), stored as
 // rows [b1(0..D-1) | b2(0..D-1)] — the same bytes per row as the fp32 input.  <y,x> is then the
-// sum of the four bf16 x bf16 products b1b1 + b1b2 + b2b1 + b2b2 (tcgen05.mma kind::f16, bf16
-// inputs, exact products, fp32 accumulate in TMEM): ~2^-15 relative instead of the 2^-10 of a
+// sum of the bf16 x bf16 products b1b1 + b1b2 + b2b1 (b2b2 <= 2^-16 is dropped; tcgen05.mma kind::f16,
+// bf16 inputs, exact products, fp32 accumulate in TMEM): ~2^-15 relative instead of the 2^-10 of a
 // tf32 contraction.  (Measured on the generator's real activations, tools/dump_knn_inputs.py: a
 // plain tf32 contraction sends 77-98 % of the queries to the exact fallback, centring alone
 // 15-34 %, centring + split 0.0 %.)  e only SELECTS candidates; the neighbours that are
@@ -176,8 +176,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // rigorous bound on |e - (d_true - |x|^2)| + |d_canon - d_true|, with xs, ys the split
 // values (b1 + b2) of the centred rows x_c, y_c, xn = |xs|, yn = max |ys|, s = xn + yn:
-//   contraction: the 4D bf16 products are exact; fp32 accumulation inside the tensor core, taken as one
-//     truncation (2^-23) per product: |dot_tc - <xs,ys>| <= 4D 2^-23 xn yn, twice that in e;
+//   contraction: three of the four term pairings are issued (b1b1 + b1b2 + b2b1); the dropped b2*b2 is at most
+//     2^-16 xn yn (2^-15 in e).  The 3D bf16 products are exact; fp32 accumulation inside the tensor core, taken
+//     as one truncation (2^-23) per product: <= 3D 2^-23 xn yn, twice that in e;
 //   split: |xs - x_c| <= 2^-16 |x_c| per coordinate (two round-to-nearest bf16 steps), so
 //     |d(xs,ys) - d(x_c,y_c)| <= 2 s * 2^-16 s (+ second order) = 2^-15 s^2;
 //   centring (relative 2^-24 per coordinate), fp32 roundings of the norms, of e and of the canonical sum:
@@ -185,7 +186,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ float feat_eps(float nq, float nmax, int D) {
   const float xn = sqrtf(nq) * 1.001f, yn = sqrtf(nmax) * 1.001f;
   const float s = xn + yn;
-  return 1.25f * ((float)(8 * D) * 1.1920929e-7f * xn * yn + (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
+  return 1.25f * (((float)(6 * D) * 1.1920929e-7f + 3.0517578e-5f) * xn * yn +
+                  (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
 }
 
 // Upper end of the 16-bit radix bucket that holds the k-th smallest (1-based) of the values a
@@ -432,13 +434,17 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     // <y,x> = sum over the four (y term, x term) pairings, all accumulated into one TMEM tile.
     const int h = D >> 4;
     auto koff = [&](int kk) { return (uint64_t)(((uint32_t)(kk >> 2) * atomA + (uint32_t)(kk & 3) * 32u) >> 4); };
+    // three of the four pairings: b2*b2 (<= 2^-16 |x||y|, accounted for in feat_eps) is not worth a quarter of the
+    // tensor-pipe time — with K = 16 per instruction every MMA re-reads both 4 KB operand slices from shared memory
+    // and the issuer measures ~270 cycles per MMA (TPG_KNN_DBG), i.e. the contraction is smem-bandwidth-bound
     uint32_t accum = 0u;
-    for (int ta = 0; ta < 2; ++ta)
-      for (int tb = 0; tb < 2; ++tb)
-        for (int kk = 0; kk < h; ++kk) {
-          umma_bf16(td, ad0 + koff(ta * h + kk), bd0 + koff(tb * h + kk), accum);  // atomA == atomB (128 rows x 128 B)
-          accum = 1u;
-        }
+    for (int pr = 0; pr < 3; ++pr) {
+      const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+      for (int kk = 0; kk < h; ++kk) {
+        umma_bf16(td, ad0 + koff(ta * h + kk), bd0 + koff(tb * h + kk), accum);  // atomA == atomB (128 rows x 128 B)
+        accum = 1u;
+      }
+    }
     umma_commit(smem_u32(&mbar_s[s]));
   };
   if (warp == FT_THREADS / 32 + 1) {
