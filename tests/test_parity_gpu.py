@@ -765,3 +765,20 @@ def test_knn_tensor_core_offset_features_stay_on_tensor_cores(F, oracle):
     np.testing.assert_array_equal(gi.cpu().numpy(), oi)
     np.testing.assert_array_equal(gd.cpu().numpy(), od)
     assert fb <= 0.02 * 2 * 2048, fb
+
+
+def test_nearest_neighbour_queries_far_outside_the_candidate_box(F, oracle):
+    """an untrained generator spreads its output over 2x the extent of the ground truth: about half of the Chamfer
+    queries lie outside the other cloud's grid (warp-cooperative wide search of grid_nn1_kernel)"""
+    rng = np.random.default_rng(41)
+    gt = synth.fluid_cloud(rng, 2, 8192)
+    pred = (2.2 * synth.fluid_cloud(rng, 2, 8192) + np.array([0.05, -0.02, 0.1], np.float32)).astype(np.float32)
+    pred[0, :50] += 3.0  # a few very far points
+    r = F.chamfer_fwd(cu(gt), cu(pred), 3)
+    o = oracle.chamfer_fwd(gt, pred, 3)
+    for k in ("i_src", "i_tgt", "d_src", "d_tgt"):
+        np.testing.assert_array_equal(r[k].cpu().numpy(), o[k])
+    od, oi = oracle.knn(pred, gt, 1)
+    gd, gi = F.knn(cu(pred), cu(gt), 1)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), od)
