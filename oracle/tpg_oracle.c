@@ -300,6 +300,11 @@ ORC_API void orc_group_reduce_bwd(const float* grad_out, const int32_t* idx,
 
 /* ------------------------------------------------------------------------
  * three_nn / three_interpolate (pointnet2_ops, upstream; north_star surface)
+ * Stated deviation: with fewer than 3 known points (m < 3) the unused slots are
+ * dist 0 / idx 0 here (and in the CUDA kernel), where upstream's kernel leaves
+ * its 1e40 initial value (-> sqrt = inf) / idx 0.  Upstream never calls it that
+ * way (feature propagation needs >= 3 known points); finite padding keeps the
+ * 1 / (dist + eps) weights of the usual caller finite.
  * ---------------------------------------------------------------------- */
 ORC_API void orc_three_nn(const float* unknown, const float* known, int B, int n,
                           int m, float* dist, int32_t* idx) {
