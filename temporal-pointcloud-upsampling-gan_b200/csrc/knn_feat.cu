@@ -244,15 +244,21 @@ __device__ __forceinline__ float ordered_key_inv(unsigned uk) {
 
 // ---- pre-pass: per-cloud mean, centred bf16 x 2 split, squared norms, per-cloud max norm ----------------------
 constexpr int FT_MEAN_CHUNKS = 16;
+constexpr int FT_SPLIT_ITERS = 4;  // row groups per CTA of feat_split_kernel (amortises the mean prologue)
 
 // partial column sums of cloud b over rows [chunk * rows_per, ...) below its length: part[b][chunk][D]
 // (fixed summation order: the centre is deterministic; any centre would be CORRECT, it only sets the margins)
 __global__ void __launch_bounds__(256) feat_mean_partial_kernel(const float* __restrict__ p, const int64_t* __restrict__ len,
                                                                 int P, int D, float* __restrict__ part,
+                                                                unsigned* __restrict__ nmax, int* __restrict__ fb_count,
                                                                 const int32_t* __restrict__ skip) {
   __shared__ float red_s[256];
   if (skip && *skip) return;
   const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  if (chunk == 0 && tid == 0) {  // (replaces a memset node) consumed by the kernels launched after this one
+    nmax[b] = 0u;
+    if (b == 0) *fb_count = 0;
+  }
   const int n = len ? min((int)len[b], P) : P;
   const int rows_per = (P + FT_MEAN_CHUNKS - 1) / FT_MEAN_CHUNKS;
   const int r0 = chunk * rows_per, r1 = min(n, r0 + rows_per);
@@ -284,8 +290,10 @@ __global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict
     mean_s[tid] = n > 0 ? t / (float)n : 0.0f;
   }
   __syncthreads();
-  const int lpr = D >> 2, rows_per_cta = 256 / lpr;
-  const int row = blockIdx.x * rows_per_cta + tid / lpr, ch = tid % lpr;
+  const int lpr = D >> 2, rows_per_it = 256 / lpr, ch = tid % lpr;
+  unsigned mloc = 0u;
+  for (int it = 0; it < FT_SPLIT_ITERS; ++it) {
+  const int row = (blockIdx.x * FT_SPLIT_ITERS + it) * rows_per_it + tid / lpr;
   float s = 0.0f;
   if (row < P) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p + ((size_t)b * P + row) * D) + ch);
@@ -308,11 +316,13 @@ __global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict
   // sum over the row's lanes (lpr = 8 or 16 consecutive lanes)
   for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
   if (row < P && ch == 0) nrm[(size_t)b * P + row] = s;
+  // rows beyond the cloud's length never become candidates; non-finite norms (inf / NaN inputs) must poison
+  // the bound, not vanish in the integer max: NaN -> +inf
+  const float sm = (row < n) ? ((s == s) ? s : __int_as_float(0x7f800000)) : 0.0f;
+  mloc = max(mloc, __float_as_uint(sm));  // s >= 0: bit order == value order
+  }
   if (nmax) {
-    // rows beyond the cloud's length never become candidates; non-finite norms (inf / NaN inputs) must poison
-    // the bound, not vanish in the integer max: NaN -> +inf
-    const float sm = (row < n) ? ((s == s) ? s : __int_as_float(0x7f800000)) : 0.0f;
-    unsigned m = __reduce_max_sync(FULL, __float_as_uint(sm));  // s >= 0: bit order == value order
+    const unsigned m = __reduce_max_sync(FULL, mloc);
     if ((tid & 31) == 0) atomicMax(nmax + b, m);
   }
 }
@@ -896,12 +906,12 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, TPG_EWORKSPACE,
               "knn: workspace must be 256-byte aligned for the tensor-core path");
   FeatWs w = feat_carve(workspace, k.B, k.P1, k.P2, k.D);
-  TPG_CUDA(cudaMemsetAsync(w.nmax2, 0, (size_t)((char*)w.nrm1 - (char*)w.nmax2), st));  // nmax2 + fb_count
   {
     // centre = mean of the candidate cloud (rows below its length); both operands are shifted by it
-    feat_mean_partial_kernel<<<dim3(FT_MEAN_CHUNKS, k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.D, w.part, k.skip);
+    feat_mean_partial_kernel<<<dim3(FT_MEAN_CHUNKS, k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.D, w.part, w.nmax2, w.fb_count,
+                                                                         k.skip);
     TPG_CHECK_LAUNCH("feat_mean_partial_kernel");
-    const int rows_per_cta = 256 / (k.D >> 2);
+    const int rows_per_cta = FT_SPLIT_ITERS * 256 / (k.D >> 2);
     feat_split_kernel<<<dim3(ceil_div(k.P2, rows_per_cta), k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.P2, k.D, w.part,
                                                                               w.split2, w.nrm2, w.nmax2, k.skip);
     TPG_CHECK_LAUNCH("feat_split_kernel");
