@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 8
+#define TPG_ABI_VERSION 9
 
 typedef void* tpg_stream_t; /* cudaStream_t */
 
@@ -230,6 +230,47 @@ int tpg_group_reduce_bwd_f32(const float* grad_out, const int32_t* arg,
                              const int32_t* seg_items, int B, int C, int N,
                              int M, int k, int op, float* grad_f,
                              tpg_stream_t stream);
+
+/* ---- K11: conv-input assembly around the grouping ---------------------------
+ * replaces, in one pass and without the per-tensor [B,C_p,M,k] intermediates and the torch.cat copy,
+ *   pointnet2_utils.QueryAndGroup.forward — discriminator.py:190:
+ *       cat([xyz[idx] - new_xyz, features[idx]], dim=1)
+ *   FlowEmbedding.forward — discriminator.py:270-277:
+ *       cat([pos2[idx] - pos1, feat2[idx], feat1.view(B,-1,N,1).repeat(1,1,1,k)], dim=1)
+ * out [B, sum_p C_p, M, k]; part p fills the channel range after the parts before it:
+ *   TPG_PART_GATHER     out[b,c,m,j] = src[b,c,idx[b,m,j]] (- center[b,c,m] if center != NULL); src [B,C,N]
+ *   TPG_PART_BROADCAST  out[b,c,m,j] = src[b,c,m];  src [B,C,M], center must be NULL, N ignored
+ * `parts` is a HOST array (1..TPG_ASSEMBLE_MAX_PARTS entries) of device pointers; idx [B,M,k] int32.
+ * Values are exact copies / single fp32 subtractions: identical to the unfused composition.           */
+#define TPG_ASSEMBLE_MAX_PARTS 4
+enum { TPG_PART_GATHER = 0, TPG_PART_BROADCAST = 1 };
+typedef struct tpg_assemble_part {
+  const float* src;
+  const float* center;
+  int C;
+  int N;
+  int mode;
+} tpg_assemble_part;
+int tpg_group_assemble_f32(const tpg_assemble_part* parts, int nparts, const int32_t* idx,
+                           int B, int M, int k, float* out, tpg_stream_t stream);
+
+/* ---- K12: EdgeConv pre-activation after the algebraic restructure -----------
+ * replaces the k-expanded front half of EdgeConv.forward — gcn_lib/pointnet/gcn.py:206-211:
+ *       feat = grouping_operation(feat, idx); edge = feat - center
+ *       feat = node_affine(feat) + edge_affine(edge)          (1x1 conv + LeakyReLU each, no norm layer)
+ * With the two 1x1 convolutions applied per NODE — p = LeakyReLU(W_n f + b_n), q = W_e f + b_e, both [B,C,N] —
+ *       out[b,c,m,j] = p[b,c,i] + LeakyReLU(q[b,c,i] - center[b,c,m]),  i = idx[b,m,j],  center = q_m - b_e
+ * (W(f_j - f_i) = W f_j - W f_i: k times fewer convolution columns, no [B,C,N,k] intermediates; rounding
+ * differs from the reference's order of operations by a few ulp, tests bound it by 1e-5 relative).
+ * Backward: tpg_edge_affine_bwd_f32 writes g2 = grad_out * LeakyReLU'(q[i] - center) ([B,C,M,k]) and, if
+ * grad_center != NULL, grad_center[b,c,m] = -sum_j g2 (sequential in j); grad_p and grad_q are the ordinary
+ * grouping backwards of grad_out and g2 (tpg_group_bwd_f32 over the shared inverse index).            */
+int tpg_edge_affine_fwd_f32(const float* p, const float* q, const float* center, const int32_t* idx,
+                            float slope, int B, int C, int N, int M, int k, float* out,
+                            tpg_stream_t stream);
+int tpg_edge_affine_bwd_f32(const float* grad_out, const float* q, const float* center,
+                            const int32_t* idx, float slope, int B, int C, int N, int M, int k,
+                            float* g2, float* grad_center, tpg_stream_t stream);
 
 /* ---- K8: three_nn / three_interpolate -------------------------------------
  * replaces pointnet2_utils.three_nn(unknown, known) and

@@ -349,6 +349,15 @@ __global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict
 // T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset (else -> fallback);
 // (F2) all threads evaluate the canonical distance of the (query, candidate) pairs; (F3) per
 // query, rank by (d_canon, idx) and write the K best.
+// one lane of a converged warp (elect.sync): the branch it guards stays warp-uniform for the compiler, so the
+// operands of the tcgen05 / TMA instructions inside live in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int DD>
 __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, const __grid_constant__ FeatMaps maps) {
   extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
   __shared__ __align__(8) uint64_t mbar_s[FT_NBUF];       // MMA(u) done (tcgen05.commit), per TMEM buffer
@@ -361,11 +370,13 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   __shared__ int cnt_s[FT_NQ];
 
   if (a.skip && *a.skip) return;  // (uniform) memoised call: nothing to do, nothing allocated yet
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULL, tid >> 5, 0);  // warp-uniform for the compiler too (role branches, uniform registers)
   const int quarter = warp & 3, colgrp = warp >> 2;
   const int nq0 = colgrp * FT_QW;  // first query (column) of this warp
   const int b = blockIdx.y, q0 = blockIdx.x * FT_NQ;
-  const int D = a.D, K = a.K;
+  constexpr int D = DD;
+  const int K = a.K;
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
   const int n2 = a.len2 ? min((int)a.len2[b], a.P2) : a.P2;
   const float INF = __int_as_float(0x7f800000);
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   const uint32_t atomA = 128u * 128u;                // one 32-float K-slab of a stage
   const uint32_t qtile = base + (uint32_t)FT_STAGES * stage_bytes;
   const uint32_t atomB = (uint32_t)FT_NQ * 128u;
-  const int cpr = D >> 2;                            // 16-byte chunks per row: 8, 16 or 32
+  constexpr int cpr = D >> 2;                        // 16-byte chunks per row: 8 or 16
   const int T = (n2 + FT_TM - 1) / FT_TM;
 
   const float* p2b = a.p2 + (size_t)b * a.P2 * D;
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 
   // candidate tile t -> smem stage: one TMA box per 32-float K-slab, issued by ONE thread; rows of
   // the next cloud that ride along in a ragged last tile are masked by their +inf norm
-  const int slabs = D >> 5;
+  constexpr int slabs = D >> 5;
   auto load_tile = [&](int t, int stage) {
     const uint32_t bar = smem_u32(&full_s[stage]);
     mbar_expect_tx(bar, stage_bytes);
@@ -430,7 +441,12 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     for (int u0 = 0; u0 < FT_STAGES && u0 < U; ++u0) load_tile(u0 % T, u0);
   }
 
-  // MMA(u): needs tile u in smem and TMEM buffer u % 4 drained by the epilogue of u - 4
+  // MMA(u): needs tile u in smem and TMEM buffer u % 4 drained by the epilogue of u - 4.  Run by ALL lanes of the
+  // issuer warp in warp-uniform control flow (descriptors stay in uniform registers: a one-lane branch made the
+  // compiler move every operand through an ELECT / R2UR loop, ~33 dependent instructions and ~295 cycles per
+  // MMA — the issue, not the tensor pipe, bounded both passes); one elected lane issues.
+  constexpr int KH = D >> 4;  // K-steps (16 bf16 = 32 bytes) per term: a row = [b1: KH steps | b2: KH steps]
+  auto koff = [](int kk) -> uint64_t { return (uint64_t)(((uint32_t)(kk >> 2) * (128u * 128u) + (uint32_t)(kk & 3) * 32u) >> 4); };
   auto issue_mma = [&](int u) {
     const int s = u % FT_NBUF;  // TMEM buffer / mbarrier
     mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
@@ -440,57 +456,49 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     // descriptors differ from their stage base only in the 14-bit start-address field (>> 4)
     const uint64_t ad0 = umma_desc_sw128(base + (uint32_t)(u % FT_STAGES) * stage_bytes);
     const uint64_t bd0 = umma_desc_sw128(qtile);
-    // a row holds D/8 32-byte K-steps (16 bf16 each): steps [0, h) = b1, [h, 2h) = b2, h = D/16.
-    // <y,x> = sum over the four (y term, x term) pairings, all accumulated into one TMEM tile.
-    const int h = D >> 4;
-    auto koff = [&](int kk) { return (uint64_t)(((uint32_t)(kk >> 2) * atomA + (uint32_t)(kk & 3) * 32u) >> 4); };
-    // three of the four pairings: b2*b2 (<= 2^-16 |x||y|, accounted for in feat_eps) is not worth a quarter of the
-    // tensor-pipe time — with K = 16 per instruction every MMA re-reads both 4 KB operand slices from shared memory
-    // and the issuer measures ~270 cycles per MMA (TPG_KNN_DBG), i.e. the contraction is smem-bandwidth-bound
-    uint32_t accum = 0u;
-    for (int pr = 0; pr < 3; ++pr) {
-      const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-      for (int kk = 0; kk < h; ++kk) {
-        umma_bf16(td, ad0 + koff(ta * h + kk), bd0 + koff(tb * h + kk), accum);  // atomA == atomB (128 rows x 128 B)
-        accum = 1u;
+    if (elect_one()) {
+      // <y,x> ~ b1b1 + b1b2 + b2b1, all accumulated into one TMEM tile; b2*b2 (<= 2^-16 |x||y|, accounted for in
+      // feat_eps) is not worth a quarter of the tensor-pipe time
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk)
+          umma_bf16(td, ad0 + koff(ta * KH + kk), bd0 + koff(tb * KH + kk), (pr | kk) ? 1u : 0u);  // atomA == atomB
       }
+      umma_commit(smem_u32(&mbar_s[s]));
     }
-    umma_commit(smem_u32(&mbar_s[s]));
+    __syncwarp();
   };
   if (warp == FT_THREADS / 32 + 1) {
     // ===== TMA-producer warp: refills a stage the moment the MMA that read it has completed =====
-    if (lane == 0) {
-      for (int u = 0; u + FT_STAGES < U; ++u) {
-        mbar_wait(smem_u32(&mbar_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF) & 1));
-        load_tile((u + FT_STAGES) % T, u % FT_STAGES);
-      }
+    for (int u = 0; u + FT_STAGES < U; ++u) {
+      mbar_wait(smem_u32(&mbar_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF) & 1));
+      if (elect_one()) load_tile((u + FT_STAGES) % T, u % FT_STAGES);
+      __syncwarp();
     }
-    __syncwarp();
     __syncthreads();
     return;
   }
   if (warp == FT_THREADS / 32) {
-    // ===== MMA-issuer warp: one thread feeds the tensor pipe as fast as tiles land and accumulators
-    //       drain; it does no epilogue work, so issue never waits behind this warp's own share =====
-    if (lane == 0) {
-      mbar_wait(smem_u32(&qfull_s), 0u);
-      if (dbg) {  // tuning: where the issuer's time goes (tools/bench_knn_feat.py)
-        long long tf = 0, tt = 0, ti = 0;
-        for (int u = 0; u < U; ++u) {
-          const long long c0 = clock64();
-          mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
-          const long long c1 = clock64();
-          if (u >= FT_NBUF) mbar_wait(smem_u32(&tfree_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF - 1) & 1));
-          const long long c2 = clock64();
-          issue_mma(u);
-          tf += c1 - c0; tt += c2 - c1; ti += clock64() - c2;
-        }
-        dbg[8] = tf; dbg[9] = tt; dbg[10] = ti;
-      } else {
-        for (int u = 0; u < U; ++u) issue_mma(u);
+    // ===== MMA-issuer warp: feeds the tensor pipe as fast as tiles land and accumulators drain; it does no
+    //       epilogue work, so issue never waits behind this warp's own share =====
+    mbar_wait(smem_u32(&qfull_s), 0u);
+    if (dbg) {  // tuning: where the issuer's time goes (tools/bench_knn_feat.py)
+      long long tf = 0, tt = 0, ti = 0;
+      for (int u = 0; u < U; ++u) {
+        const long long c0 = clock64();
+        mbar_wait(smem_u32(&full_s[u % FT_STAGES]), (uint32_t)((u / FT_STAGES) & 1));
+        const long long c1 = clock64();
+        if (u >= FT_NBUF) mbar_wait(smem_u32(&tfree_s[u % FT_NBUF]), (uint32_t)((u / FT_NBUF - 1) & 1));
+        const long long c2 = clock64();
+        issue_mma(u);
+        tf += c1 - c0; tt += c2 - c1; ti += clock64() - c2;
       }
+      if (lane == 0) { dbg[8] = tf; dbg[9] = tt; dbg[10] = ti; }
+    } else {
+      for (int u = 0; u < U; ++u) issue_mma(u);
     }
-    __syncwarp();
     __syncthreads();  // joins the epilogue warps before the TMEM dealloc
     return;
   }
@@ -928,13 +936,14 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
              k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr, k.skip};
   const size_t aux = max((size_t)FT_NQ * 64 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
   const size_t smem = (size_t)k.D * 512 * FT_STAGES + (size_t)k.D * 4 * FT_NQ + 1024 + aux;
-  TPG_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = k.D == 32 ? knn_feat_tc_kernel<32> : knn_feat_tc_kernel<64>;
+  TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k.P1, FT_NQ), k.B);
   FeatMaps maps;
   TPG_REQUIRE(make_feat_map(&maps.cand, reinterpret_cast<const float*>(w.split2), (long long)k.B * k.P2, k.D) &&
                   make_feat_map(&maps.query, reinterpret_cast<const float*>(w.split1), (long long)k.B * k.P1, k.D),
               TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
-  knn_feat_tc_kernel<<<grid, FT_BLOCK, smem, st>>>(a, maps);
+  kern<<<grid, FT_BLOCK, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
   if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms(), 512, 0, st>>>(a);
   else knn_feat_fallback_kernel<16><<<num_sms(), 512, 0, st>>>(a);

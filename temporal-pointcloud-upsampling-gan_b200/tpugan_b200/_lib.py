@@ -14,10 +14,17 @@ LIB_NAME = "libtpugan_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 TPG_OK = 0
-ABI_VERSION = 8
+ABI_VERSION = 9
 TPG_EINVAL, TPG_EUNSUPPORTED, TPG_ECUDA, TPG_EWORKSPACE = -1, -2, -3, -4
 REDUCE_MAX, REDUCE_SUM, REDUCE_MIN = 0, 1, 2
 CHAMFER_FWD, CHAMFER_REV, CHAMFER_BOTH = 1, 2, 3
+PART_GATHER, PART_BROADCAST = 0, 1
+ASSEMBLE_MAX_PARTS = 4
+
+
+class AssemblePart(ctypes.Structure):
+    """struct tpg_assemble_part (include/tpugan_b200.h)."""
+    _fields_ = [("src", c_void_p), ("center", c_void_p), ("C", c_int), ("N", c_int), ("mode", c_int)]
 
 
 class TpgError(RuntimeError):
@@ -61,6 +68,9 @@ _PROTOS = {
     "tpg_group_reduce_workspace_bytes": (_Z, [_I, _I, _I]),
     "tpg_group_reduce_fwd_ws_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_group_reduce_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "tpg_group_assemble_f32": (_I, [_P, _I, _P, _I, _I, _I, _P, _P]),
+    "tpg_edge_affine_fwd_f32": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P]),
+    "tpg_edge_affine_bwd_f32": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
     "tpg_three_nn_workspace_bytes": (_Z, [_I, _I, _I]),
     "tpg_three_nn_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "tpg_three_interpolate_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),

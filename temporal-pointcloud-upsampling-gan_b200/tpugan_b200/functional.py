@@ -451,6 +451,82 @@ def group_reduce_bwd(grad_out, arg, off, items, N: int, k: int, op: int) -> torc
     return gf
 
 
+# --------------------------------------------------------------------------- conv-input assembly (K11 / K12)
+def group_assemble(parts, idx) -> torch.Tensor:
+    """One-pass assembly of a concatenated conv input (include/tpugan_b200.h: tpg_group_assemble_f32).
+    parts: sequence of ("gather", src [B,C,N], center [B,C,M] or None) / ("broadcast", src [B,C,M], None);
+    idx int32 [B,M,k] -> [B, sum C, M, k]."""
+    _req(idx, "idx", torch.int32, 3)
+    B, M, k = idx.shape
+    if not 1 <= len(parts) <= _lib.ASSEMBLE_MAX_PARTS:
+        raise RuntimeError(f"group_assemble: 1..{_lib.ASSEMBLE_MAX_PARTS} parts")
+    arr = (_lib.AssemblePart * len(parts))()
+    ctot = 0
+    for n, (mode, src, center) in enumerate(parts):
+        _req(src, f"part {n} source", torch.float32, 3)
+        if src.shape[0] != B or src.device != idx.device:
+            raise RuntimeError("group_assemble: batch / device mismatch between a part and idx")
+        C = src.shape[1]
+        if mode == "gather":
+            if center is not None:
+                _req(center, f"part {n} center", torch.float32, 3)
+                if tuple(center.shape) != (B, C, M):
+                    raise RuntimeError("group_assemble: center must be [B,C,M]")
+            arr[n] = _lib.AssemblePart(src.data_ptr(), center.data_ptr() if center is not None else None, C,
+                                       src.shape[2], _lib.PART_GATHER)
+        elif mode == "broadcast":
+            if src.shape[2] != M or center is not None:
+                raise RuntimeError("group_assemble: a broadcast part is [B,C,M] and takes no center")
+            arr[n] = _lib.AssemblePart(src.data_ptr(), None, C, 0, _lib.PART_BROADCAST)
+        else:
+            raise RuntimeError(f"group_assemble: unknown part mode {mode!r}")
+        ctot += C
+    rec = _log.begin("group_assemble", idx=idx, modes=[p[0] for p in parts], srcs=[p[1] for p in parts],
+                     centers=[p[2] for p in parts]) if _log.on else None
+    out = torch.empty((B, ctot, M, k), dtype=torch.float32, device=idx.device)
+    with _on_device(idx.device):
+        _lib.call("tpg_group_assemble_f32", ctypes.cast(arr, _vp), len(parts), _ptr(idx), B, M, k, _ptr(out), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
+    return out
+
+
+def edge_affine_fwd(p, q, center, idx, slope: float) -> torch.Tensor:
+    """out[b,c,m,j] = p[b,c,i] + LeakyReLU_slope(q[b,c,i] - center[b,c,m]), i = idx[b,m,j]  (tpg_edge_affine_fwd_f32)."""
+    _req(p, "p", torch.float32, 3)
+    _req(q, "q", torch.float32, 3)
+    _req(center, "center", torch.float32, 3)
+    _req(idx, "idx", torch.int32, 3)
+    B, C, N = q.shape
+    _, M, k = idx.shape
+    if tuple(p.shape) != (B, C, N) or tuple(center.shape) != (B, C, M) or idx.shape[0] != B:
+        raise RuntimeError("edge_affine: p, q must be [B,C,N], center [B,C,M], idx [B,M,k]")
+    rec = _log.begin("edge_affine", p=p, q=q, center=center, idx=idx, slope=float(slope)) if _log.on else None
+    out = torch.empty((B, C, M, k), dtype=torch.float32, device=q.device)
+    with _on_device(q.device):
+        _lib.call("tpg_edge_affine_fwd_f32", _ptr(p), _ptr(q), _ptr(center), _ptr(idx), float(slope), B, C, N, M, k,
+                  _ptr(out), _stream())
+    if rec is not None:
+        _log.end(rec, out=out)
+    return out
+
+
+def edge_affine_bwd(grad_out, q, center, idx, slope: float, want_center: bool = True):
+    """-> (g2 [B,C,M,k] = grad_out * LeakyReLU'(q[i] - center), grad_center [B,C,M] = -sum_j g2 or None)."""
+    _req(grad_out, "grad_out", torch.float32, 4)
+    B, C, N = q.shape
+    _, M, k = idx.shape
+    rec = _log.begin("edge_affine_bwd", grad_out=grad_out, q=q, center=center, idx=idx, slope=float(slope)) if _log.on else None
+    g2 = torch.empty((B, C, M, k), dtype=torch.float32, device=q.device)
+    gc = torch.empty((B, C, M), dtype=torch.float32, device=q.device) if want_center else None
+    with _on_device(q.device):
+        _lib.call("tpg_edge_affine_bwd_f32", _ptr(grad_out), _ptr(q), _ptr(center), _ptr(idx), float(slope), B, C, N, M, k,
+                  _ptr(g2), _ptr(gc), _stream())
+    if rec is not None:
+        _log.end(rec, g2=g2, grad_center=gc)
+    return g2, gc
+
+
 # --------------------------------------------------------------------------- three_nn / interpolate
 def three_nn(unknown, known):
     _req(unknown, "unknown", torch.float32, 3)
@@ -727,6 +803,77 @@ class GroupReduce(torch.autograd.Function):
         if rec is not None:
             _log.end(rec, grad_f=gf)
         return gf, None, None
+
+
+class GroupAssemble(torch.autograd.Function):
+    """cat of gathered (optionally centre-subtracted) and broadcast parts in one pass (K11):
+    QueryAndGroup (discriminator.py:190) and FlowEmbedding's conv input (discriminator.py:270-277).
+    apply(idx, modes, *tensors) with tensors = (src_0, center_0, src_1, center_1, ...), center None where unused."""
+
+    @staticmethod
+    def forward(ctx, idx, modes, *tensors):
+        parts = [(m, tensors[2 * n], tensors[2 * n + 1]) for n, m in enumerate(modes)]
+        ctx.modes = tuple(modes)
+        ctx.shapes = [(p[1].shape[1], p[1].shape[2]) for p in parts]
+        ctx.has_center = [p[2] is not None for p in parts]
+        ctx.save_for_backward(idx)
+        if csr_cache.prefetch_enabled:
+            for m, src, _ in parts:
+                if m == "gather" and src.requires_grad:
+                    csr_cache.prefetch(idx, src.shape[2])
+        return group_assemble(parts, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grads = []
+        c0 = 0
+        for n, mode in enumerate(ctx.modes):
+            C, N = ctx.shapes[n]
+            g = grad_out[:, c0:c0 + C]
+            c0 += C
+            gs = gc = None
+            if mode == "gather":
+                if ctx.needs_input_grad[2 + 2 * n]:
+                    gcont = g.contiguous()
+                    rec = _log.begin("group_bwd", grad_out=gcont, idx=idx, N=N) if _log.on else None
+                    gs = group_bwd_auto(gcont, idx, N)
+                    if rec is not None:
+                        _log.end(rec, grad_f=gs)
+                if ctx.has_center[n] and ctx.needs_input_grad[3 + 2 * n]:
+                    gc = -g.sum(-1)
+            elif ctx.needs_input_grad[2 + 2 * n]:
+                gs = g.sum(-1)
+            grads += [gs, gc]
+        return (None, None, *grads)
+
+
+class EdgeAffine(torch.autograd.Function):
+    """p[idx] + LeakyReLU(q[idx] - center) (K12): the k-expanded half of the restructured EdgeConv
+    (gcn_lib/pointnet/gcn.py:206-211).  Differentiable w.r.t. p, q, center."""
+
+    @staticmethod
+    def forward(ctx, p, q, center, idx, slope):
+        ctx.slope = float(slope)
+        ctx.save_for_backward(q, center, idx)
+        if csr_cache.prefetch_enabled and (p.requires_grad or q.requires_grad):
+            csr_cache.prefetch(idx, q.shape[2])
+        return edge_affine_fwd(p, q, center, idx, slope)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, center, idx = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        N = q.shape[2]
+        need_p, need_q, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gp = gq = gc = None
+        if need_p:
+            gp = group_bwd_auto(grad_out, idx, N)
+        if need_q or need_c:
+            g2, gc = edge_affine_bwd(grad_out, q, center, idx, ctx.slope, want_center=need_c)
+            if need_q:
+                gq = group_bwd_auto(g2, idx, N)
+        return gp, gq, gc, None, None
 
 
 class ThreeInterpolate(torch.autograd.Function):
