@@ -57,8 +57,8 @@ constexpr int FT_NQ = 128;   // queries per CTA (UMMA N): 8 clouds x 16 CTAs = 1
 constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
 constexpr int FT_NBUF = 4;             // TMEM accumulator buffers: MMA(u+1..u+3) in flight while tile u is consumed
 constexpr int FT_TMEM_COLS = FT_NBUF * FT_NQ;  // 512 columns: all of TMEM (one CTA per SM)
-constexpr int FT_MAX_K = 24; // needs slack below the 32 list slots for the margin zone
-constexpr int FT_CAP = 60;         // candidate slots per query (all four lane quarters append to one buffer)
+constexpr int FT_MAX_K = 24;
+constexpr int FT_RSLACK = 4;  // tau0 bounds the (K + FT_RSLACK)-th smallest e: with the group collisions ~K + 10 hits per query
 constexpr int FT_STAGES = 4;       // candidate-tile ring: tiles u+1..u+3 feed the MMAs in flight, u+4 is loading
 
 struct FeatArgs {
@@ -69,11 +69,14 @@ struct FeatArgs {
   int B, P1, P2, D, K;
   const float* nrm1;       // [B,P1] squared norms of the (centred, split) queries
   const float* nrm2;       // [B,P2] squared norms of the (centred, split) candidates
-  const unsigned* nmax2;   // [B]    max squared candidate norm (float bits)
+  const unsigned* nmax2;   // [B][FT_NMAX_PARTS] partial maxima of the squared candidate norms (float bits)
   float* dists;            // [B,P1,K]
   int64_t* idx;            // [B,P1,K]
   int* fb_count;           // [1]
   int* fb_list;            // [B*P1]
+  unsigned* masks;         // [B][4*T][P1] hit masks of pass 1: word (t*4 + quarter) bit l = candidate t*128 + quarter*32 + l
+  float* tau0;             // [B,P1] admission bound of every query
+  int T;                   // candidate tiles per cloud = ceil(P2 / 128)
   long long* dbg;          // [ctas][8] phase timestamps (tools/bench_knn_feat.py)
   const int32_t* skip;     // nonzero -> every kernel of the call returns at once (results come from a memoised call)
 };
@@ -242,88 +245,103 @@ __device__ __forceinline__ float ordered_key_inv(unsigned uk) {
   return __int_as_float(bits);
 }
 
-// ---- pre-pass: per-cloud mean, centred bf16 x 2 split, squared norms, per-cloud max norm ----------------------
-constexpr int FT_MEAN_CHUNKS = 16;
-constexpr int FT_SPLIT_ITERS = 4;  // row groups per CTA of feat_split_kernel (amortises the mean prologue)
+// ---- pre-pass: centre, centred bf16 x 2 split, squared norms, per-cloud max norm ------------------------------
+// ONE kernel.  The centre is the mean of FT_CENTRE_ROWS rows sampled evenly over the candidate cloud, recomputed by
+// every CTA (128 rows from L2, fixed summation order): ANY common shift of both operands is correct — the centre
+// only sets the size of the norms, hence of the margins — and a sampled mean removes the large common offset of
+// real network features as well as the exact one, without a second kernel in front of this one.
+constexpr int FT_CENTRE_ROWS = 128;
+constexpr int FT_NMAX_PARTS = 32;  // per-cloud partial maxima of the candidate norms (one per CTA of the split launch)
 
-// partial column sums of cloud b over rows [chunk * rows_per, ...) below its length: part[b][chunk][D]
-// (fixed summation order: the centre is deterministic; any centre would be CORRECT, it only sets the margins)
-__global__ void __launch_bounds__(256) feat_mean_partial_kernel(const float* __restrict__ p, const int64_t* __restrict__ len,
-                                                                int P, int D, float* __restrict__ part,
-                                                                unsigned* __restrict__ nmax, int* __restrict__ fb_count,
-                                                                const int32_t* __restrict__ skip) {
-  __shared__ float red_s[256];
-  if (skip && *skip) return;
-  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  if (chunk == 0 && tid == 0) {  // (replaces a memset node) consumed by the kernels launched after this one
-    nmax[b] = 0u;
-    if (b == 0) *fb_count = 0;
-  }
-  const int n = len ? min((int)len[b], P) : P;
-  const int rows_per = (P + FT_MEAN_CHUNKS - 1) / FT_MEAN_CHUNKS;
-  const int r0 = chunk * rows_per, r1 = min(n, r0 + rows_per);
-  const int col = tid % D, sub = tid / D, nsub = 256 / D;
-  float acc = 0.0f;
-  for (int r = r0 + sub; r < r1; r += nsub) acc += __ldg(p + ((size_t)b * P + r) * D + col);
-  red_s[tid] = acc;
-  __syncthreads();
-  if (tid < D) {
-    float t = 0.0f;
-    for (int u = 0; u < nsub; ++u) t += red_s[u * D + tid];
-    part[((size_t)b * FT_MEAN_CHUNKS + chunk) * D + tid] = t;
-  }
-}
-
-// One float4 chunk per thread (LPR = D/4 lanes per row): v = x - mean; b1 = bf16_rn(v); b2 = bf16_rn(v - b1);
+// One float4 chunk per thread (LPR = D/4 lanes per row): v = x - centre; b1 = bf16_rn(v); b2 = bf16_rn(v - b1);
 // out row = [b1(0..D-1) | b2(0..D-1)] (2D bf16 = the bytes of the fp32 row); nrm = sum (b1 + b2)^2.
-__global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict__ p, const int64_t* __restrict__ len_c,
-                                                         int Pc, int P, int D, const float* __restrict__ part,
+// grid.x <= FT_NMAX_PARTS CTAs per cloud, each looping over its row groups; CTA x owns nmax_part[b][x].
+__global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict__ p, const float* __restrict__ pc,
+                                                         const int64_t* __restrict__ len_c, int Pc, int P, int D,
                                                          uint2* __restrict__ split, float* __restrict__ nrm,
-                                                         unsigned* __restrict__ nmax, const int32_t* __restrict__ skip) {
+                                                         unsigned* __restrict__ nmax_part, const int32_t* __restrict__ skip) {
+  __shared__ float red_s[256];
   __shared__ float mean_s[64];
   if (skip && *skip) return;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int n = len_c ? min((int)len_c[b], Pc) : Pc;  // valid rows of the candidate cloud
-  if (tid < D) {
-    float t = 0.0f;
-    for (int c = 0; c < FT_MEAN_CHUNKS; ++c) t += part[((size_t)b * FT_MEAN_CHUNKS + c) * D + tid];
-    mean_s[tid] = n > 0 ? t / (float)n : 0.0f;
-  }
-  __syncthreads();
-  const int lpr = D >> 2, rows_per_it = 256 / lpr, ch = tid % lpr;
-  unsigned mloc = 0u;
-  for (int it = 0; it < FT_SPLIT_ITERS; ++it) {
-  const int row = (blockIdx.x * FT_SPLIT_ITERS + it) * rows_per_it + tid / lpr;
-  float s = 0.0f;
-  if (row < P) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p + ((size_t)b * P + row) * D) + ch);
-    const float c[4] = {v.x - mean_s[4 * ch], v.y - mean_s[4 * ch + 1], v.z - mean_s[4 * ch + 2], v.w - mean_s[4 * ch + 3]};
-    unsigned short h1[4], h2[4];
+  {
+    // all of a thread's sample rows are requested before the first is used (the kernel is pure latency)
+    const int col = tid % D, sub = tid / D, nsub = 256 / D;
+    constexpr int PER = FT_CENTRE_ROWS / 4;  // >= rows per thread (nsub = 8 or 4)
+    float v[PER];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat16 b1 = __float2bfloat16_rn(c[k]);
-      const float f1 = __bfloat162float(b1);
-      const __nv_bfloat16 b2 = __float2bfloat16_rn(c[k] - f1);
-      const float xs = f1 + __bfloat162float(b2);  // exact in fp32 (<= 17 significant bits)
-      s = fmaf(xs, xs, s);
-      h1[k] = __bfloat16_as_ushort(b1);
-      h2[k] = __bfloat16_as_ushort(b2);
+    for (int u = 0; u < PER; ++u) {
+      const int i = sub + u * nsub;
+      v[u] = 0.0f;
+      if (n > 0 && i < FT_CENTRE_ROWS) v[u] = __ldg(pc + ((size_t)b * Pc + (int)(((long long)i * n) / FT_CENTRE_ROWS)) * D + col);
     }
-    uint2* orow = split + ((size_t)b * P + row) * (size_t)(D >> 1);  // row = D/2 uint2 (2D bf16)
-    orow[ch] = make_uint2((unsigned)h1[0] | ((unsigned)h1[1] << 16), (unsigned)h1[2] | ((unsigned)h1[3] << 16));
-    orow[lpr + ch] = make_uint2((unsigned)h2[0] | ((unsigned)h2[1] << 16), (unsigned)h2[2] | ((unsigned)h2[3] << 16));
+    float acc = 0.0f;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) acc += v[u];
+    red_s[tid] = acc;
+    __syncthreads();
+    if (tid < D) {
+      float t = 0.0f;
+      for (int u = 0; u < nsub; ++u) t += red_s[u * D + tid];
+      mean_s[tid] = t * (1.0f / FT_CENTRE_ROWS);
+    }
+    __syncthreads();
   }
-  // sum over the row's lanes (lpr = 8 or 16 consecutive lanes)
-  for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-  if (row < P && ch == 0) nrm[(size_t)b * P + row] = s;
-  // rows beyond the cloud's length never become candidates; non-finite norms (inf / NaN inputs) must poison
-  // the bound, not vanish in the integer max: NaN -> +inf
-  const float sm = (row < n) ? ((s == s) ? s : __int_as_float(0x7f800000)) : 0.0f;
-  mloc = max(mloc, __float_as_uint(sm));  // s >= 0: bit order == value order
+  const int lpr = D >> 2, rows_per_it = 256 / lpr, ch = tid % lpr;
+  const int iters = (P + (int)gridDim.x * rows_per_it - 1) / ((int)gridDim.x * rows_per_it);
+  unsigned mloc = 0u;
+  const float m0 = mean_s[4 * ch], m1 = mean_s[4 * ch + 1], m2 = mean_s[4 * ch + 2], m3 = mean_s[4 * ch + 3];
+  for (int it0 = 0; it0 < iters; it0 += 4) {
+    float4 rv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // up to 4 row groups in flight
+      const int row = (blockIdx.x * iters + it0 + u) * rows_per_it + tid / lpr;
+      if (it0 + u < iters && row < P) rv[u] = __ldg(reinterpret_cast<const float4*>(p + ((size_t)b * P + row) * D) + ch);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (it0 + u >= iters) break;  // (uniform)
+      const int row = (blockIdx.x * iters + it0 + u) * rows_per_it + tid / lpr;
+      float s = 0.0f;
+      if (row < P) {
+        const float c[4] = {rv[u].x - m0, rv[u].y - m1, rv[u].z - m2, rv[u].w - m3};
+        unsigned short h1[4], h2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat16 b1 = __float2bfloat16_rn(c[k]);
+          const float f1 = __bfloat162float(b1);
+          const __nv_bfloat16 b2 = __float2bfloat16_rn(c[k] - f1);
+          const float xs = f1 + __bfloat162float(b2);  // exact in fp32 (<= 17 significant bits)
+          s = fmaf(xs, xs, s);
+          h1[k] = __bfloat16_as_ushort(b1);
+          h2[k] = __bfloat16_as_ushort(b2);
+        }
+        uint2* orow = split + ((size_t)b * P + row) * (size_t)(D >> 1);  // row = D/2 uint2 (2D bf16)
+        orow[ch] = make_uint2((unsigned)h1[0] | ((unsigned)h1[1] << 16), (unsigned)h1[2] | ((unsigned)h1[3] << 16));
+        orow[lpr + ch] = make_uint2((unsigned)h2[0] | ((unsigned)h2[1] << 16), (unsigned)h2[2] | ((unsigned)h2[3] << 16));
+      }
+      // sum over the row's lanes (lpr = 8 or 16 consecutive lanes)
+      for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      if (row < P && ch == 0) nrm[(size_t)b * P + row] = s;
+      // rows beyond the cloud's length never become candidates; non-finite norms (inf / NaN inputs) must poison
+      // the bound, not vanish in the integer max: NaN -> +inf
+      const float sm = (row < n) ? ((s == s) ? s : __int_as_float(0x7f800000)) : 0.0f;
+      mloc = max(mloc, __float_as_uint(sm));  // s >= 0: bit order == value order
+    }
   }
-  if (nmax) {
+  if (nmax_part) {
     const unsigned m = __reduce_max_sync(FULL, mloc);
-    if ((tid & 31) == 0) atomicMax(nmax + b, m);
+    __syncthreads();  // red_s is free again
+    if ((tid & 31) == 0) reinterpret_cast<unsigned*>(red_s)[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned t = 0u;
+      for (int w = 0; w < 8; ++w) t = max(t, reinterpret_cast<unsigned*>(red_s)[w]);
+      nmax_part[(size_t)b * FT_NMAX_PARTS + blockIdx.x] = t;
+    }
+    // slots of CTAs that do not exist
+    if (blockIdx.x == 0 && tid >= (int)gridDim.x && tid < FT_NMAX_PARTS) nmax_part[(size_t)b * FT_NMAX_PARTS + tid] = 0u;
   }
 }
 
@@ -366,10 +384,10 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   __shared__ __align__(8) uint64_t tfree_s[FT_NBUF];      // all 16 warps have drained the TMEM buffer
   __shared__ uint32_t tmem_base_s;
   __shared__ float tau0_s[FT_NQ];
-  __shared__ float limit_s[FT_NQ];
-  __shared__ int cnt_s[FT_NQ];
+  __shared__ unsigned wmask_s[FT_THREADS / 32][32];   // pass 1: a warp's 32 hit masks on their way to lane-major order
 
   if (a.skip && *a.skip) return;  // (uniform) memoised call: nothing to do, nothing allocated yet
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.fb_count = 0;  // (replaces a memset node) counted up by the rank kernel
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULL, tid >> 5, 0);  // warp-uniform for the compiler too (role branches, uniform registers)
   const int quarter = warp & 3, colgrp = warp >> 2;
@@ -380,7 +398,6 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
   const int n2 = a.len2 ? min((int)a.len2[b], a.P2) : a.P2;
   const float INF = __int_as_float(0x7f800000);
-  const unsigned lt_mask = (1u << lane) - 1u;
 
   // dynamic smem, 1024-aligned: [stage0 | stage1 | queries | group values / candidate buffers]
   const uint32_t raw = smem_u32(ft_smem_raw);
@@ -390,11 +407,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   const uint32_t atomA = 128u * 128u;                // one 32-float K-slab of a stage
   const uint32_t qtile = base + (uint32_t)FT_STAGES * stage_bytes;
   const uint32_t atomB = (uint32_t)FT_NQ * 128u;
-  constexpr int cpr = D >> 2;                        // 16-byte chunks per row: 8 or 16
   const int T = (n2 + FT_TM - 1) / FT_TM;
-
-  const float* p2b = a.p2 + (size_t)b * a.P2 * D;
-  const float* p1b = a.p1 + (size_t)b * a.P1 * D;
 
   // candidate tile t -> smem stage: one TMA box per 32-float K-slab, issued by ONE thread; rows of
   // the next cloud that ride along in a ragged last tile are masked by their +inf norm
@@ -428,8 +441,6 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   const int U = 2 * T;
   unsigned char* aux = base_ptr + (uint32_t)FT_STAGES * stage_bytes + (uint32_t)D * 4u * FT_NQ;
   float* gval_s = reinterpret_cast<float*>(aux);    // pass 0 -> select: [FT_NQ][64] group minima
-  float2* buf_s = reinterpret_cast<float2*>(aux);   // pass 1: [FT_NQ][FT_CAP] (e, idx) — aliases gval_s
-  for (int g = tid; g < FT_NQ; g += FT_THREADS) cnt_s[g] = 0;
 
   __syncthreads();  // barriers initialised, TMEM allocated
   tc_fence_after();
@@ -508,6 +519,9 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   float reg[FT_QW];
 #pragma unroll
   for (int n = 0; n < FT_QW; ++n) reg[n] = INF;
+  unsigned* wmask = &wmask_s[warp][0];
+  unsigned* mrow = a.masks + (size_t)b * (size_t)(4 * T) * a.P1;   // this cloud's mask words: [4T][P1]
+  const bool qcol_ok = q0 + nq0 + lane < a.P1;                       // lane c publishes the masks of query q0 + nq0 + c
 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
@@ -523,7 +537,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
       // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
       //      processed together so their (dependent) radix steps overlap
       constexpr int QPW = FT_NQ / (FT_THREADS / 32);
-      const int R = min(32, K + 8);
+      const int R = min(32, K + FT_RSLACK);
       unsigned uk[QPW][2];
 #pragma unroll
       for (int qq = 0; qq < QPW; ++qq)
@@ -531,10 +545,13 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         for (int v = 0; v < 2; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 64 + v * 32 + lane]);
       unsigned bound[QPW];
       warp_radix_bound16_multi<QPW, 2>(uk, R, bound);
-      epi_sync();  // gval_s is dead from here on: buf_s may overwrite it
       if (lane == 0)
 #pragma unroll
-        for (int qq = 0; qq < QPW; ++qq) tau0_s[warp * QPW + qq] = ordered_key_inv(bound[qq]);
+        for (int qq = 0; qq < QPW; ++qq) {
+          const float tq = ordered_key_inv(bound[qq]);
+          tau0_s[warp * QPW + qq] = tq;
+          if (q0 + warp * QPW + qq < a.P1) a.tau0[(size_t)b * a.P1 + q0 + warp * QPW + qq] = tq;
+        }
       epi_sync();
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) reg[n] = tau0_s[nq0 + n];
@@ -550,41 +567,19 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) reg[n] = fminf(reg[n], fmaf(-2.0f, __uint_as_float(acc[n]), ncj));
     } else {
-      // Appends are predicated, not branched, and issued in groups of 8 columns: the 8 slot counters' ATOMS
-      // round trips (~80 cycles each) overlap instead of stalling the warp once per column that has a hit
-      // in any lane (41 % of the columns).
-      const float jbits = __int_as_float(j);
-      const uint32_t valid = j < n2 ? 1u : 0u;
-      const uint32_t cnt0 = smem_u32(&cnt_s[nq0]);
-      const uint32_t buf0 = smem_u32(&buf_s[nq0 * FT_CAP]);
+      // Pass 1 records WHICH candidates lie under the bound, nothing else: one ballot per query column gives the
+      // 32-bit hit mask of this warp's 32 candidates (no shared-memory atomics, no per-hit stores: the first
+      // versions appended (e, idx) pairs through smem counters and spent 2700-4000 cycles per tile on the
+      // ATOMS round trips).  Lane 0 parks the 32 masks in smem, lane c publishes the word of column c.
+      const bool valid = j < n2;
 #pragma unroll
-      for (int g = 0; g < FT_QW; g += 8) {
-        float e[8];
-        uint32_t pos[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          e[c] = fmaf(-2.0f, __uint_as_float(acc[g + c]), ncj);  // inf for padded candidates
-          asm volatile(
-              "{\n\t.reg .pred p, v;\n\t"
-              "setp.ne.b32 v, %4, 0;\n\t"
-              "setp.le.and.f32 p, %1, %2, v;\n\t"
-              "mov.u32 %0, 0xffffffff;\n\t"
-              "@p atom.shared.add.u32 %0, [%3], 1;\n\t}\n"
-              : "=r"(pos[c])
-              : "f"(e[c]), "f"(reg[g + c]), "r"(cnt0 + 4u * (uint32_t)(g + c)), "r"(valid)
-              : "memory");
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = buf0 + ((uint32_t)(g + c) * FT_CAP + pos[c]) * 8u;
-          asm volatile(
-              "{\n\t.reg .pred q;\n\t"
-              "setp.lt.u32 q, %0, %1;\n\t"
-              "@q st.shared.v2.f32 [%2], {%3, %4};\n\t}\n" ::"r"(pos[c]),
-              "r"((uint32_t)FT_CAP), "r"(addr), "f"(e[c]), "f"(jbits)
-              : "memory");
-        }
+      for (int c = 0; c < FT_QW; ++c) {
+        const float e = fmaf(-2.0f, __uint_as_float(acc[c]), ncj);  // inf for padded candidates
+        const unsigned m = __ballot_sync(FULL, valid && e <= reg[c]);
+        if (lane == 0) wmask[c] = m;
       }
+      __syncwarp();
+      if (qcol_ok) mrow[(size_t)(t * 4 + quarter) * a.P1 + q0 + nq0 + lane] = wmask[lane];
     }
     // this warp has drained TMEM buffer u % 4 (tcgen05.wait::ld inside tmem_ld32): MMA(u+4) may overwrite it.
     // No CTA-wide barrier in the loop: warps run ahead until the next MMA-done barrier.
@@ -592,119 +587,105 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&tfree_s[u % FT_NBUF]));
   }
-  epi_sync();
   if (dbg && tid == 0) dbg[4] = clock64();
-
-  // ---- finalisation, one warp per query (QPW queries per warp), no CTA barrier ----
-  // F1 margin + superset check + candidate list (<= 32); F2 canonical distances: the candidate rows are
-  // fetched with fully coalesced 16-byte loads (8 or 16 lanes per row) into a padded per-warp tile, then lane r
-  // sums row r sequentially in d order (a row per lane straight from global memory is L1-tag-bound: 32
-  // lines per request); F3 rank by (d_canon, idx) with shuffles and write the K best.
-  constexpr int QPW = FT_NQ / (FT_THREADS / 32);
-  const float nmax = __uint_as_float(a.nmax2[b]);
-  const int rstride = D + 4;                                         // floats; keeps float4 reads of 8 rows conflict-free
-  float* wtile = reinterpret_cast<float*>(base_ptr) + (size_t)warp * (32 * rstride + D + 32);  // stage memory is free now
-  float* wq = wtile + 32 * rstride;                                  // the query row
-  int* wcand = reinterpret_cast<int*>(wq + D);                       // compacted candidate indices
-  const int lpr = cpr;                                               // lanes per row: 8 (D=32) or 16 (D=64)
-  const int rpi = 32 / lpr;                                          // rows per load instruction
-  // F1 for the warp's QPW queries at once: the 16 dependent radix steps of the queries interleave, and the
-  // norms arrive with one coalesced load
-  {
-    unsigned uk[QPW][2];
-#pragma unroll
-    for (int qq = 0; qq < QPW; ++qq) {
-      const int n = warp * QPW + qq;
-      const int C = cnt_s[n];
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int i = lane + 32 * s2;
-        uk[qq][s2] = (C <= FT_CAP && i < C) ? ordered_key(buf_s[n * FT_CAP + i].x) : 0xffffffffu;
-      }
-    }
-    unsigned tkk[QPW];
-    warp_radix_bound16_multi<QPW, 2>(uk, K, tkk);
-    float eps2 = 0.0f;
-    if (lane < QPW && q0 + warp * QPW + lane < n1)
-      eps2 = 2.0f * feat_eps(a.nrm1[(size_t)b * a.P1 + q0 + warp * QPW + lane], nmax, D);
-#pragma unroll
-    for (int qq = 0; qq < QPW; ++qq) {
-      const int n = warp * QPW + qq;
-      // upper bound (< 1% loose) of the K-th smallest buffered e: a larger T_K only widens the margin
-      const float tk = cnt_s[n] >= K ? ordered_key_inv(tkk[qq]) : INF;
-      const float lim = tk + __shfl_sync(FULL, eps2, qq);
-      if (lane == 0) limit_s[n] = lim;
-    }
-    __syncwarp();
+  __syncthreads();
+  if (dbg && tid == 0) dbg[5] = clock64();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(FT_TMEM_COLS) : "memory");
   }
-  for (int qq = 0; qq < QPW; ++qq) {
-    const int n = warp * QPW + qq;
-    const int qi = q0 + n;
-    if (qi >= n1) {
-      if (qi < a.P1 && lane < K) {  // rows beyond lengths1: zeros (pytorch3d convention)
-        a.dists[((size_t)b * a.P1 + qi) * K + lane] = 0.0f;
-        a.idx[((size_t)b * a.P1 + qi) * K + lane] = 0;
-      }
-      continue;
-    }
-    const int C = cnt_s[n];
-    bool ok = C <= FT_CAP;
-    float ev[2];
-    int jv[2];
+}
+
+// ---- ranking kernel: one warp per query, many warps per SM (the chain below is all latency) -----------------
+// The hits of a query (pass 1 masks) are expanded into a candidate list, their rows are fetched with coalesced
+// 16-byte loads into a padded per-warp tile, lane r sums row r sequentially in d order (the canonical distance),
+// and the K best by (d_canon, idx) are written.  Completeness: a candidate j that was NOT recorded has
+// e_j > tau0, hence d_canon(j) > tau0 + |x|^2 - eps (eps bounds |e - (d_true - |x|^2)| + |d_canon - d_true|,
+// feat_eps); so when the K-th smallest canonical distance among the hits lies strictly below that bound, no
+// unrecorded candidate can enter (or tie into) the result.  Otherwise, or with more than FT_HCAP hits, the query
+// goes to the exact fallback.
+constexpr int FT_HCAP = 64;          // hits handled per query (two rounds of 32)
+template <int DD>
+__global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank_kernel(FeatArgs a) {
+  constexpr int D = DD, cpr = D >> 2, lpr = cpr, rpi = 32 / lpr, rstride = D + 4;
+  constexpr int FT_RANK_WARPS = 256 / DD;  // 8 (D = 32) or 4 (D = 64) warps: < 48 KB of static shared memory
+  __shared__ __align__(16) float tile_s[FT_RANK_WARPS][32 * rstride + D];
+  __shared__ int cand_s[FT_RANK_WARPS][FT_HCAP];
+  if (a.skip && *a.skip) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long flat = (long long)blockIdx.x * FT_RANK_WARPS + warp;
+  if (flat >= (long long)a.B * a.P1) return;
+  const int b = (int)(flat / a.P1), qi = (int)(flat - (long long)b * a.P1);
+  const int K = a.K;
+  const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
+  float* od = a.dists + ((size_t)b * a.P1 + qi) * K;
+  int64_t* oi = a.idx + ((size_t)b * a.P1 + qi) * K;
+  if (qi >= n1) {  // rows beyond lengths1: zeros (pytorch3d convention)
+    if (lane < K) { od[lane] = 0.0f; oi[lane] = 0; }
+    return;
+  }
+  const float INF = __int_as_float(0x7f800000);
+  float* wtile = &tile_s[warp][0];
+  int* wcand = &cand_s[warp][0];
+  const float* p2b = a.p2 + (size_t)b * a.P2 * D;
+  // everything the tail needs is requested up front: the warp's chain is latency, not bandwidth
+  const unsigned* mq = a.masks + (size_t)b * (size_t)(4 * a.T) * a.P1 + qi;
+  const int nwords = 4 * a.T;
+  unsigned mw0 = lane < nwords ? __ldg(mq + (size_t)lane * a.P1) : 0u;
+  unsigned mw1 = lane + 32 < nwords ? __ldg(mq + (size_t)(lane + 32) * a.P1) : 0u;
+  const float t0 = __ldg(a.tau0 + (size_t)b * a.P1 + qi);
+  const float nq = __ldg(a.nrm1 + (size_t)b * a.P1 + qi);
+  const unsigned nmax_bits = __reduce_max_sync(FULL, __ldg(a.nmax2 + (size_t)b * FT_NMAX_PARTS + lane));
+  float* wq = wtile + 32 * rstride;  // the query row
+  if (lane < cpr) reinterpret_cast<float4*>(wq)[lane] = __ldg(reinterpret_cast<const float4*>(a.p1 + ((size_t)b * a.P1 + qi) * D) + lane);
+  // ---- candidate list from the hit masks (ascending candidate index) ----
+  int H = 0;
+  for (int w0 = 0; w0 < nwords; w0 += 32) {
+    const int w = w0 + lane;
+    unsigned m = w0 == 0 ? mw0 : (w0 == 32 ? mw1 : (w < nwords ? __ldg(mq + (size_t)w * a.P1) : 0u));
+    const int c = __popc(m);
+    int incl = c;
 #pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const int i = lane + 32 * s2;
-      ev[s2] = INF; jv[s2] = 0x7fffffff;
-      if (ok && i < C) {
-        const float2 v = buf_s[n * FT_CAP + i];
-        ev[s2] = v.x; jv[s2] = __float_as_int(v.y);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int pos = H + incl - c;
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      if (pos < FT_HCAP) wcand[pos] = w * 32 + bit;
+      ++pos;
+    }
+    H += __shfl_sync(FULL, incl, 31);
+  }
+  __syncwarp();
+  bool ok = H <= FT_HCAP;
+  // ---- canonical distances, 32 candidates per round: rows arrive with coalesced 16-byte loads in a padded
+  //      per-warp tile, lane r then sums row r sequentially in d order ----
+  unsigned long long key0 = ~0ull, key1 = ~0ull;  // (d_canon bits, idx): d >= 0, so integer order == (d, idx) order
+  auto round = [&](int base_r) -> unsigned long long {
+    const int nr = min(32, H - base_r);
+    const int sub = lane / lpr, ch = lane - sub * lpr;
+    for (int r0 = 0; r0 < nr; r0 += 8 * rpi) {  // 8 independent loads in flight per lane
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * rpi + sub;
+        if (r < nr) v[u] = __ldg(reinterpret_cast<const float4*>(p2b + (size_t)wcand[base_r + r] * D) + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * rpi + sub;
+        if (r < nr) *reinterpret_cast<float4*>(wtile + r * rstride + ch * 4) = v[u];
       }
     }
-    const float limit = limit_s[n];
-    const float t0 = tau0_s[n];
-    // everything with e <= tau0 is buffered, so the margin zone must end below tau0
-    // (tau0 == inf: every candidate of the cloud is buffered)
-    ok = ok && (limit < t0 || t0 == INF);
-    const bool cand0 = ok && ev[0] <= limit && lane < C, cand1 = ok && ev[1] <= limit && lane + 32 < C;
-    const unsigned cm0 = __ballot_sync(FULL, cand0), cm1 = __ballot_sync(FULL, cand1);
-    const int ncand = __popc(cm0) + __popc(cm1);
-    if (!ok || ncand > 32) {  // (warp-uniform) exact fallback kernel takes this query
-      if (lane == 0) {
-        const int pos = atomicAdd(a.fb_count, 1);
-        a.fb_list[pos] = b * a.P1 + qi;
-      }
-      continue;
-    }
-    __syncwarp();  // the previous query's readers are done with wtile / wcand
-    if (cand0) wcand[__popc(cm0 & lt_mask)] = jv[0];
-    if (cand1) wcand[__popc(cm0) + __popc(cm1 & lt_mask)] = jv[1];
-    if (lane < cpr) reinterpret_cast<float4*>(wq)[lane] = __ldg(reinterpret_cast<const float4*>(p1b + (size_t)qi * D) + lane);
     __syncwarp();
-    {
-      const int sub = lane / lpr, ch = lane - sub * lpr;
-      for (int r0 = 0; r0 < ncand; r0 += 8 * rpi) {  // 8 independent loads in flight per lane (all 32 rows at D = 32)
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = r0 + u * rpi + sub;
-          if (r < ncand) v[u] = __ldg(reinterpret_cast<const float4*>(p2b + (size_t)wcand[r] * D) + ch);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = r0 + u * rpi + sub;
-          if (r < ncand) *reinterpret_cast<float4*>(wtile + r * rstride + ch * 4) = v[u];
-        }
-      }
-    }
-    __syncwarp();
-    const bool cand = lane < ncand;
-    float dc = INF;
-    int ci = 0x7fffffff;
-    if (cand) {
-      ci = wcand[lane];
+    unsigned long long key = ~0ull;
+    if (lane < nr) {
       const float4* y = reinterpret_cast<const float4*>(wtile + lane * rstride);
       const float4* x = reinterpret_cast<const float4*>(wq);
       float acc = 0.0f;
+#pragma unroll 4
       for (int c = 0; c < cpr; ++c) {
         const float4 x0 = x[c], y0 = y[c];
         acc = sq_acc(acc, x0.x, y0.x);
@@ -712,25 +693,57 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         acc = sq_acc(acc, x0.z, y0.z);
         acc = sq_acc(acc, x0.w, y0.w);
       }
-      dc = acc;
+      key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)wcand[base_r + lane];
     }
-    int rank = 0;
-    for (int m2 = 0; m2 < ncand; ++m2) {
-      const float od2 = __shfl_sync(FULL, dc, m2);
-      const int oi2 = __shfl_sync(FULL, ci, m2);
-      rank += (od2 < dc || (od2 == dc && oi2 < ci)) ? 1 : 0;
+    return key;
+  };
+  if (ok) {
+    key0 = round(0);
+    if (H > 32) {
+      __syncwarp();  // the first round's readers are done with wtile
+      key1 = round(32);
     }
-    float* od = a.dists + ((size_t)b * a.P1 + qi) * K;
-    int64_t* oi = a.idx + ((size_t)b * a.P1 + qi) * K;
-    if (cand && rank < K) { od[rank] = dc; oi[rank] = (int64_t)ci; }
-    if (lane < K && lane >= ncand) { od[lane] = 0.0f; oi[lane] = 0; }  // fewer than K candidates in the cloud
   }
-
-  __syncthreads();
-  if (dbg && tid == 0) dbg[5] = clock64();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(FT_TMEM_COLS) : "memory");
+  // ---- rank by (d_canon, idx) ----
+  int rank0 = 0, rank1 = 0;
+  if (ok) {
+    const int nA = min(H, 32), nB = H - nA;
+    if (nB == 0) {
+      for (int m2 = 0; m2 < nA; ++m2) rank0 += __shfl_sync(FULL, key0, m2) < key0 ? 1 : 0;
+    } else {
+      for (int m2 = 0; m2 < nA; ++m2) {
+        const unsigned long long o = __shfl_sync(FULL, key0, m2);
+        rank0 += o < key0 ? 1 : 0;
+        rank1 += o < key1 ? 1 : 0;
+      }
+      for (int m2 = 0; m2 < nB; ++m2) {
+        const unsigned long long o = __shfl_sync(FULL, key1, m2);
+        rank0 += o < key0 ? 1 : 0;
+        rank1 += o < key1 ? 1 : 0;
+      }
+    }
+    // K-th smallest canonical distance among the hits
+    const int kk = min(K, H);
+    unsigned top = 0u;
+    if (lane < H && rank0 < kk) top = (unsigned)(key0 >> 32);
+    if (lane + 32 < H && rank1 < kk) top = max(top, (unsigned)(key1 >> 32));
+    const float dk = __uint_as_float(__reduce_max_sync(FULL, top));
+    if (t0 != INF) {  // tau0 == inf: every candidate of the cloud is a hit
+      const float eps = feat_eps(nq, __uint_as_float(nmax_bits), D);
+      // 1/16 more than eps covers the roundings of this very expression
+      ok = H >= K && dk < (t0 + nq) - 1.0625f * eps;
+    }
   }
+  if (!ok) {  // (warp-uniform) exact fallback kernel takes this query
+    if (lane == 0) {
+      const int pos = atomicAdd(a.fb_count, 1);
+      a.fb_list[pos] = b * a.P1 + qi;
+    }
+    return;
+  }
+  if (lane < H && rank0 < K) { od[rank0] = __uint_as_float((unsigned)(key0 >> 32)); oi[rank0] = (int64_t)(unsigned)key0; }
+  if (lane + 32 < H && rank1 < K) { od[rank1] = __uint_as_float((unsigned)(key1 >> 32)); oi[rank1] = (int64_t)(unsigned)key1; }
+  if (lane < K && lane >= H) { od[lane] = 0.0f; oi[lane] = 0; }  // fewer than K candidates in the cloud
 }
 
 // ---- exact fallback: one CTA per flagged query (16 warps x 1/16 of the candidates, then a two-level merge) ------
@@ -820,7 +833,6 @@ __global__ void __launch_bounds__(512) knn_feat_fallback_kernel(FeatArgs a) {
 
 // ---- host side -------------------------------------------------------------------------------------
 struct FeatWs {
-  float* part;     // [B][FT_MEAN_CHUNKS][D] partial column sums of p2
   uint2* split1;   // [B*P1][2D bf16] centred, split queries
   uint2* split2;   // [B*P2][2D bf16] centred, split candidates
   float* nrm1;
@@ -828,6 +840,8 @@ struct FeatWs {
   unsigned* nmax2;
   int* fb_count;
   int* fb_list;
+  unsigned* masks; // [B][4T][P1] pass-1 hit masks
+  float* tau0;     // [B*P1]
   long long* dbg;
   size_t total;
 };
@@ -836,14 +850,15 @@ static FeatWs feat_carve(void* base, int B, int P1, int P2, int D) {
   FeatWs w;
   char* p = reinterpret_cast<char*>(base);
   size_t o = 0;
-  w.nmax2 = reinterpret_cast<unsigned*>(p + o); o += align_up(sizeof(unsigned) * (size_t)B, 256);
+  w.nmax2 = reinterpret_cast<unsigned*>(p + o); o += align_up(sizeof(unsigned) * (size_t)B * 32, 256);
   w.fb_count = reinterpret_cast<int*>(p + o);   o += 256;
   w.nrm1 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P1, 256);
   w.nrm2 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P2, 256);
   w.fb_list = reinterpret_cast<int*>(p + o);    o += align_up(sizeof(int) * (size_t)B * P1, 256);
-  w.part = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * FT_MEAN_CHUNKS * D, 256);
   w.split1 = reinterpret_cast<uint2*>(p + o);   o += align_up(sizeof(float) * (size_t)B * P1 * D, 1024);
   w.split2 = reinterpret_cast<uint2*>(p + o);   o += align_up(sizeof(float) * (size_t)B * P2 * D, 1024);
+  w.tau0 = reinterpret_cast<float*>(p + o);     o += align_up(sizeof(float) * (size_t)B * P1, 256);
+  w.masks = reinterpret_cast<unsigned*>(p + o); o += align_up(sizeof(unsigned) * (size_t)B * P1 * 4 * (size_t)((P2 + FT_TM - 1) / FT_TM), 256);
   w.dbg = reinterpret_cast<long long*>(p + o);  o += align_up(sizeof(long long) * 16 * (size_t)B * (size_t)((P1 + FT_NQ - 1) / FT_NQ), 256);
   w.total = o;
   return w;
@@ -914,27 +929,30 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, TPG_EWORKSPACE,
               "knn: workspace must be 256-byte aligned for the tensor-core path");
   FeatWs w = feat_carve(workspace, k.B, k.P1, k.P2, k.D);
+  // tuning (tools/bench_knn_feat.py): TPG_KNN_STOP=n returns after the n-th stage (1 split, 2 tcgen05, 3 rank)
+  const char* stop_s = getenv("TPG_KNN_STOP");
+  const int stop = stop_s ? atoi(stop_s) : 99;
   {
-    // centre = mean of the candidate cloud (rows below its length); both operands are shifted by it
-    feat_mean_partial_kernel<<<dim3(FT_MEAN_CHUNKS, k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.D, w.part, w.nmax2, w.fb_count,
-                                                                         k.skip);
-    TPG_CHECK_LAUNCH("feat_mean_partial_kernel");
-    const int rows_per_cta = FT_SPLIT_ITERS * 256 / (k.D >> 2);
-    feat_split_kernel<<<dim3(ceil_div(k.P2, rows_per_cta), k.B), 256, 0, st>>>(k.p2, k.len2, k.P2, k.P2, k.D, w.part,
-                                                                              w.split2, w.nrm2, w.nmax2, k.skip);
+    // centre = sampled mean of the candidate cloud (rows below its length); both operands are shifted by it
+    const int rows_per_it = 256 / (k.D >> 2);
+    auto split_ctas = [&](int P) { return max(1, min(FT_NMAX_PARTS, ceil_div(P, rows_per_it))); };
+    feat_split_kernel<<<dim3(split_ctas(k.P2), k.B), 256, 0, st>>>(k.p2, k.p2, k.len2, k.P2, k.P2, k.D, w.split2, w.nrm2,
+                                                                  w.nmax2, k.skip);
     TPG_CHECK_LAUNCH("feat_split_kernel");
     if (k.p1 == k.p2 && k.P1 == k.P2) {
       w.nrm1 = w.nrm2;  // self search: one pre-pass
       w.split1 = w.split2;
     } else {
-      feat_split_kernel<<<dim3(ceil_div(k.P1, rows_per_cta), k.B), 256, 0, st>>>(k.p1, k.len2, k.P2, k.P1, k.D, w.part,
-                                                                                w.split1, w.nrm1, nullptr, k.skip);
+      feat_split_kernel<<<dim3(split_ctas(k.P1), k.B), 256, 0, st>>>(k.p1, k.p2, k.len2, k.P2, k.P1, k.D, w.split1, w.nrm1,
+                                                                    nullptr, k.skip);
       TPG_CHECK_LAUNCH("feat_split_kernel");
     }
   }
+  if (stop <= 1) return TPG_OK;
   FeatArgs a{k.p1, k.p2, k.len1, k.len2, k.B, k.P1, k.P2, k.D, k.K, w.nrm1, w.nrm2, w.nmax2,
-             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, getenv("TPG_KNN_DBG") ? w.dbg : nullptr, k.skip};
-  const size_t aux = max((size_t)FT_NQ * 64 * sizeof(float), (size_t)FT_NQ * FT_CAP * sizeof(float2));
+             k.dists, reinterpret_cast<int64_t*>(k.idx), w.fb_count, w.fb_list, w.masks, w.tau0, ceil_div(k.P2, FT_TM),
+             getenv("TPG_KNN_DBG") ? w.dbg : nullptr, k.skip};
+  const size_t aux = (size_t)FT_NQ * 64 * sizeof(float);
   const size_t smem = (size_t)k.D * 512 * FT_STAGES + (size_t)k.D * 4 * FT_NQ + 1024 + aux;
   auto kern = k.D == 32 ? knn_feat_tc_kernel<32> : knn_feat_tc_kernel<64>;
   TPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -945,6 +963,16 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
               TPG_ECUDA, "knn: cuTensorMapEncodeTiled failed");
   kern<<<grid, FT_BLOCK, smem, st>>>(a, maps);
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
+  if (stop <= 2) return TPG_OK;
+  {
+    const long long nq = (long long)k.B * k.P1;
+    const int rw = 256 / k.D;  // warps (queries) per CTA
+    const unsigned rblocks = (unsigned)((nq + rw - 1) / rw);
+    if (k.D == 32) knn_feat_rank_kernel<32><<<rblocks, rw * 32, 0, st>>>(a);
+    else knn_feat_rank_kernel<64><<<rblocks, rw * 32, 0, st>>>(a);
+    TPG_CHECK_LAUNCH("knn_feat_rank_kernel");
+  }
+  if (stop <= 3) return TPG_OK;
   if (k.D == 32) knn_feat_fallback_kernel<8><<<num_sms(), 512, 0, st>>>(a);
   else knn_feat_fallback_kernel<16><<<num_sms(), 512, 0, st>>>(a);
   TPG_CHECK_LAUNCH("knn_feat_fallback_kernel");

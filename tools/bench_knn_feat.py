@@ -23,9 +23,10 @@ for (B, P, D, K) in [(8, 2048, 32, 20), (8, 2048, 64, 12), (8, 2048, 32, 9), (8,
     dbg_bytes = ((16 * 8 * nct + 255) // 256) * 256
     dbg = ws[n - dbg_bytes: n - dbg_bytes + 128 * nct].view(torch.int64).view(nct, 16).cpu().numpy()
     ph = np.diff(dbg[:, :6], axis=1)
-    names = ["setup", "pass0", "tau0-select", "pass1", "final"]
+    names = ["setup", "pass0", "tau0-select", "pass1", "drain"]
     print(f"B={B} P={P} D={D} K={K}: call {a.elapsed_time(b) * 1e3:.1f} us; per-CTA cycles (mean/max): " +
           "  ".join(f"{nm}={ph[:, j].mean():.0f}/{ph[:, j].max():.0f}" for j, nm in enumerate(names)) +
           f"  total={(dbg[:, 5] - dbg[:, 0]).mean():.0f}  span={(dbg[:, 5].max() - dbg[:, 0].min())}")
     print('   issuer cycles per CTA: wait-full / wait-tmem-free / issue =', dbg[:, 8:11].mean(0).astype(int))
-    print('   flagged for exact fallback:', int(ws[256:260].view(torch.int32)[0]), 'of', B * P)
+    fo = lib.tpg_knn_fallback_count_offset(B)
+    print('   flagged for exact fallback:', int(ws[fo:fo + 4].view(torch.int32)[0]), 'of', B * P)
