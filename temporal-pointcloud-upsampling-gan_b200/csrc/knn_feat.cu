@@ -604,17 +604,26 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 // unrecorded candidate can enter (or tie into) the result.  Otherwise, or with more than FT_HCAP hits, the query
 // goes to the exact fallback.
 constexpr int FT_HCAP = 64;          // hits handled per query (two rounds of 32)
+constexpr int FT_RANK_WARPS = 8;
+
+// same bound as feat_eps with MUFU square roots (2 ulp; the 1.001 factors cover them)
+__device__ __forceinline__ float feat_eps_fast(float nq, float nmax, int D) {
+  const float xn = __frcp_rn(rsqrtf(nq)) * 1.001f, yn = __frcp_rn(rsqrtf(nmax)) * 1.001f;
+  const float s = xn + yn;
+  return 1.25f * (((float)(6 * D) * 1.1920929e-7f + 3.0517578e-5f) * xn * yn +
+                  (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
+}
+
 template <int DD>
-__global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank_kernel(FeatArgs a) {
-  constexpr int D = DD, cpr = D >> 2, lpr = cpr, rpi = 32 / lpr, rstride = D + 4;
-  constexpr int FT_RANK_WARPS = 256 / DD;  // 8 (D = 32) or 4 (D = 64) warps: < 48 KB of static shared memory
-  __shared__ __align__(16) float tile_s[FT_RANK_WARPS][32 * rstride + D];
+__global__ void __launch_bounds__(FT_RANK_WARPS * 32, 4) knn_feat_rank_kernel(FeatArgs a) {
+  constexpr int D = DD, cpr = D >> 2;
+  __shared__ __align__(16) float q_s[FT_RANK_WARPS][D];
+  __shared__ __align__(16) unsigned long long key_s[FT_RANK_WARPS][FT_HCAP];
   __shared__ int cand_s[FT_RANK_WARPS][FT_HCAP];
   if (a.skip && *a.skip) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long flat = (long long)blockIdx.x * FT_RANK_WARPS + warp;
-  if (flat >= (long long)a.B * a.P1) return;
-  const int b = (int)(flat / a.P1), qi = (int)(flat - (long long)b * a.P1);
+  const int b = blockIdx.y, qi = blockIdx.x * FT_RANK_WARPS + warp;
+  if (qi >= a.P1) return;
   const int K = a.K;
   const int n1 = a.len1 ? min((int)a.len1[b], a.P1) : a.P1;
   float* od = a.dists + ((size_t)b * a.P1 + qi) * K;
@@ -624,8 +633,9 @@ __global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank
     return;
   }
   const float INF = __int_as_float(0x7f800000);
-  float* wtile = &tile_s[warp][0];
+  float* wq = &q_s[warp][0];
   int* wcand = &cand_s[warp][0];
+  unsigned long long* wkey = &key_s[warp][0];
   const float* p2b = a.p2 + (size_t)b * a.P2 * D;
   // everything the tail needs is requested up front: the warp's chain is latency, not bandwidth
   const unsigned* mq = a.masks + (size_t)b * (size_t)(4 * a.T) * a.P1 + qi;
@@ -635,13 +645,39 @@ __global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank
   const float t0 = __ldg(a.tau0 + (size_t)b * a.P1 + qi);
   const float nq = __ldg(a.nrm1 + (size_t)b * a.P1 + qi);
   const unsigned nmax_bits = __reduce_max_sync(FULL, __ldg(a.nmax2 + (size_t)b * FT_NMAX_PARTS + lane));
-  float* wq = wtile + 32 * rstride;  // the query row
   if (lane < cpr) reinterpret_cast<float4*>(wq)[lane] = __ldg(reinterpret_cast<const float4*>(a.p1 + ((size_t)b * a.P1 + qi) * D) + lane);
-  // ---- candidate list from the hit masks (ascending candidate index) ----
-  int H = 0;
-  for (int w0 = 0; w0 < nwords; w0 += 32) {
+  // ---- candidate list from the hit masks (ascending candidate index); word w bit i = candidate 32 w + i ----
+  int H;
+  {
+    // the first 64 words (all of them up to 2048 candidates): both counts ride one scan
+    const int c0 = __popc(mw0), c1 = __popc(mw1);
+    int incl = c0 | (c1 << 16);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int tot = __shfl_sync(FULL, incl, 31);
+    const int tot0 = tot & 0xffff;
+    int pos = (incl & 0xffff) - c0;
+    while (mw0) {
+      const int bit = __ffs(mw0) - 1;
+      mw0 &= mw0 - 1;
+      if (pos < FT_HCAP) wcand[pos] = lane * 32 + bit;
+      ++pos;
+    }
+    pos = tot0 + (incl >> 16) - c1;
+    while (mw1) {
+      const int bit = __ffs(mw1) - 1;
+      mw1 &= mw1 - 1;
+      if (pos < FT_HCAP) wcand[pos] = (lane + 32) * 32 + bit;
+      ++pos;
+    }
+    H = tot0 + (tot >> 16);
+  }
+  for (int w0 = 64; w0 < nwords; w0 += 32) {  // clouds of more than 2048 candidates
     const int w = w0 + lane;
-    unsigned m = w0 == 0 ? mw0 : (w0 == 32 ? mw1 : (w < nwords ? __ldg(mq + (size_t)w * a.P1) : 0u));
+    unsigned m = w < nwords ? __ldg(mq + (size_t)w * a.P1) : 0u;
     const int c = __popc(m);
     int incl = c;
 #pragma unroll
@@ -660,66 +696,53 @@ __global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank
   }
   __syncwarp();
   bool ok = H <= FT_HCAP;
-  // ---- canonical distances, 32 candidates per round: rows arrive with coalesced 16-byte loads in a padded
-  //      per-warp tile, lane r then sums row r sequentially in d order ----
-  unsigned long long key0 = ~0ull, key1 = ~0ull;  // (d_canon bits, idx): d >= 0, so integer order == (d, idx) order
-  auto round = [&](int base_r) -> unsigned long long {
-    const int nr = min(32, H - base_r);
-    const int sub = lane / lpr, ch = lane - sub * lpr;
-    for (int r0 = 0; r0 < nr; r0 += 8 * rpi) {  // 8 independent loads in flight per lane
-      float4 v[8];
+  // ---- canonical distances: lane r reads the row of candidate r itself (16-byte loads, all requested before the
+  //      first is used) and sums it sequentially in d order; key = (d_canon bits, idx): d >= 0, so the integer
+  //      order of the keys is the (d, idx) order ----
+  auto canon = [&](int r) -> unsigned long long {
+    const int ci = wcand[r];
+    const float4* y = reinterpret_cast<const float4*>(p2b + (size_t)ci * D);
+    const float4* x = reinterpret_cast<const float4*>(wq);
+    float acc = 0.0f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + u * rpi + sub;
-        if (r < nr) v[u] = __ldg(reinterpret_cast<const float4*>(p2b + (size_t)wcand[base_r + r] * D) + ch);
-      }
+    for (int h = 0; h < cpr; h += 8) {
+      float4 yv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + u * rpi + sub;
-        if (r < nr) *reinterpret_cast<float4*>(wtile + r * rstride + ch * 4) = v[u];
+      for (int c = 0; c < 8; ++c) yv[c] = __ldg(y + h + c);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 x0 = x[h + c];
+        acc = sq_acc(acc, x0.x, yv[c].x);
+        acc = sq_acc(acc, x0.y, yv[c].y);
+        acc = sq_acc(acc, x0.z, yv[c].z);
+        acc = sq_acc(acc, x0.w, yv[c].w);
       }
     }
-    __syncwarp();
-    unsigned long long key = ~0ull;
-    if (lane < nr) {
-      const float4* y = reinterpret_cast<const float4*>(wtile + lane * rstride);
-      const float4* x = reinterpret_cast<const float4*>(wq);
-      float acc = 0.0f;
-#pragma unroll 4
-      for (int c = 0; c < cpr; ++c) {
-        const float4 x0 = x[c], y0 = y[c];
-        acc = sq_acc(acc, x0.x, y0.x);
-        acc = sq_acc(acc, x0.y, y0.y);
-        acc = sq_acc(acc, x0.z, y0.z);
-        acc = sq_acc(acc, x0.w, y0.w);
-      }
-      key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)wcand[base_r + lane];
-    }
-    return key;
+    return ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)ci;
   };
+  unsigned long long key0 = ~0ull, key1 = ~0ull;
   if (ok) {
-    key0 = round(0);
-    if (H > 32) {
-      __syncwarp();  // the first round's readers are done with wtile
-      key1 = round(32);
-    }
+    if (lane < H) key0 = canon(lane);
+    if (H > 32 && lane + 32 < H) key1 = canon(lane + 32);  // (first test warp-uniform)
+    wkey[lane] = key0;
+    if (H > 32) wkey[lane + 32] = key1;
   }
-  // ---- rank by (d_canon, idx) ----
+  __syncwarp();
+  // ---- rank by (d_canon, idx): every lane walks the key list (broadcast 16-byte reads, two keys each) ----
   int rank0 = 0, rank1 = 0;
   if (ok) {
-    const int nA = min(H, 32), nB = H - nA;
-    if (nB == 0) {
-      for (int m2 = 0; m2 < nA; ++m2) rank0 += __shfl_sync(FULL, key0, m2) < key0 ? 1 : 0;
-    } else {
-      for (int m2 = 0; m2 < nA; ++m2) {
-        const unsigned long long o = __shfl_sync(FULL, key0, m2);
-        rank0 += o < key0 ? 1 : 0;
-        rank1 += o < key1 ? 1 : 0;
+    const int He = (H + 1) & ~1;  // the list is padded with ~0 keys up to 32 / 64 entries
+    const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(wkey);
+    if (H <= 32) {
+      for (int m2 = 0; m2 < He; m2 += 2) {
+        const ulonglong2 o = kp[m2 >> 1];
+        rank0 += (o.x < key0 ? 1 : 0) + (o.y < key0 ? 1 : 0);
       }
-      for (int m2 = 0; m2 < nB; ++m2) {
-        const unsigned long long o = __shfl_sync(FULL, key1, m2);
-        rank0 += o < key0 ? 1 : 0;
-        rank1 += o < key1 ? 1 : 0;
+    } else {
+      for (int m2 = 0; m2 < He; m2 += 2) {
+        const ulonglong2 o = kp[m2 >> 1];
+        rank0 += (o.x < key0 ? 1 : 0) + (o.y < key0 ? 1 : 0);
+        rank1 += (o.x < key1 ? 1 : 0) + (o.y < key1 ? 1 : 0);
       }
     }
     // K-th smallest canonical distance among the hits
@@ -729,7 +752,7 @@ __global__ void __launch_bounds__(256 * 32 / DD, DD == 32 ? 4 : 6) knn_feat_rank
     if (lane + 32 < H && rank1 < kk) top = max(top, (unsigned)(key1 >> 32));
     const float dk = __uint_as_float(__reduce_max_sync(FULL, top));
     if (t0 != INF) {  // tau0 == inf: every candidate of the cloud is a hit
-      const float eps = feat_eps(nq, __uint_as_float(nmax_bits), D);
+      const float eps = feat_eps_fast(nq, __uint_as_float(nmax_bits), D);
       // 1/16 more than eps covers the roundings of this very expression
       ok = H >= K && dk < (t0 + nq) - 1.0625f * eps;
     }
@@ -965,11 +988,9 @@ int knn_feat_dispatch(const KnnArgs& k, void* workspace, size_t workspace_bytes,
   TPG_CHECK_LAUNCH("knn_feat_tc_kernel");
   if (stop <= 2) return TPG_OK;
   {
-    const long long nq = (long long)k.B * k.P1;
-    const int rw = 256 / k.D;  // warps (queries) per CTA
-    const unsigned rblocks = (unsigned)((nq + rw - 1) / rw);
-    if (k.D == 32) knn_feat_rank_kernel<32><<<rblocks, rw * 32, 0, st>>>(a);
-    else knn_feat_rank_kernel<64><<<rblocks, rw * 32, 0, st>>>(a);
+    const dim3 rgrid(ceil_div(k.P1, FT_RANK_WARPS), k.B);
+    if (k.D == 32) knn_feat_rank_kernel<32><<<rgrid, FT_RANK_WARPS * 32, 0, st>>>(a);
+    else knn_feat_rank_kernel<64><<<rgrid, FT_RANK_WARPS * 32, 0, st>>>(a);
     TPG_CHECK_LAUNCH("knn_feat_rank_kernel");
   }
   if (stop <= 3) return TPG_OK;

@@ -70,3 +70,15 @@ for n in path:
     i = calls[n]["in"]
     shp = {k: v.get("shape") for k, v in i.items() if isinstance(v, dict) and "shape" in v}
     print(f"  {n:4d} {calls[n]['op']:11s} {dur[n]:8.1f} us  {shp} {({k: i[k] for k in ('K', 'npoint', 'nsample') if k in i})}")
+
+# ---- per (op, shape) table of the whole step (same measurements) ----
+agg = collections.defaultdict(list)
+for n, c in enumerate(calls):
+    i = c["in"]
+    shp = tuple((k, tuple(v["shape"])) for k, v in i.items() if isinstance(v, dict) and "shape" in v)
+    extra = tuple((k, i[k]) for k in ("K", "npoint", "nsample") if k in i)
+    agg[(c["op"], shp, extra)].append(dur[n])
+print("\nper (op, shape): count, mean us, total us")
+for (op, shp, extra), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    s = " ".join(f"{k}{list(sh)}" for k, sh in shp)
+    print(f"  {op:11s} x{len(v):3d} {np.mean(v):8.1f} us  {sum(v):9.1f} us  {s} {dict(extra) if extra else ''}")
