@@ -168,6 +168,52 @@ def group_reduce_bwd(grad_out, idx, arg, N, op=0):
     return g
 
 
+# --------------------------------------------------------------------------- conv-input assembly (K11 / K12)
+def group_assemble(parts, idx):
+    """The unfused composition the reference writes in torch — QueryAndGroup (discriminator.py:190, upstream
+    pointnet2_utils.QueryAndGroup.forward) and FlowEmbedding.forward (discriminator.py:270-277):
+    parts = [("gather", src [B,C,N], center [B,C,M] or None) | ("broadcast", src [B,C,M], None)], idx [B,M,k]
+    -> cat over channels of  src[idx] (- center)  /  src repeated along k.  Plain fp32 element ops."""
+    idx = _i32(idx)
+    k = idx.shape[2]
+    outs = []
+    for mode, src, center in parts:
+        src = _f32(src)
+        if mode == "gather":
+            outs.append(group_fwd(src, idx, center))
+        else:
+            outs.append(np.repeat(src[:, :, :, None], k, axis=3))
+    return np.concatenate(outs, axis=1)
+
+
+def _edge_pre(q, center, idx):
+    q, center, idx = _f32(q), _f32(center), _i32(idx)
+    B = q.shape[0]
+    qj = np.stack([q[b][:, idx[b]] for b in range(B)])            # [B,C,M,k]
+    return qj - center[:, :, :, None]                               # one fp32 subtraction per element
+
+
+def edge_affine_fwd(p, q, center, idx, slope):
+    """EdgeConv after the restructure (gcn_lib/pointnet/gcn.py:206-211): p[j] + LeakyReLU(q[j] - center_i), every
+    step a single fp32 operation in this order (sub, mul by slope on the negative side, add)."""
+    p, idx = _f32(p), _i32(idx)
+    pre = _edge_pre(q, center, idx)
+    act = np.where(pre > 0, pre, pre * np.float32(slope)).astype(np.float32)
+    pj = np.stack([p[b][:, idx[b]] for b in range(p.shape[0])])
+    return pj + act
+
+
+def edge_affine_bwd(grad_out, q, center, idx, slope):
+    """-> (g2 = grad_out * LeakyReLU'(q[j] - center_i), grad_center = -sum_j g2 summed sequentially in j)."""
+    g = _f32(grad_out)
+    pre = _edge_pre(q, center, idx)
+    g2 = np.where(pre > 0, g, g * np.float32(slope)).astype(np.float32)
+    acc = np.zeros(g2.shape[:3], np.float32)
+    for j in range(g2.shape[3]):
+        acc = acc + g2[..., j]
+    return g2, -acc
+
+
 # --------------------------------------------------------------------------- three_nn / interpolate
 def three_nn(unknown, known):
     unknown, known = _f32(unknown), _f32(known)

@@ -127,18 +127,19 @@ class QueryAndGroup(nn.Module):
         r"""xyz (B, N, 3), new_xyz (B, npoint, 3), features (B, C, N) -> (B, 3 + C, npoint, nsample)"""
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
         xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, C + 3, npoint, nsample)
-            else:
-                new_features = grouped_features
-        else:
+        centre = new_xyz.transpose(1, 2).contiguous()
+        if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz
-        return new_features
+        # one pass writes cat([xyz[idx] - new_xyz, features[idx]]) (K11, tpg_group_assemble_f32): no per-tensor
+        # [B,C,npoint,nsample] intermediates, no separate "- centre" pass, no torch.cat copy; same values
+        modes, tensors = [], []
+        if self.use_xyz or features is None:
+            modes.append("gather")
+            tensors += [xyz_trans, centre]
+        if features is not None:
+            modes.append("gather")
+            tensors += [features.contiguous(), None]
+        return F.GroupAssemble.apply(idx, tuple(modes), *tensors)
 
 
 class GroupAll(nn.Module):

@@ -189,9 +189,12 @@ def index_points_static(points, idx):
 class static_model_methods:
     """Context manager: rebinds the synchronising functions / methods of the reference's modules."""
 
-    def __init__(self, mods: Optional[Dict[str, Any]] = None, fused_idgcn: bool = True):
+    def __init__(self, mods: Optional[Dict[str, Any]] = None, fused_idgcn: bool = True, fused_flow: bool = True,
+                 restructured_edgeconv: bool = False):
         self.mods = mods or {}
         self.fused_idgcn = fused_idgcn
+        self.fused_flow = fused_flow
+        self.restructured_edgeconv = restructured_edgeconv
         self._undo: List = []
 
     def _mod(self, name):
@@ -213,12 +216,32 @@ class static_model_methods:
             if gcn is not None:
                 self._undo.append((gcn.IDGCNLayer, "forward", gcn.IDGCNLayer.forward))
                 gcn.IDGCNLayer.forward = _idgcn_forward_fused
+        if self.fused_flow and hasattr(dis, "FlowEmbedding"):  # conv input of the flow embedding in one pass (identical)
+            from .reference_patches import _flow_embedding_forward_fused
+
+            self._undo.append((dis.FlowEmbedding, "forward", dis.FlowEmbedding.forward))
+            dis.FlowEmbedding.forward = _flow_embedding_forward_fused
+        if self.restructured_edgeconv:  # per-node convs + K12 (fp32 reordering: not bit-identical)
+            from . import reference_patches as rp
+
+            gcn = sys.modules.get("gcn_lib.pointnet.gcn")
+            if gcn is not None:
+                if rp._EDGECONV_ORIGINAL[0] is None:
+                    rp._EDGECONV_ORIGINAL[0] = gcn.EdgeConv.forward
+                self._undo.append((gcn.EdgeConv, "forward", gcn.EdgeConv.forward))
+                gcn.EdgeConv.forward = rp._edgeconv_forward_restructured
+                self._restore_flag = rp._RESTRUCTURE_EDGECONV
+                rp._RESTRUCTURE_EDGECONV = True
         return self
 
     def __exit__(self, *exc):
         for obj, name, old in reversed(self._undo):
             setattr(obj, name, old)
         self._undo = []
+        if self.restructured_edgeconv:
+            from . import reference_patches as rp
+
+            rp._RESTRUCTURE_EDGECONV = getattr(self, "_restore_flag", False)
         return False
 
 
@@ -308,7 +331,7 @@ class GraphedFluidStep:
 
     def __init__(self, mods, sr_net, spatial_dis, tempo_dis, lowres_pos_lst, highres_pos_lst, opt, optims,
                  furthest_distance: float = 1.0, warmup: int = 3, capture: bool = True, overlap_frames: bool = False,
-                 fused_idgcn: bool = True):
+                 fused_idgcn: bool = True, fused_flow: bool = True, restructured_edgeconv: bool = False):
         self.mods, self.nets = mods, (sr_net, spatial_dis, tempo_dis)
         self.lowres = [t.clone() for t in lowres_pos_lst]
         self.highres = [t.clone() for t in highres_pos_lst]
@@ -324,7 +347,8 @@ class GraphedFluidStep:
         self.captured = False
         self.side_streams = [torch.cuda.Stream() for _ in range(self.frames - 1)] if overlap_frames else None
         self.g_out = self.d_out = None
-        self._patch = static_model_methods(mods, fused_idgcn=fused_idgcn)
+        self._patch = static_model_methods(mods, fused_idgcn=fused_idgcn, fused_flow=fused_flow,
+                                           restructured_edgeconv=restructured_edgeconv)
         self.graph_g = self.graph_d = None
         if capture:
             self._capture(warmup)

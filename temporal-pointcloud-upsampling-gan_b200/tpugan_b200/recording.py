@@ -78,6 +78,8 @@ class CallLog:
 def _keep(v):
     if isinstance(v, torch.Tensor):
         return v.detach().clone()
+    if isinstance(v, (list, tuple)):
+        return [_keep(x) for x in v]
     return v
 
 

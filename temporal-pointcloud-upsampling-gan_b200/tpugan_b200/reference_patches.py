@@ -19,10 +19,18 @@ reference site                                    rebound to
   FRNN x2 + DGL graph + SpMM per sample           reference's needs ``dgl``)
 ``train_step_final.interpolate_vel_lst`` (:51)    ``interpolation.interpolate_vel_lst``: one batched
   Python loop over frames x samples               launch per frame
+``FlowEmbedding.forward`` (discriminator.py:      conv input ``cat([pos2[idx] - pos1, feat2[idx],
+  252-283): 2 groupings, a subtraction, a         feat1 repeated])`` written in ONE pass by the
+  repeat and two torch.cat copies                 assembly kernel (K11); identical values
+``EdgeConv.forward`` (gcn.py:195-212), opt-in     algebraic restructure (K12): the two 1x1 convs run
+  (``edgeconv=True``): grouping, "- centre",      per node instead of per edge, the k-expanded sum
+  node_affine + edge_affine on [B,C,N,k]          ``P[j] + LeakyReLU(Q[j] - Q[i] + b)`` is one kernel
 ===============================================  ===================================================
 
 Results are identical to the unpatched run (indices bit-exact, values exact or <= 1e-5 for the
-interpolation); tests/test_surfaces_gpu.py checks each rebinding against the unpatched code.
+interpolation) — except the EdgeConv restructure, which reorders fp32 arithmetic (W(f_j - f_i) = W f_j - W f_i)
+and therefore is off by default and checked at 1e-5 relative; tests/test_surfaces_gpu.py checks each rebinding
+against the unpatched code.
 """
 from __future__ import annotations
 
@@ -34,11 +42,87 @@ import torch
 from . import gcn_dense, interpolation
 
 
+# EdgeConv layers take the restructured path (K12) while this is set (patch_reference(edgeconv=True) / graph step)
+_RESTRUCTURE_EDGECONV = False
+
+
+def edgeconv_restructurable(conv) -> bool:
+    """The restructure needs both affine branches to be exactly `1x1 conv -> LeakyReLU` (no norm layer between: a
+    BatchNorm over N*k columns has other statistics than one over N columns)."""
+    def ok(seq):
+        return (isinstance(seq, torch.nn.Sequential) and len(seq) == 2 and isinstance(seq[0], torch.nn.Conv2d)
+                and seq[0].kernel_size == (1, 1) and isinstance(seq[1], torch.nn.LeakyReLU))
+    return (getattr(conv, "norm", None) == "none" and ok(conv.node_affine) and ok(conv.edge_affine)
+            and conv.node_affine[1].negative_slope >= 0.0)
+
+
+def edgeconv_restructured(conv, feat, knn_idx):
+    """EdgeConv.forward (gcn_lib/pointnet/gcn.py:205-212) after the algebraic restructure, on a searched list:
+        node_affine(f_j) + edge_affine(f_j - f_i) = act(W_n f_j + b_n) + act(W_e f_j - W_e f_i + b_e)
+    so with P = node_affine(f) and Q = W_e f + b_e computed per NODE ([B,C',N], N columns instead of N*k) the
+    k-expanded tensor is  P[j] + act(Q[j] - (Q[i] - b_e))  — one kernel (F.EdgeAffine, K12), no `grouped`, `edge_feat`,
+    conv outputs or activations of size [B,C,N,k].  Each conv module is called exactly once, as in the reference, so
+    spectral-norm power iterations advance identically."""
+    from . import functional as F
+
+    idx = knn_idx.type(torch.int32).contiguous()
+    x = feat.unsqueeze(-1)                                   # [B,C,N,1]
+    p = conv.node_affine(x).squeeze(-1).contiguous()         # act(W_n f + b_n)
+    econv, eact = conv.edge_affine[0], conv.edge_affine[1]
+    q = econv(x).squeeze(-1).contiguous()                    # W_e f + b_e
+    centre = q if econv.bias is None else (q - econv.bias.view(1, -1, 1)).contiguous()
+    out = F.EdgeAffine.apply(p, q, centre, idx, float(eact.negative_slope))
+    return conv.aggregate_fn(conv.mlp(out))
+
+
+def _edgeconv_forward_restructured(self, feat, pos=None):
+    """EdgeConv.forward (gcn_lib/pointnet/gcn.py:195-212): the search as in the reference, then the restructured body."""
+    if not edgeconv_restructurable(self):
+        return _EDGECONV_ORIGINAL[0](self, feat, pos)
+    if len(feat.shape) == 4 and feat.shape[-1] == 1:
+        feat = feat.squeeze(-1)
+    feat_t = feat.permute(0, 2, 1).contiguous()
+    knn_idx = self.dilated_knn_graph(pos if pos is not None else feat_t)
+    return edgeconv_restructured(self, feat_t.permute(0, 2, 1).contiguous(), knn_idx)
+
+
+_EDGECONV_ORIGINAL: List[Any] = [None]
+
+
+def _flow_embedding_forward_fused(self, pos1, pos2, feature1, feature2, radius):
+    """FlowEmbedding.forward (discriminator.py:252-283) with its conv input — cat([pos2[idx] - pos1, feat2[idx],
+    feat1 repeated over the 32 samples]) — written in one pass (K11).  Everything else is the layer's own code."""
+    import torch.nn.functional as Fn
+
+    from . import functional as F
+
+    # the reference's module (its ball_query_wrapper may itself be rebound): the class remembers where it lives
+    dis = sys.modules.get(type(self).__module__) or sys.modules["discriminator"]
+    pos1_t = pos1.permute(0, 2, 1).contiguous()
+    pos2_t = pos2.permute(0, 2, 1).contiguous()
+    B, N, C = pos1_t.shape
+    idx = dis.ball_query_wrapper(radius, 32, pos1_t, pos2_t)  # idx is use to index pos2
+    idx = idx.type(torch.int32).contiguous()
+    if self.corr_func != 'concat':
+        raise NotImplementedError("FlowEmbedding: only corr_func='concat' exists in the reference")
+    feat1_new = F.GroupAssemble.apply(idx, ("gather", "gather", "broadcast"),
+                                      pos2.contiguous(), pos1.contiguous().view(B, -1, N),
+                                      feature2.contiguous(), None,
+                                      feature1.contiguous().view(B, -1, N), None)  # [B, 2*C+3, N, S]
+    for i, conv in enumerate(self.mlp_convs):
+        bn = self.mlp_bns[i]
+        feat1_new = Fn.leaky_relu(bn(conv(feat1_new)))
+    feat1_new = torch.max(feat1_new, -1)[0]  # [B, mlp[-1], npoint]
+    return pos1, feat1_new
+
+
 def _edgeconv_with_idx(conv, feat, knn_idx):
     """EdgeConv.forward (gcn_lib/pointnet/gcn.py:195-212) on a neighbour list that was searched already: feat [B,C,N],
     knn_idx int64 [B,N,k] (already dilated).  Same ops in the same order as the reference from the cast on."""
     from pointnet2_ops.pointnet2_utils import grouping_operation
 
+    if _RESTRUCTURE_EDGECONV and edgeconv_restructurable(conv):
+        return edgeconv_restructured(conv, feat, knn_idx)
     knn_idx = knn_idx.type(torch.int32).contiguous()
     center_feat = feat.unsqueeze(-1)
     grouped = grouping_operation(feat, knn_idx)
@@ -93,15 +177,20 @@ class PatchHandle:
         self.applied.append(label)
 
     def unpatch(self):
+        global _RESTRUCTURE_EDGECONV
         for obj, name, old in reversed(self._undo):
             setattr(obj, name, old)
         self._undo, self.applied = [], []
+        _RESTRUCTURE_EDGECONV = False
 
 
 def patch_reference(mods: Optional[Dict[str, Any]] = None, ball_query: bool = True, idgcn: bool = True,
-                    interpolation_kernel: bool = True) -> PatchHandle:
+                    interpolation_kernel: bool = True, flow_embedding: bool = True, edgeconv: bool = False) -> PatchHandle:
     """Rebind the names listed in the module docstring inside the reference's imported modules (looked up in
-    ``mods`` — a dict of modules as returned by tools/refstep.import_reference — or in ``sys.modules``)."""
+    ``mods`` — a dict of modules as returned by tools/refstep.import_reference — or in ``sys.modules``).
+    ``edgeconv=True`` additionally switches every eligible EdgeConv to the algebraic restructure (not bit-identical:
+    fp32 reordering, <= 1e-5 relative)."""
+    global _RESTRUCTURE_EDGECONV
     def mod(name):
         if mods and name in mods:
             return mods[name]
@@ -115,6 +204,13 @@ def patch_reference(mods: Optional[Dict[str, Any]] = None, ball_query: bool = Tr
         h._set(dis, "ball_query_wrapper", gcn_dense.ball_query_wrapper, "discriminator.ball_query_wrapper -> one kNN search")
     if idgcn and gcn is not None:
         h._set(gcn.IDGCNLayer, "forward", _idgcn_forward_fused, "IDGCNLayer.forward -> fused gather+max")
+    if flow_embedding and dis is not None and hasattr(dis, "FlowEmbedding"):
+        h._set(dis.FlowEmbedding, "forward", _flow_embedding_forward_fused, "FlowEmbedding.forward -> one-pass conv input (K11)")
+    if edgeconv and gcn is not None:
+        if _EDGECONV_ORIGINAL[0] is None:
+            _EDGECONV_ORIGINAL[0] = gcn.EdgeConv.forward
+        h._set(gcn.EdgeConv, "forward", _edgeconv_forward_restructured, "EdgeConv.forward -> per-node convs + K12")
+        _RESTRUCTURE_EDGECONV = True
     if interpolation_kernel:
         for m in (gl, gli, tsf):
             h._set(m, "cubic_interpolation", interpolation.cubic_interpolation, f"{getattr(m, '__name__', '?')}.cubic_interpolation -> K10")

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared_functions():
         assert hasattr(lib, name), name
     lib.tpg_abi_version.restype = ctypes.c_int
-    assert lib.tpg_abi_version() == built.ABI_VERSION == 8  # host-only call
+    assert lib.tpg_abi_version() == built.ABI_VERSION == 9  # host-only call
 
 
 def test_library_is_sm100a_only(built):

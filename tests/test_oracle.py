@@ -349,3 +349,46 @@ def test_oracle_grouping_and_chamfer_equal_torch_formulations(oracle):
     a, b = synth.fluid_cloud(rng, 2, 300), synth.fluid_cloud(rng, 2, 500)
     t = float(_tf().chamfer(torch.from_numpy(a).double(), torch.from_numpy(b).double()))
     assert abs(float(oracle.chamfer_distance(a, b, bidirectional=True)) - t) <= 1e-5 * abs(t)
+
+
+def test_assembly_oracles_equal_the_torch_compositions_of_the_reference(oracle):
+    """K11 / K12 restatements vs the reference's own torch expressions: QueryAndGroup / FlowEmbedding's cat
+    (discriminator.py:270-277) and EdgeConv's node_affine + edge_affine on grouped tensors (gcn.py:206-211)."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    B, N, M, k, C = 2, 50, 20, 6, 5
+    idx = rng.integers(0, N, (B, M, k)).astype(np.int32)
+    pos2 = rng.standard_normal((B, 3, N)).astype(np.float32)
+    pos1 = rng.standard_normal((B, 3, M)).astype(np.float32)
+    f2 = rng.standard_normal((B, C, N)).astype(np.float32)
+    f1 = rng.standard_normal((B, C, M)).astype(np.float32)
+    tidx = torch.from_numpy(idx).long()
+
+    def group(f):  # grouping_operation in plain torch
+        return torch.stack([torch.from_numpy(f[b])[:, tidx[b]] for b in range(B)])
+
+    ref = torch.cat([group(pos2) - torch.from_numpy(pos1).view(B, -1, M, 1),
+                     torch.cat([group(f2), torch.from_numpy(f1).view(B, -1, M, 1).repeat(1, 1, 1, k)], dim=1)], dim=1)
+    out = oracle.group_assemble([("gather", pos2, pos1), ("gather", f2, None), ("broadcast", f1, None)], idx)
+    assert np.array_equal(out, ref.numpy())
+
+    # EdgeConv: act(Wn f_j + bn) + act(We (f_j - f_i) + be) in float64 vs the restructured form
+    Cin, Co = 7, 4
+    f = rng.standard_normal((B, Cin, N))
+    idn = rng.integers(0, N, (B, N, k)).astype(np.int32)
+    Wn, We = rng.standard_normal((Co, Cin)), rng.standard_normal((Co, Cin))
+    bn, be = rng.standard_normal(Co), rng.standard_normal(Co)
+    lrelu = lambda v: np.where(v > 0, v, 0.2 * v)
+    grouped = np.stack([f[b][:, idn[b]] for b in range(B)])             # [B,Cin,N,k]
+    edge = grouped - f[:, :, :, None]
+    ref64 = lrelu(np.einsum("oc,bcnk->bonk", Wn, grouped) + bn[None, :, None, None]) + \
+        lrelu(np.einsum("oc,bcnk->bonk", We, edge) + be[None, :, None, None])
+    p = lrelu(np.einsum("oc,bcn->bon", Wn, f) + bn[None, :, None])
+    q = np.einsum("oc,bcn->bon", We, f) + be[None, :, None]
+    got = oracle.edge_affine_fwd(p.astype(np.float32), q.astype(np.float32), (q - be[None, :, None]).astype(np.float32), idn, 0.2)
+    assert np.abs(got - ref64).max() <= 1e-5 * np.abs(ref64).max()
+    g = rng.standard_normal(got.shape).astype(np.float32)
+    g2, gc = oracle.edge_affine_bwd(g, q.astype(np.float32), (q - be[None, :, None]).astype(np.float32), idn, 0.2)
+    pre = np.stack([q[b][:, idn[b]] for b in range(B)]) - (q - be[None, :, None])[:, :, :, None]
+    assert np.allclose(g2, np.where(pre > 0, g, 0.2 * g), rtol=1e-6, atol=1e-7) and np.allclose(gc, -g2.sum(-1), rtol=1e-5, atol=1e-5)

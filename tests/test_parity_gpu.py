@@ -534,6 +534,71 @@ def test_group_reduce_fwd_bwd(F, oracle, op, B, C, N, M, k):
     np.testing.assert_array_equal(gb.cpu().numpy(), ob)
 
 
+# ----------------------------------------------------------------------------- conv-input assembly (K11 / K12)
+ASSEMBLE_CASES = [
+    # B, M, k, parts: (mode, C, N, with_center)
+    (2, 100, 16, [("gather", 3, 1200, True), ("gather", 6, 1200, False)]),                     # QueryAndGroup
+    (2, 256, 32, [("gather", 3, 256, True), ("gather", 64, 256, False), ("broadcast", 64, 0, False)]),  # FlowEmbedding
+    (1, 33, 7, [("gather", 5, 77, True)]),                                                       # L % 4 != 0
+    (1, 50, 4, [("broadcast", 2, 0, False), ("gather", 9, 30000, False)]),                       # rows beyond shared memory
+    (3, 128, 16, [("gather", 130, 512, False), ("gather", 3, 512, True)]),
+]
+
+
+@pytest.mark.parametrize("B,M,k,spec", ASSEMBLE_CASES)
+def test_group_assemble(F, oracle, B, M, k, spec):
+    rng = np.random.default_rng(B * 1000 + M + k)
+    ns = [n for (m, _, n, _) in spec if m == "gather"]
+    idx = rng.integers(0, min(ns), (B, M, k)).astype(np.int32)
+    parts_np, parts_t = [], []
+    for mode, C, N, wc in spec:
+        src = rng.standard_normal((B, C, N if mode == "gather" else M)).astype(np.float32)
+        cen = rng.standard_normal((B, C, M)).astype(np.float32) if wc else None
+        parts_np.append((mode, src, cen))
+        parts_t.append((mode, cu(src), None if cen is None else cu(cen)))
+    out = F.group_assemble(parts_t, cu(idx)).cpu().numpy()
+    assert np.array_equal(out, oracle.group_assemble(parts_np, idx))
+
+
+def test_group_assemble_autograd(F, oracle):
+    rng = np.random.default_rng(5)
+    B, N, M, k, C = 2, 300, 64, 8, 10
+    idx = rng.integers(0, N, (B, M, k)).astype(np.int32)
+    xyz = cu(rng.standard_normal((B, 3, N)).astype(np.float32)).requires_grad_(True)
+    cen = cu(rng.standard_normal((B, 3, M)).astype(np.float32)).requires_grad_(True)
+    f2 = cu(rng.standard_normal((B, C, N)).astype(np.float32)).requires_grad_(True)
+    f1 = cu(rng.standard_normal((B, C, M)).astype(np.float32)).requires_grad_(True)
+    out = F.GroupAssemble.apply(cu(idx), ("gather", "gather", "broadcast"), xyz, cen, f2, None, f1, None)
+    w = cu(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+    (out * w).sum().backward()
+    wn = w.cpu().numpy()
+    assert rel_err(xyz.grad.cpu().numpy(), oracle.group_bwd(np.ascontiguousarray(wn[:, :3]), idx, N)) <= RTOL
+    assert rel_err(f2.grad.cpu().numpy(), oracle.group_bwd(np.ascontiguousarray(wn[:, 3:3 + C]), idx, N)) <= RTOL
+    assert rel_err(cen.grad.cpu().numpy(), -wn[:, :3].astype(np.float64).sum(-1)) <= RTOL
+    assert rel_err(f1.grad.cpu().numpy(), wn[:, 3 + C:].astype(np.float64).sum(-1)) <= RTOL
+
+
+@pytest.mark.parametrize("B,C,N,k", [(2, 16, 2048, 20), (1, 7, 300, 10), (2, 32, 2048, 9), (1, 4, 30000, 4)])
+def test_edge_affine_forward_backward(F, oracle, B, C, N, k):
+    rng = np.random.default_rng(C * 100 + k)
+    idx = rng.integers(0, N, (B, N, k)).astype(np.int32)
+    p = rng.standard_normal((B, C, N)).astype(np.float32)
+    q = rng.standard_normal((B, C, N)).astype(np.float32)
+    cen = (q - rng.standard_normal((1, C, 1)).astype(np.float32)).astype(np.float32)
+    out = F.edge_affine_fwd(cu(p), cu(q), cu(cen), cu(idx), 0.2).cpu().numpy()
+    assert np.array_equal(out, oracle.edge_affine_fwd(p, q, cen, idx, 0.2))
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    g2, gc = F.edge_affine_bwd(cu(g), cu(q), cu(cen), cu(idx), 0.2)
+    o2, oc = oracle.edge_affine_bwd(g, q, cen, idx, 0.2)
+    assert np.array_equal(g2.cpu().numpy(), o2) and np.array_equal(gc.cpu().numpy(), oc)
+    # autograd: d/dp, d/dq, d/dcenter of sum(out * g)
+    tp, tq, tc = (cu(a).requires_grad_(True) for a in (p, q, cen))
+    (F.EdgeAffine.apply(tp, tq, tc, cu(idx), 0.2) * cu(g)).sum().backward()
+    assert rel_err(tp.grad.cpu().numpy(), oracle.group_bwd(g, idx, N)) <= RTOL
+    assert rel_err(tq.grad.cpu().numpy(), oracle.group_bwd(o2, idx, N)) <= RTOL
+    assert np.array_equal(tc.grad.cpu().numpy(), oc)
+
+
 # ----------------------------------------------------------------------------- three_nn / interpolate
 @pytest.mark.parametrize("B,n,m", [(2, 500, 128), (1, 2048, 512), (1, 10, 3), (2, 64, 2), (2, 3000, 2048), (1, 8192, 4096),
                                    (1, 3000, 20000)])

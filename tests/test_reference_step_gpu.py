@@ -21,10 +21,14 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 pytestmark = pytest.mark.gpu
 
-# boundary calls of one full G+D step (tests/golden/*_step_schedule.json)
-FLUID_COUNTS = {"knn": 42, "group": 105, "frnn": 11, "chamfer": 1, "fps": 27, "gather": 27, "ball_query": 27,
-                "group_bwd": 66, "gather_bwd": 9, "chamfer_bwd": 1}
-ACTION_COUNTS = {"knn": 36, "group": 99, "frnn": 9, "chamfer": 1, "fps": 27, "gather": 27, "ball_query": 27}
+# boundary calls of one full G+D step (tests/golden/*_step_schedule.json).  The reference's 105 (99)
+# grouping_operation calls include the two of every QueryAndGroup (discriminator.py:190), which the drop-in
+# pointnet2_utils.QueryAndGroup writes in one assembly pass: verify_calls.grouping_equivalents counts those back.
+FLUID_COUNTS = {"knn": 42, "frnn": 11, "chamfer": 1, "fps": 27, "gather": 27, "ball_query": 27,
+                "group_bwd": 66, "gather_bwd": 9, "chamfer_bwd": 1, "group_assemble": 27}
+FLUID_GROUPINGS = 105
+ACTION_COUNTS = {"knn": 36, "frnn": 9, "chamfer": 1, "fps": 27, "gather": 27, "ball_query": 27, "group_assemble": 27}
+ACTION_GROUPINGS = 99
 
 
 @pytest.fixture(scope="module")
@@ -72,8 +76,9 @@ def test_reference_fluid_step_gpu(torch_cuda, oracle, B, n_lo, ratio):
     assert all(_changed(before, ctx.networks())), "an optimiser did not step"
     got = verify_calls.counts(calls)
     extra = {k: v for k, v in got.items() if k not in FLUID_COUNTS}
-    assert set(extra) <= {"gather_rows"}, extra  # index_points is plain torch indexing in the reference
+    assert set(extra) <= {"gather_rows", "group"}, extra  # index_points is plain torch indexing in the reference
     assert {k: got.get(k, 0) for k in FLUID_COUNTS} == FLUID_COUNTS
+    assert verify_calls.grouping_equivalents(calls) == FLUID_GROUPINGS
     # the hard-mask path padded with (999,999,999) dummies and FPS met them
     fps_in = [c.inputs["xyz"] for c in calls if c.op == "fps"]
     assert any(bool((x == 999).any()) for x in fps_in), "no dummy block reached FPS"
@@ -96,6 +101,7 @@ def test_reference_action_step_gpu(torch_cuda, oracle):
     assert all(_changed(before, ctx.networks()))
     got = verify_calls.counts(calls)
     assert {k: got.get(k, 0) for k in ACTION_COUNTS} == ACTION_COUNTS
+    assert verify_calls.grouping_equivalents(calls) == ACTION_GROUPINGS
     assert got.get("group_bwd", 0) > 0 and got.get("chamfer_bwd", 0) == 1
     verify_calls.check_log(oracle, calls)
 

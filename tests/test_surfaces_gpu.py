@@ -330,12 +330,98 @@ def test_patch_reference_equals_unpatched(oracle):
         calls = log.stop()
         assert all(np.isfinite(v) for v in losses.values())
         cnt = verify_calls.counts(calls)
-        assert cnt["frnn"] == 2 and cnt["group_reduce"] == 6 and cnt["group_reduce_bwd"] == 6 and cnt["group"] == 99, cnt
+        assert cnt["frnn"] == 2 and cnt["group_reduce"] == 6 and cnt["group_reduce_bwd"] == 6, cnt
+        # 105 groupings - 6 fused into gather+max; QueryAndGroup (27) and FlowEmbedding (9) assemble theirs in one pass
+        assert verify_calls.grouping_equivalents(calls) == 99 and cnt["group_assemble"] == 36, cnt
         assert cnt["knn"] == 42 - 12, cnt  # 2 IDGCN layers x 3 frames x 2 repeated searches saved
         verify_calls.check_log(oracle, calls)
     finally:
         h.unpatch()
     assert dis.ball_query_wrapper is not None and gcn.IDGCNLayer.forward.__name__ == "forward"
+
+
+def test_flow_embedding_and_edgeconv_patches(oracle):
+    """f3 / f2: FlowEmbedding's conv input assembled in one pass (identical), EdgeConv after the algebraic restructure
+    (fp32 reordering: 1e-5) — each against the reference's unpatched layer."""
+    import refstep
+    import tpugan_b200
+    import verify_calls
+    from tpugan_b200.recording import log
+
+    mods = refstep.import_reference("cuda")
+    dis = mods["discriminator"]
+    gcn = sys.modules["gcn_lib.pointnet.gcn"]
+    rng = np.random.default_rng(23)
+    torch.manual_seed(5)
+    # fp32 convolutions: with cuDNN's default TF32 the two orders of operation differ by the TF32 rounding itself
+    # (W f_j - W f_i rounds relative to |f|, W (f_j - f_i) relative to |f_j - f_i|: ~3e-4 of the output here)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    B, N, C = 2, 256, 16
+    flow = dis.FlowEmbedding(C, [C, 32, 32], sn=False).cuda()
+    pos1 = cu(synth.fluid_cloud(rng, B, N).transpose(0, 2, 1))
+    pos2 = cu(synth.fluid_cloud(rng, B, N).transpose(0, 2, 1))
+    f1, f2 = (cu(rng.standard_normal((B, C, N)).astype(np.float32)) for _ in range(2))
+    edge = gcn.EdgeConv(32, 32, k=20, dilation=2, aggregate='max', mlp_layer=True, bn=False, insn=False).cuda()
+    edge_sn = gcn.EdgeConv(3, 32, k=12, dilation=1, aggregate='max', mlp_layer=False, bn=False, insn=False, sn=True).cuda()
+    edge_bn = gcn.EdgeConv(32, 32, k=8, bn=True).cuda()
+    x = cu(rng.standard_normal((B, 32, 1100)).astype(np.float32))
+    xp = cu(synth.fluid_cloud(rng, B, 1100).transpose(0, 2, 1))
+
+    def run_flow():
+        a, b, c, d = (t.clone().requires_grad_(True) for t in (pos1, pos2, f1, f2))
+        _, y = flow(a, b, c, d, 0.05)
+        y.square().sum().backward()
+        return y.detach(), [t.grad.clone() for t in (a, b, c, d)], [p.grad.clone() for p in flow.parameters()]
+
+    def run_edge(layer, inp):
+        layer.zero_grad()
+        t = inp.clone().requires_grad_(True)
+        y = layer(t)
+        y.square().sum().backward()
+        return y.detach(), t.grad.clone(), [p.grad.clone() for p in layer.parameters()]
+
+    flow.zero_grad()
+    y0, gi0, gp0 = run_flow()
+    e0 = run_edge(edge, x)
+    edge_sn.eval()  # spectral norm: no power-iteration update between the two runs
+    s0 = run_edge(edge_sn, xp)
+    b0 = run_edge(edge_bn, x)
+    h = tpugan_b200.patch_reference(mods, edgeconv=True)
+    try:
+        assert any("FlowEmbedding" in a for a in h.applied) and any("EdgeConv" in a for a in h.applied), h.applied
+        flow.zero_grad()
+        log.start(capture=True)
+        y1, gi1, gp1 = run_flow()
+        calls = log.stop()
+        cnt = verify_calls.counts(calls)
+        assert cnt.get("group_assemble") == 1 and cnt.get("group", 0) == 0, cnt
+        verify_calls.check_log(oracle, calls)
+        assert torch.equal(y1, y0)  # same values into the same convolutions
+        for a, b in zip(gi1 + gp1, gi0 + gp0):
+            close(a, b.cpu().numpy(), rtol=1e-4)
+        log.start(capture=True)
+        e1 = run_edge(edge, x)
+        calls = log.stop()
+        cnt = verify_calls.counts(calls)
+        assert cnt.get("edge_affine") == 1 and cnt.get("edge_affine_bwd") == 1 and cnt.get("group", 0) == 0, cnt
+        verify_calls.check_log(oracle, calls)
+        close(e1[0], e0[0].cpu().numpy(), rtol=1e-5)
+        close(e1[1], e0[1].cpu().numpy(), rtol=1e-4)
+        for a, b in zip(e1[2], e0[2]):
+            close(a, b.cpu().numpy(), rtol=1e-4)
+        s1 = run_edge(edge_sn, xp)  # spectral-normalised 1x1 convs, search on positions, single-conv mlp
+        close(s1[0], s0[0].cpu().numpy(), rtol=1e-5)
+        close(s1[1], s0[1].cpu().numpy(), rtol=1e-4)
+        log.start(capture=True)
+        b1 = run_edge(edge_bn, x)    # BatchNorm inside the affine branches: not restructurable, reference path taken
+        cnt = verify_calls.counts(log.stop())
+        assert cnt.get("edge_affine", 0) == 0 and cnt.get("group") == 1, cnt
+        close(b1[0], b0[0].cpu().numpy(), rtol=1e-5)
+    finally:
+        h.unpatch()
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert gcn.EdgeConv.forward.__name__ == "forward" and dis.FlowEmbedding.forward.__name__ == "forward"
 
 
 # ---------------------------------------------------------------------------------------- f4: GPU data pipeline

@@ -74,6 +74,19 @@ def check_call(oracle, c) -> str:
         ref = oracle.group_reduce_bwd(i["grad_out"], i["idx"], i["arg"], i["N"], i["op"])
         _close(o["grad_f"], ref, op)
         return "grad 1e-5"
+    if op == "group_assemble":
+        parts = list(zip(i["modes"], [_np(t) for t in c.inputs["srcs"]], [_np(t) for t in c.inputs["centers"]]))
+        assert np.array_equal(o["out"], oracle.group_assemble(parts, i["idx"])), "group_assemble values"
+        return "values exact"
+    if op == "edge_affine":
+        assert np.array_equal(o["out"], oracle.edge_affine_fwd(i["p"], i["q"], i["center"], i["idx"], i["slope"])), op
+        return "values exact"
+    if op == "edge_affine_bwd":
+        g2, gc = oracle.edge_affine_bwd(i["grad_out"], i["q"], i["center"], i["idx"], i["slope"])
+        assert np.array_equal(o["g2"], g2), "edge_affine_bwd g2"
+        if o.get("grad_center") is not None:
+            assert np.array_equal(o["grad_center"], gc), "edge_affine_bwd grad_center"
+        return "values exact"
     if op == "three_nn":
         d, idx = oracle.three_nn(i["unknown"], i["known"])
         assert np.array_equal(o["idx"], idx), "three_nn idx"
@@ -162,3 +175,15 @@ def counts(calls):
     for c in calls:
         out[c.op] = out.get(c.op, 0) + 1
     return out
+
+
+def grouping_equivalents(calls):
+    """Number of `grouping_operation` calls the log stands for: plain groupings plus the gather parts of every
+    one-pass assembly (QueryAndGroup = 2 groupings, FlowEmbedding = 2 groupings + a repeat)."""
+    n = 0
+    for c in calls:
+        if c.op == "group":
+            n += 1
+        elif c.op == "group_assemble":
+            n += sum(1 for m in c.inputs["modes"] if m == "gather")
+    return n
