@@ -440,6 +440,33 @@ def real_step_leg(args, world, rank, dev, batch, timed):
             del gs, ctx2
         except Exception as e:
             graphed = {"unavailable": repr(e)[:300]}
+        if graphed and "ms_per_step" in graphed:
+            # §8 row f2: the same captured step with every EdgeConv restructured (per-node 1x1 convs + K12): k times
+            # fewer convolution columns, no [B,C,N,k] intermediates in front of the shared MLP; fp32 reordering only
+            try:
+                torch.cuda.empty_cache()
+                ctx3 = refstep.build(domain, B=batch, n_lo=n_lo, ratio=ratio, backend="cuda", device=dev, seed=1 + rank, capturable=True)
+                gs = refstep.graphed_step(ctx3, capture=True, restructured_edgeconv=True)
+                it = [12]
+
+                def one_r():
+                    it[0] += 2
+                    return gs.step(it[0])
+
+                for _ in range(3):
+                    one_r()
+                ms_r = timed(one_r, steps, 0, flush=False)
+                rl = one_r()
+                graphed["restructured_edgeconv"] = {
+                    "train_steps_per_s": 1e3 / ms_r, "ms_per_step": ms_r,
+                    "what": "GraphedFluidStep(restructured_edgeconv=True): W(f_j - f_i) = W f_j - W f_i, EdgeConv's two "
+                            "k-expanded 1x1 convolutions run per node, K12 writes P[j] + LeakyReLU(Q[j] - Q[i] + b)",
+                    "losses": {k: float(v) for k, v in rl.items()}}
+                if ctx3.hook is not None:
+                    ctx3.hook.remove()
+                del gs, ctx3
+            except Exception as e:
+                graphed["restructured_edgeconv"] = {"unavailable": repr(e)[:300]}
         ctx = None
     if ctx is not None and ctx.hook is not None:
         ctx.hook.remove()

@@ -16,17 +16,19 @@
 // 15-34 %, centring + split 0.0 %.)  e only SELECTS candidates; the neighbours that are
 // returned are re-ranked with the canonical distance (sequential fp32, no FMA) on the ORIGINAL
 // rows, so indices and distances are identical to the brute-force kernel:
-//   * a first pass over the e-matrix yields, per query, a valid upper bound tau0 of the
-//     (K+8)-th smallest e; a second pass buffers every candidate with e <= tau0;
-//   * with T_K the K-th smallest buffered e and eps a rigorous bound on
-//     |e - E| + |d_canon - d_true|, every canonical top-K neighbour has e <= T_K + 2 eps
-//     (proof in DESIGN.md §4 K2); if T_K + 2 eps < tau0 the buffer is a superset and the K
-//     results are the (d_canon, idx)-smallest of its members inside the margin;
-//   * otherwise (near-duplicate features, huge norms, buffer overflow) the query goes to
-//     an exact SIMT fallback (a fraction of a percent of the queries on N(0,1) features).
+//   * pass 0 over the e-matrix keeps, per query, the minima of 64 disjoint candidate groups; the K smallest
+//     group minima are K distinct candidates, so their K-th smallest T bounds the K-th smallest e overall;
+//   * with eps a rigorous bound on |e - (d_true - |x|^2)| + |d_canon - d_true| (feat_eps), every canonical
+//     top-K neighbour has e <= T + 2 eps (proof in DESIGN.md §4 K2); pass 1 re-issues the MMAs and records,
+//     as one ballot per (query, 32 candidates), WHICH candidates have e <= tau0 = T + 2.25 eps
+//     (~K + 5 per query) — bit masks in global memory, no atomics, no per-hit stores;
+//   * knn_feat_rank_kernel (one warp per query, many warps per SM) expands the masks, sums the canonical
+//     distance of every hit and writes the K best by (d_canon, idx); it re-checks completeness on the
+//     canonical distances themselves (K-th smallest < tau0 + |x|^2 - eps) and sends a query with more than
+//     64 hits (near-duplicate features, huge norms) to the exact SIMT fallback kernel.
 //
-// Kernel anatomy (one CTA = 128 queries of one cloud, one wave of CTAs; 16 epilogue warps + one MMA-issuer warp
-// + one TMA-producer warp):
+// Kernel anatomy (knn_feat_tc_kernel: one CTA = 128 queries of one cloud, one wave of CTAs; 16 epilogue warps
+// + one MMA-issuer warp + one TMA-producer warp):
 //   MMA shape M=128 (candidates) x N=128 (queries) x K=16 (bf16) per instruction, cta_group::1.
 //   Candidates are the M operand on purpose: TMEM lane == candidate, so a thread owns one
 //   candidate row of the accumulator tile and sweeps its queries without any cross-lane
@@ -37,10 +39,11 @@
 //     full[stage]   TMA -> MMA issuer            tile landed
 //     done[buf]     tcgen05.commit -> epilogue, producer   accumulator ready, smem stage free
 //     tfree[buf]    16 epilogue warps -> MMA issuer         accumulator drained (tcgen05.ld complete)
-//   issuer warp (one thread): for every tile u: wait full / tfree, issue 4 x D/16 MMAs, commit;
-//   producer warp (one thread): wait done(u), TMA tile u+4 into the stage MMA(u) read;
-//   epilogue warps: wait done(u); tcgen05.ld -> registers; per-lane min (pass 0) / predicated append
-//   (pass 1); arrive tfree(u).
+//   issuer warp (warp-uniform control flow, one elected lane): for every tile u: wait full / tfree, issue
+//     3 x D/16 MMAs back to back from uniform registers, commit (~91 cycles per MMA: the tensor pipe's rate);
+//   producer warp (one elected lane): wait done(u), TMA tile u+4 into the stage MMA(u) read;
+//   epilogue warps: wait done(u); tcgen05.ld -> registers; per-lane min (pass 0) / one ballot per query
+//   column (pass 1); arrive tfree(u).
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -58,7 +61,7 @@ constexpr int FT_QW = 32;    // queries (accumulator columns) per warp
 constexpr int FT_NBUF = 4;             // TMEM accumulator buffers: MMA(u+1..u+3) in flight while tile u is consumed
 constexpr int FT_TMEM_COLS = FT_NBUF * FT_NQ;  // 512 columns: all of TMEM (one CTA per SM)
 constexpr int FT_MAX_K = 24;
-constexpr int FT_RSLACK = 4;  // tau0 bounds the (K + FT_RSLACK)-th smallest e: with the group collisions ~K + 10 hits per query
+constexpr int FT_NMAX_PARTS = 32;  // per-cloud partial maxima of the candidate norms (one per CTA of the split launch)
 constexpr int FT_STAGES = 4;       // candidate-tile ring: tiles u+1..u+3 feed the MMAs in flight, u+4 is loading
 
 struct FeatArgs {
@@ -193,6 +196,14 @@ __device__ __forceinline__ float feat_eps(float nq, float nmax, int D) {
                   (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
 }
 
+// same bound as feat_eps with MUFU square roots (2 ulp; the 1.001 factors cover them)
+__device__ __forceinline__ float feat_eps_fast(float nq, float nmax, int D) {
+  const float xn = __frcp_rn(rsqrtf(nq)) * 1.001f, yn = __frcp_rn(rsqrtf(nmax)) * 1.001f;
+  const float s = xn + yn;
+  return 1.25f * (((float)(6 * D) * 1.1920929e-7f + 3.0517578e-5f) * xn * yn +
+                  (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
+}
+
 // Upper end of the 16-bit radix bucket that holds the k-th smallest (1-based) of the values a
 // warp holds as `nv` ordered-unsigned keys per lane: a valid upper bound of the exact k-th
 // smallest, less than 1% (2^-7 relative) above it.  Keys of absent values must be 0xffffffff.
@@ -251,7 +262,6 @@ __device__ __forceinline__ float ordered_key_inv(unsigned uk) {
 // only sets the size of the norms, hence of the margins — and a sampled mean removes the large common offset of
 // real network features as well as the exact one, without a second kernel in front of this one.
 constexpr int FT_CENTRE_ROWS = 128;
-constexpr int FT_NMAX_PARTS = 32;  // per-cloud partial maxima of the candidate norms (one per CTA of the split launch)
 
 // One float4 chunk per thread (LPR = D/4 lanes per row): v = x - centre; b1 = bf16_rn(v); b2 = bf16_rn(v - b1);
 // out row = [b1(0..D-1) | b2(0..D-1)] (2D bf16 = the bytes of the fp32 row); nrm = sum (b1 + b2)^2.
@@ -351,22 +361,17 @@ __global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict
 // The kernel is bound by the latency of its 2*T dependent tile iterations, so the CTA is made
 // as wide as TMEM/smem allow and the whole problem runs as ONE wave of CTAs.
 //
-// Two passes over the e-matrix (the MMAs are simply issued twice: the tensor pipe is idle
-// otherwise, and the tiles come from L2).  Neither pass has a cross-lane operation in its inner
-// loop (shuffle / vote / redux throughput was the limiter of the first versions):
+// Two passes over the e-matrix (the MMAs are simply issued twice: the tiles come from L2, and re-issuing costs less
+// than keeping 1 MB of accumulators per CTA).  Cross-lane work is one ballot per query column in pass 1 only:
 //   pass 0  every lane keeps, per query, the running minimum of the e-values of the candidates it
 //           sees (one FMNMX per value): 128 disjoint candidate groups per query (4 lane quarters
-//           x 32 lanes).  The R smallest group minima are R distinct candidates, so the R-th
-//           smallest of them (tau0, 16-bit radix select, upper bucket end) is a VALID upper bound
-//           of the R-th smallest e overall — and a tight one.  R = K + 8.
-//   pass 1  the 32 bounds of a warp's queries sit in registers; every candidate with e <= tau0 is
-//           appended to the (quarter, query) buffer through a shared-memory counter (predicated
-//           ATOMS + STS; ~1.2 R candidates per query in total).  Buffer order is irrelevant.
-// Finalisation: (F1) per query, T_K = K-th smallest buffered e (radix bound); every canonical
-// top-K neighbour has e <= T_K + 2 eps and everything with e <= tau0 is buffered, so if
-// T_K + 2 eps < tau0 the buffered candidates inside the margin are a superset (else -> fallback);
-// (F2) all threads evaluate the canonical distance of the (query, candidate) pairs; (F3) per
-// query, rank by (d_canon, idx) and write the K best.
+//           x 32 lanes), merged pairwise to 64.  The K smallest group minima are K distinct candidates, so the
+//           K-th smallest of them (16-bit radix select, upper bucket end) bounds the K-th smallest e overall;
+//           tau0 = that bound + 2.25 eps.
+//   pass 1  the 32 bounds of a warp's queries sit in registers; for every query column the warp ballots
+//           "e <= tau0" over its 32 candidates and publishes the 32-bit hit mask ([4T][P1] words per cloud).
+// The ranking (canonical distances of the hits, K best by (d_canon, idx)) is knn_feat_rank_kernel below.
+
 // one lane of a converged warp (elect.sync): the branch it guards stays warp-uniform for the compiler, so the
 // operands of the tcgen05 / TMA instructions inside live in uniform registers
 __device__ __forceinline__ bool elect_one() {
@@ -522,6 +527,9 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
   unsigned* wmask = &wmask_s[warp][0];
   unsigned* mrow = a.masks + (size_t)b * (size_t)(4 * T) * a.P1;   // this cloud's mask words: [4T][P1]
   const bool qcol_ok = q0 + nq0 + lane < a.P1;                       // lane c publishes the masks of query q0 + nq0 + c
+  // for the admission bound (tau0): the cloud's largest candidate norm and the norms of this warp's QPW queries
+  const unsigned nmax_part = __ldg(a.nmax2 + (size_t)b * FT_NMAX_PARTS + lane);
+  const float nq_lane = __ldg(a.nrm1 + (size_t)b * a.P1 + min(q0 + warp * (FT_NQ / (FT_THREADS / 32)) + (lane & 7), a.P1 - 1));
 
   for (int u = 0; u < U; ++u) {
     const int t = u < T ? u : u - T;
@@ -537,7 +545,11 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
       // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
       //      processed together so their (dependent) radix steps overlap
       constexpr int QPW = FT_NQ / (FT_THREADS / 32);
-      const int R = min(32, K + FT_RSLACK);
+      // The K smallest group minima are K distinct candidates, so their K-th smallest T bounds the K-th smallest
+      // e overall; every canonical top-K neighbour has e <= e_(K) + 2 eps <= T + 2 eps (eps = feat_eps: the error of
+      // e plus that of the canonical sum), so tau0 = T + 2.25 eps admits a superset — about K + 5 hits per query
+      // (group collisions, radix bucket), and the ranking kernel's completeness check then holds by construction.
+      const int R = min(32, K);
       unsigned uk[QPW][2];
 #pragma unroll
       for (int qq = 0; qq < QPW; ++qq)
@@ -545,13 +557,17 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         for (int v = 0; v < 2; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 64 + v * 32 + lane]);
       unsigned bound[QPW];
       warp_radix_bound16_multi<QPW, 2>(uk, R, bound);
-      if (lane == 0)
+      const unsigned nm = __reduce_max_sync(FULL, nmax_part);  // (loaded before the passes)
+      float eps_q = 0.0f;
+      if (lane < QPW) eps_q = feat_eps_fast(nq_lane, __uint_as_float(nm), D);
 #pragma unroll
-        for (int qq = 0; qq < QPW; ++qq) {
-          const float tq = ordered_key_inv(bound[qq]);
+      for (int qq = 0; qq < QPW; ++qq) {
+        const float tq = ordered_key_inv(bound[qq]) + 2.25f * __shfl_sync(FULL, eps_q, qq);
+        if (lane == 0) {
           tau0_s[warp * QPW + qq] = tq;
           if (q0 + warp * QPW + qq < a.P1) a.tau0[(size_t)b * a.P1 + q0 + warp * QPW + qq] = tq;
         }
+      }
       epi_sync();
 #pragma unroll
       for (int n = 0; n < FT_QW; ++n) reg[n] = tau0_s[nq0 + n];
@@ -605,14 +621,6 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 // goes to the exact fallback.
 constexpr int FT_HCAP = 64;          // hits handled per query (two rounds of 32)
 constexpr int FT_RANK_WARPS = 8;
-
-// same bound as feat_eps with MUFU square roots (2 ulp; the 1.001 factors cover them)
-__device__ __forceinline__ float feat_eps_fast(float nq, float nmax, int D) {
-  const float xn = __frcp_rn(rsqrtf(nq)) * 1.001f, yn = __frcp_rn(rsqrtf(nmax)) * 1.001f;
-  const float s = xn + yn;
-  return 1.25f * (((float)(6 * D) * 1.1920929e-7f + 3.0517578e-5f) * xn * yn +
-                  (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
-}
 
 template <int DD>
 __global__ void __launch_bounds__(FT_RANK_WARPS * 32, 4) knn_feat_rank_kernel(FeatArgs a) {

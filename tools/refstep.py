@@ -205,7 +205,7 @@ def step(ctx: StepContext, n_iter: int = 12, freeze_D: bool = False) -> Dict[str
 
 
 def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3, overlap_frames: bool = False,
-                 fused_idgcn: bool = True):
+                 fused_idgcn: bool = True, restructured_edgeconv: bool = False):
     """The graph-capturable form of the fluid step (tpugan_b200.graph_step) over this context's networks, frames and
     (capturable) optimisers."""
     from tpugan_b200.graph_step import GraphedFluidStep
@@ -214,7 +214,7 @@ def graphed_step(ctx: StepContext, capture: bool = True, warmup: int = 3, overla
     og, ot, os_ = ctx.optims
     return GraphedFluidStep(ctx.mods, ctx.sr_net, ctx.spatial_dis, ctx.tempo_dis, ctx.lo, ctx.hi, ctx.opt, (og, ot, os_),
                             furthest_distance=1.0, warmup=warmup, capture=capture, overlap_frames=overlap_frames,
-                            fused_idgcn=fused_idgcn)
+                            fused_idgcn=fused_idgcn, restructured_edgeconv=restructured_edgeconv)
 
 
 def snapshot(ctx: StepContext):
