@@ -800,10 +800,11 @@ def run_ours(args):
                        "frac": fl / (ms_tc * 1e-3) / 1e12 / pk, "launches_per_step": len(tc_calls),
                        "avg_launch_us": ms_tc * 1e3 / len(tc_calls),
                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)",
-                       "note": "call = mean + split pre-pass + tcgen05 kernel + exact-fallback launch; achieved = ALGORITHMIC "
-                               "flops (2 P1 P2 D); the kernel issues 8x that in bf16 MMAs (four split products, two passes) and "
-                               "spends most of its time in the SIMT selection / exact re-ranking that make the indices "
-                               "bit-exact (DESIGN.md K2)"}
+                       "note": "call = split pre-pass + tcgen05 kernel + ranking kernel + exact-fallback launch; achieved = "
+                               "ALGORITHMIC flops (2 P1 P2 D); the tcgen05 kernel issues 6x that in bf16 MMAs (three split "
+                               "products, two passes) at the tensor pipe's rate (~91 cycles per 128x128x16 MMA, tensor pipe "
+                               "~45 % active at D = 64); the rest of the call is the SIMT selection and the exact re-ranking "
+                               "that make the indices bit-exact (DESIGN.md K2)"}
     if args.per_call and rank == 0:
         agg = {}
         for ci, c in enumerate(doc["calls"]):

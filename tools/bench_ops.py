@@ -131,6 +131,57 @@ def run_sweep(quick=False, reps=7, verbose=True):
         us = bn.timeit(lambda: F.inverse_index(idx, N))
         bn.add("inverse index", f"B={Bg} N={N} L={N * k}", us, 4 * Bg * (2 * N * k + N))
         del go
+    # K11: conv-input assembly — QueryAndGroup (discriminator.py:190) and FlowEmbedding (discriminator.py:270-277)
+    # shapes of the fluid step, one pass vs the reference's composition (groupings, "- centre", repeat, torch.cat)
+    for (Cf, N, M, k, flow) in ([(128, 1024, 256, 32, False)] if quick else
+                                [(3, 2048, 1024, 32, False), (128, 1024, 256, 32, False), (256, 256, 256, 32, True)]):
+        xyz = torch.randn(B, 3, N, device=dev)
+        cen = torch.randn(B, 3, M, device=dev)
+        f2 = torch.randn(B, Cf, N, device=dev)
+        f1 = torch.randn(B, Cf, M, device=dev)
+        idx = torch.randint(0, N, (B, M, k), device=dev, dtype=torch.int32)
+        parts = [("gather", xyz, cen), ("gather", f2, None)] + ([("broadcast", f1, None)] if flow else [])
+        ctot = 3 + Cf * (2 if flow else 1)
+        nbytes = 4 * B * (3 * N + 3 * M + Cf * N + (Cf * M if flow else 0) + M * k + ctot * M * k)
+
+        def unfused():
+            a = F.group_fwd(xyz, idx) - cen.unsqueeze(-1)
+            b_ = F.group_fwd(f2, idx)
+            if flow:
+                b_ = torch.cat([b_, f1.view(B, -1, M, 1).repeat(1, 1, 1, k)], dim=1)
+            return torch.cat([a, b_], dim=1)
+
+        us = bn.timeit(unfused)
+        name = "FlowEmbedding input" if flow else "QueryAndGroup"
+        bn.add(name + " (unfused)", f"B={B} C=3+{Cf}{'x2' if flow else ''} N={N} M={M} k={k}", us, nbytes, "groupings, subtraction, repeat, torch.cat")
+        us = bn.timeit(lambda: F.group_assemble(parts, idx))
+        bn.add(name + " (K11)", f"B={B} C=3+{Cf}{'x2' if flow else ''} N={N} M={M} k={k}", us, nbytes)
+    # K12: the k-expanded front half of EdgeConv (gcn.py:206-211) at the generator's shapes: reference composition
+    # (grouping, "- centre", two 1x1 convolutions + LeakyReLU on [B,C,N,k], add) vs per-node convolutions + one kernel
+    for (Cin, Co, N, k) in ([(32, 16, 2048, 20)] if quick else [(32, 16, 2048, 20), (32, 16, 2048, 10), (64, 32, 2048, 12)]):
+        feat = torch.randn(B, Cin, N, device=dev)
+        idx = torch.randint(0, N, (B, N, k), device=dev, dtype=torch.int32)
+        node = torch.nn.Sequential(torch.nn.Conv2d(Cin, Co, 1), torch.nn.LeakyReLU(0.2)).to(dev)
+        edge = torch.nn.Sequential(torch.nn.Conv2d(Cin, Co, 1), torch.nn.LeakyReLU(0.2)).to(dev)
+        nbytes = 4 * B * (Cin * N + N * k + Co * N * k)
+
+        def ref_front():
+            with torch.no_grad():
+                g = F.group_fwd(feat, idx)
+                return node(g) + edge(g - feat.unsqueeze(-1))
+
+        def restructured():
+            with torch.no_grad():
+                x = feat.unsqueeze(-1)
+                p = node(x).squeeze(-1)
+                q = edge[0](x).squeeze(-1)
+                c = q - edge[0].bias.view(1, -1, 1)
+                return F.edge_affine_fwd(p, q, c, idx, 0.2)
+
+        us = bn.timeit(ref_front)
+        bn.add("EdgeConv front (reference)", f"B={B} C={Cin}->{Co} N={N} k={k}", us, nbytes, "grouping, - centre, 2 convs + LeakyReLU on [B,C,N,k], add")
+        us = bn.timeit(restructured)
+        bn.add("EdgeConv front (K12)", f"B={B} C={Cin}->{Co} N={N} k={k}", us, nbytes, "2 per-node convs + edge_affine kernel")
     for c, n in ([(64, 8192)] if quick else [(64, 8192), (256, 8192), (128, 65536)]):
         m = n // 4
         Bt = B if n <= 8192 else 2
