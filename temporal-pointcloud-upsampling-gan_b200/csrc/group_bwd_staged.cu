@@ -267,7 +267,8 @@ static int group_bwd_staged_seg(const float* go, const int32_t* off, const int32
   a.items_bytes = (int)align_up((size_t)2 * L + 2, 128);  // + the one-past-the-end peek
   const int ring_floats = (SB_SMEM_BYTES - a.items_bytes) / 4;
   // channels per thread (one item walk serves TCG channels): as many as still leave >= min_tiles tiles and chunks
-  // of >= 4096 floats (or whole rows).  min_tiles is half a wave: the step replays many groupings concurrently,
+  // of >= 1536 floats (or whole rows; measured on the step's shapes, tools/bench_group_bwd.py: shorter chunks cost
+  // less than walking the item list twice as often).  min_tiles is half a wave: the step replays many groupings concurrently,
   // so SM-time matters more than the latency of one call.
   int TCG = 1;
   const int max_tcg = NPT <= 2 ? 4 : (NPT == 4 ? 2 : 1);  // NPT = 8: one channel per item walk (registers)
@@ -276,7 +277,7 @@ static int group_bwd_staged_seg(const float* go, const int32_t* off, const int32
     const long long TC = (long long)a.G * t;
     if (TC > SB_MAX_TC) continue;
     const long long lc = ring_floats / (2 * TC);
-    if (lc >= min(L, 4096) && (long long)B * ((C + TC - 1) / TC) >= min_tiles) { TCG = t; break; }
+    if (lc >= min(L, 1536) && (long long)B * ((C + TC - 1) / TC) >= min_tiles) { TCG = t; break; }
   }
   int S = 0;
   if (force > 0) {
