@@ -433,6 +433,7 @@ class TraceReplay:
                 idx = state["fwd"][i["fwd_id"]]
                 used.append(idx)
                 owner = state["csr"].setdefault((id(idx), int(i["N"])), n)  # the call that builds the shared CSR
+                bwd_idx, bwd_N = idx, int(i["N"])
 
                 def run(idx=idx, d=d, i=i, n=n):
                     out = ops.group_bwd(d["grad_out"], idx, int(i["N"]))
@@ -457,6 +458,11 @@ class TraceReplay:
                 if op == "chamfer_bwd":
                     waits.add(state["chamfer_call"])
                 ops.lane_enter(lane_of[n], [done[w] for w in sorted(waits) if w in done and lane_of[w] != lane_of[n]])
+            if self.timers is not None and op in ("group_bwd", "gather_bwd") and hasattr(ops, "prepare_bwd"):
+                ta = ops.tick()
+                nb = ops.prepare_bwd(bwd_idx, bwd_N)
+                if nb:
+                    self.timers.setdefault("inverse_index", []).append((ta, ops.tick(), nb))
             t0 = ops.tick() if self.timers is not None else None
             run()
             if t0 is not None:
@@ -564,6 +570,14 @@ class TorchCudaOps:
         off, items = self.F.csr_cache.get(idx, N)
         return self.F.group_bwd(grad_out, off, items, N)
 
+    def prepare_bwd(self, idx, N):
+        """Builds the inverse index of idx now if no call has yet (timed legs: the build — other kernels than the
+        gradient's — is then accounted for as its own op, "inverse_index").  Returns its algorithmic bytes or 0."""
+        if self.F.csr_cache._key(idx, N) in self.F.csr_cache.entries:
+            return 0
+        self.F.csr_cache.get(idx, N)
+        return 4 * (2 * idx.numel() + idx.shape[0] * N)
+
     def chamfer(self, src, tgt, directions):
         r = self.F.chamfer_fwd(src, tgt, directions)
         return (src, tgt, directions, r)
@@ -626,6 +640,9 @@ class ShimApiOps(TorchCudaOps):
         out = self.pu.grouping_operation(f, idx)
         self._fwd.setdefault(("g", idx.data_ptr(), tuple(out.shape)), []).append((f, out))
         return out
+
+    def prepare_bwd(self, idx, N):
+        return 0  # autograd's backward builds (or finds) the inverse index itself
 
     def group_bwd(self, grad_out, idx, N):
         key = ("g", idx.data_ptr(), tuple(grad_out.shape))
