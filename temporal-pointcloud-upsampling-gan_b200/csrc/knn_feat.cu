@@ -77,7 +77,7 @@ struct FeatArgs {
   int64_t* idx;            // [B,P1,K]
   int* fb_count;           // [1]
   int* fb_list;            // [B*P1]
-  unsigned* masks;         // [B][4*T][P1] hit masks of pass 1: word (t*4 + quarter) bit l = candidate t*128 + quarter*32 + l
+  unsigned* masks;         // [B][P1][4*T] hit masks of pass 1: word (t*4 + quarter) bit l = candidate t*128 + quarter*32 + l
   float* tau0;             // [B,P1] admission bound of every query
   int T;                   // candidate tiles per cloud = ceil(P2 / 128)
   long long* dbg;          // [ctas][8] phase timestamps (tools/bench_knn_feat.py)
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 #pragma unroll
   for (int n = 0; n < FT_QW; ++n) reg[n] = INF;
   unsigned* wmask = &wmask_s[warp][0];
-  unsigned* mrow = a.masks + (size_t)b * (size_t)(4 * T) * a.P1;   // this cloud's mask words: [4T][P1]
+  unsigned* mrow = a.masks + (size_t)b * (size_t)(4 * T) * a.P1;   // this cloud's mask words: [P1][4T] (query-major)
   const bool qcol_ok = q0 + nq0 + lane < a.P1;                       // lane c publishes the masks of query q0 + nq0 + c
   // for the admission bound (tau0): the cloud's largest candidate norm and the norms of this warp's QPW queries
   const unsigned nmax_part = __ldg(a.nmax2 + (size_t)b * FT_NMAX_PARTS + lane);
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         if (lane == 0) wmask[c] = m;
       }
       __syncwarp();
-      if (qcol_ok) mrow[(size_t)(t * 4 + quarter) * a.P1 + q0 + nq0 + lane] = wmask[lane];
+      if (qcol_ok) mrow[(size_t)(q0 + nq0 + lane) * (size_t)(4 * T) + t * 4 + quarter] = wmask[lane];
     }
     // this warp has drained TMEM buffer u % 4 (tcgen05.wait::ld inside tmem_ld32): MMA(u+4) may overwrite it.
     // No CTA-wide barrier in the loop: warps run ahead until the next MMA-done barrier.
@@ -649,10 +649,10 @@ __global__ void __launch_bounds__(FT_RANK_WARPS * 32, 4) knn_feat_rank_kernel(Fe
   unsigned long long* wkey = &key_s[warp][0];
   const float* p2b = a.p2 + (size_t)b * a.P2 * D;
   // everything the tail needs is requested up front: the warp's chain is latency, not bandwidth
-  const unsigned* mq = a.masks + (size_t)b * (size_t)(4 * a.T) * a.P1 + qi;
+  const unsigned* mq = a.masks + ((size_t)b * a.P1 + qi) * (size_t)(4 * a.T);  // the query's 4T mask words, contiguous
   const int nwords = 4 * a.T;
-  unsigned mw0 = lane < nwords ? __ldg(mq + (size_t)lane * a.P1) : 0u;
-  unsigned mw1 = lane + 32 < nwords ? __ldg(mq + (size_t)(lane + 32) * a.P1) : 0u;
+  unsigned mw0 = lane < nwords ? __ldg(mq + lane) : 0u;
+  unsigned mw1 = lane + 32 < nwords ? __ldg(mq + lane + 32) : 0u;
   const float t0 = __ldg(a.tau0 + (size_t)b * a.P1 + qi);
   const float nq = __ldg(a.nrm1 + (size_t)b * a.P1 + qi);
   const unsigned nmax_bits = __reduce_max_sync(FULL, __ldg(a.nmax2 + (size_t)b * FT_NMAX_PARTS + lane));
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(FT_RANK_WARPS * 32, 4) knn_feat_rank_kernel(Fe
   }
   for (int w0 = 64; w0 < nwords; w0 += 32) {  // clouds of more than 2048 candidates
     const int w = w0 + lane;
-    unsigned m = w < nwords ? __ldg(mq + (size_t)w * a.P1) : 0u;
+    unsigned m = w < nwords ? __ldg(mq + w) : 0u;
     const int c = __popc(m);
     int incl = c;
 #pragma unroll
