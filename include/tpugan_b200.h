@@ -80,8 +80,8 @@ int tpg_set_option(const char* name, long value);
  * p1 [B,P1,D], p2 [B,P2,D] -> dists [B,P1,K] (squared), idx [B,P1,K] int64.
  * Slots beyond min(K, lengths2[b]) and rows beyond lengths1[b] hold 0 / 0.
  * 1 <= D <= 256, 1 <= K <= 1024.
- * Feature-space searches (D = 32/64, K <= 24, P2 >= 1024) run on the tensor cores
- * (tcgen05: centred operands split into two bf16 terms, four-product bf16 contraction with fp32
+ * Feature-space searches (D = 32/64, K <= 24, P2 >= 1024, hit-mask workspace B*P1*P2/8 bytes <= 1 GiB) run on the
+ * tensor cores (tcgen05: centred operands split into two bf16 terms, three-product bf16 contraction with fp32
  * accumulation as candidate search + exact fp32 re-rank on the original rows) and 3-D searches over clouds of
  * >= 2048 points (K <= 32) walk a uniform grid; both return results identical to the
  * brute-force path and need tpg_knn_workspace_bytes() bytes of workspace; for every

@@ -945,6 +945,8 @@ bool knn_feat_eligible(const KnnArgs& a) {
   if (a.D != 32 && a.D != 64) return false;  // the shapes the generator uses (gcn.py:200-203,258)
   if (a.K > FT_MAX_K || a.P2 < 1024) return false;  // below that the brute-force kernel is as fast
   if ((long long)a.B * a.P1 >= (1LL << 31)) return false;
+  // the hit masks of pass 1 are a P1 x P2 bit matrix per cloud: keep that workspace below 1 GiB (8 x 16384^2 fits)
+  if ((long long)a.B * a.P1 * (long long)((a.P2 + FT_TM - 1) / FT_TM) * 16 > (1LL << 30)) return false;
   if ((reinterpret_cast<uintptr_t>(a.p1) | reinterpret_cast<uintptr_t>(a.p2)) & 15) return false;
   if (!tmap_encoder()) return false;  // no TMA descriptor encoder: SIMT path
   return true;

@@ -133,7 +133,8 @@ class _KnnMemo:
     def eligible(p1, p2, K):
         D = p1.shape[2]
         return D in (32, 64) and p2.shape[1] >= 1024 and K <= 24 and p1.is_contiguous() and p2.is_contiguous() \
-            and p1.data_ptr() % 16 == 0 and p2.data_ptr() % 16 == 0
+            and p1.data_ptr() % 16 == 0 and p2.data_ptr() % 16 == 0 \
+            and p1.shape[0] * p1.shape[1] * ((p2.shape[1] + 127) // 128) * 16 <= (1 << 30)  # knn_feat_eligible
 
     def clear(self):
         self.entries.clear()

@@ -30,7 +30,9 @@ ALG = {"group_bwd_staged_kernel": 4 * B_ * (64 * 32768 + 32768 + 64 * 2048), "gr
        "group_reduce_fwd_smem_kernel": 4 * B_ * (64 * 2048 + 32768 + 2 * 64 * 2048), "knn_feat_tc_kernel": 4 * B_ * 64 * 4096 + 12 * B_ * 2048 * 12,
        "fps_reg_kernel": 12 * B_ * 2048 + 4 * B_ * 512, "ball_query_kernel": 12 * B_ * (8192 + 1024) + 4 * B_ * 1024 * 32,
        "grid_knn_kernel": 4 * B_ * 3 * 2 * 8192 + 12 * B_ * 8192 * 16, "grid_nn1_kernel": 20 * B_ * 2 * 8192,
-       "csr_cluster_kernel": 4 * B_ * (2 * 32768 + 2048)}
+       "csr_cluster_kernel": 4 * B_ * (2 * 32768 + 2048),
+       "group_assemble_kernel": 4 * B_ * (3 * 256 + 3 * 256 + 2 * 256 * 256 + 256 * 32 + (3 + 512) * 256 * 32),
+       "edge_affine_kernel": 4 * B_ * (3 * 16 * 2048 + 2048 * 20 + 16 * 2048 * 20)}
 traffic = {"_source": f"{tag}: dram__bytes_read.sum + dram__bytes_write.sum and lts__t_bytes.sum of one launch per kernel "
                       "(ncu --set full --clock-control none, L2 flushed before the launch; tools/prof_kernels.py)"}
 for name, r in seen.items():

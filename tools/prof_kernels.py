@@ -32,7 +32,7 @@ def twice(fn):
 z = np.load(os.path.join(ROOT, "tests", "golden", "knn_real_features.npz"))
 x32 = torch.from_numpy(np.repeat(z["c4_K20_D32"], B, 0)).to(dev)   # real generator activations
 x64 = torch.from_numpy(np.repeat(z["c14_K12_D64"], B, 0)).to(dev)
-twice(lambda: F.knn(x32, x32, 20))     # K2: feat_mean_partial, feat_split, knn_feat_tc, fallback
+twice(lambda: F.knn(x32, x32, 20))     # K2: feat_split, knn_feat_tc, knn_feat_rank, fallback
 twice(lambda: F.knn(x64, x64, 12))
 p2 = torch.from_numpy(synth.fluid_cloud(rng, B, 2048)).to(dev)
 p8 = torch.from_numpy(synth.fluid_cloud(rng, B, 8192)).to(dev)
@@ -50,6 +50,14 @@ go = torch.randn(B, 64, 2048, 16, device=dev)
 off, items = F.inverse_index(idx, 2048)
 twice(lambda: F.group_bwd(go, off, items, 2048))
 twice(lambda: F.inverse_index(idx, 2048))
+# K11: flow-embedding conv input; K12: restructured EdgeConv front half
+xyz, cen = torch.randn(B, 3, 256, device=dev), torch.randn(B, 3, 256, device=dev)
+f2, f1 = torch.randn(B, 256, 256, device=dev), torch.randn(B, 256, 256, device=dev)
+idx32 = torch.randint(0, 256, (B, 256, 32), device=dev, dtype=torch.int32)
+twice(lambda: F.group_assemble([("gather", xyz, cen), ("gather", f2, None), ("broadcast", f1, None)], idx32))
+pq = torch.randn(2, B, 16, 2048, device=dev)
+idx20 = torch.randint(0, 2048, (B, 2048, 20), device=dev, dtype=torch.int32)
+twice(lambda: F.edge_affine_fwd(pq[0], pq[1], pq[1] - 0.1, idx20, 0.2))
 tgt = torch.from_numpy(synth.fluid_cloud(rng, B, 8192)).to(dev)
 src = (tgt + 0.003 * torch.randn_like(tgt)).contiguous()
 twice(lambda: F.chamfer_fwd(src, tgt, 3))
