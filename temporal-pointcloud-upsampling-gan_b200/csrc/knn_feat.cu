@@ -204,46 +204,42 @@ __device__ __forceinline__ float feat_eps_fast(float nq, float nmax, int D) {
                   (3.0517578e-5f + (float)(2 * D + 32) * 5.9604645e-8f) * s * s);
 }
 
-// Upper end of the 16-bit radix bucket that holds the k-th smallest (1-based) of the values a
-// warp holds as `nv` ordered-unsigned keys per lane: a valid upper bound of the exact k-th
-// smallest, less than 1% (2^-7 relative) above it.  Keys of absent values must be 0xffffffff.
-template <int NV>
-__device__ __forceinline__ unsigned warp_radix_bound16(const unsigned (&uk)[NV], int k) {
-  unsigned prefix = 0u, himask = 0u;
-#pragma unroll 1
-  for (int bit = 31; bit >= 16; --bit) {
-    const unsigned bmask = 1u << bit;
-    unsigned local = 0;
+// k-th smallest (1-based) of the 64 unsigned keys a warp holds two per lane (element 2 * lane + s), for NQ
+// independent key sets at once: a bitonic sorting network — 21 compare-exchange stages, 15 of them one SHFL + one
+// predicated min/max per key, 6 inside the lane.  ~110 instructions per set instead of the ~340 of the 16-step
+// radix select it replaces (which bounded the kernel's admission-bound phase at 10.7 K cycles), and the result is
+// the exact k-th smallest, not the upper end of a radix bucket.  Keys of absent values must be 0xffffffff.
+template <int NQ>
+__device__ __forceinline__ void warp_kth_smallest64_multi(unsigned (&v)[NQ][2], int k, unsigned (&out)[NQ]) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) local += ((uk[v] & (himask | bmask)) == prefix) ? 1u : 0u;
-    const int c = (int)__reduce_add_sync(FULL, local);  // one REDUX per step instead of NV ballots
-    if (k > c) { prefix |= bmask; k -= c; }
-    himask |= bmask;
-  }
-  return prefix | 0xffffu;
-}
-// same bound for NQ independent value sets at once (their dependent bit steps interleave)
-template <int NQ, int NV>
-__device__ __forceinline__ void warp_radix_bound16_multi(const unsigned (&uk)[NQ][NV], int k0, unsigned (&out)[NQ]) {
-  unsigned prefix[NQ], himask = 0u;
-  int k[NQ];
+  for (int kk = 2; kk <= 64; kk <<= 1) {
+    const bool asc = ((2 * lane) & kk) == 0;  // direction of this element's block (kk == 64: ascending everywhere)
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) { prefix[q] = 0u; k[q] = k0; }
-#pragma unroll 1
-  for (int bit = 31; bit >= 16; --bit) {
-    const unsigned bmask = 1u << bit;
+    for (int j = kk >> 1; j >= 1; j >>= 1) {
+      if (j == 1) {  // partner = the lane's other key
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      unsigned local = 0;
+        for (int q = 0; q < NQ; ++q) {
+          const unsigned lo = min(v[q][0], v[q][1]), hi = max(v[q][0], v[q][1]);
+          v[q][0] = asc ? lo : hi;
+          v[q][1] = asc ? hi : lo;
+        }
+      } else {       // partner = the same slot of lane ^ (j / 2)
+        const int lj = j >> 1;
+        const bool take_max = ((lane & lj) != 0) == asc;  // the higher element of an ascending pair keeps the maximum
 #pragma unroll
-      for (int v = 0; v < NV; ++v) local += ((uk[q][v] & (himask | bmask)) == prefix[q]) ? 1u : 0u;
-      const int c = (int)__reduce_add_sync(FULL, local);
-      if (k[q] > c) { prefix[q] |= bmask; k[q] -= c; }
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const unsigned p = __shfl_xor_sync(FULL, v[q][s2], lj);
+            v[q][s2] = take_max ? max(v[q][s2], p) : min(v[q][s2], p);
+          }
+      }
     }
-    himask |= bmask;
   }
+  const int e = k - 1;
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) out[q] = prefix[q] | 0xffffu;
+  for (int q = 0; q < NQ; ++q) out[q] = __shfl_sync(FULL, (e & 1) ? v[q][1] : v[q][0], e >> 1);
 }
 __device__ __forceinline__ unsigned ordered_key(float f) {  // unsigned order == float order
   const int bits = __float_as_int(f);
@@ -366,7 +362,7 @@ __global__ void __launch_bounds__(256) feat_split_kernel(const float* __restrict
 //   pass 0  every lane keeps, per query, the running minimum of the e-values of the candidates it
 //           sees (one FMNMX per value): 128 disjoint candidate groups per query (4 lane quarters
 //           x 32 lanes), merged pairwise to 64.  The K smallest group minima are K distinct candidates, so the
-//           K-th smallest of them (16-bit radix select, upper bucket end) bounds the K-th smallest e overall;
+//           K-th smallest of them (bitonic sort of the 64 merged minima in registers) bounds the K-th smallest e overall;
 //           tau0 = that bound + 2.25 eps.
 //   pass 1  the 32 bounds of a warp's queries sit in registers; for every query column the warp ballots
 //           "e <= tau0" over its 32 candidates and publishes the 32-bit hit mask ([4T][P1] words per cloud).
@@ -541,14 +537,16 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
         const float m2 = fminf(reg[n], __shfl_xor_sync(FULL, reg[n], 16));
         if (lane < 16) gval_s[(nq0 + n) * 64 + quarter * 16 + lane] = m2;
       }
+      if (dbg && tid == 0) dbg[11] = clock64();
       epi_sync();
+      if (dbg && tid == 0) dbg[12] = clock64();
       // ---- tau0 = R-th smallest of the 128 group minima of a query; the warp's queries are
-      //      processed together so their (dependent) radix steps overlap
+      //      processed together so the stages of their sorting networks interleave
       constexpr int QPW = FT_NQ / (FT_THREADS / 32);
       // The K smallest group minima are K distinct candidates, so their K-th smallest T bounds the K-th smallest
       // e overall; every canonical top-K neighbour has e <= e_(K) + 2 eps <= T + 2 eps (eps = feat_eps: the error of
       // e plus that of the canonical sum), so tau0 = T + 2.25 eps admits a superset — about K + 5 hits per query
-      // (group collisions, radix bucket), and the ranking kernel's completeness check then holds by construction.
+      // (group collisions), and the ranking kernel's completeness check then holds by construction.
       const int R = min(32, K);
       unsigned uk[QPW][2];
 #pragma unroll
@@ -556,7 +554,8 @@ __global__ void __launch_bounds__(FT_BLOCK, 1) knn_feat_tc_kernel(FeatArgs a, co
 #pragma unroll
         for (int v = 0; v < 2; ++v) uk[qq][v] = ordered_key(gval_s[(warp * QPW + qq) * 64 + v * 32 + lane]);
       unsigned bound[QPW];
-      warp_radix_bound16_multi<QPW, 2>(uk, R, bound);
+      warp_kth_smallest64_multi<QPW>(uk, R, bound);
+      if (dbg && tid == 0) dbg[13] = clock64();
       const unsigned nm = __reduce_max_sync(FULL, nmax_part);  // (loaded before the passes)
       float eps_q = 0.0f;
       if (lane < QPW) eps_q = feat_eps_fast(nq_lane, __uint_as_float(nm), D);
