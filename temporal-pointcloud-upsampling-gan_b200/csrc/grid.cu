@@ -616,7 +616,9 @@ int grid_knn_dispatch(const KnnArgs& a, void* workspace, size_t workspace_bytes,
   }
   GridKnnArgs k{a.p1, qrec, a.len1, a.B, a.P1, a.K, a.use_radius, a.r, a.r_per_cloud, g, a.dists, a.idx, a.out_mode};
   // plain kNN with K <= 24 (<= 32 * GK_PER candidates in the first block at the grid's cell size): select-based kernel
-  if ((a.out_mode == OUT_KNN || a.out_mode == OUT_THREE) && !a.use_radius && a.K <= 24)  // (three_nn = kNN with K = 3)
+  // (three_nn, K = 3, stays on the insertion kernel: measured 140 vs 175 us at 8 x 8192 x 2048 — the select's fixed
+  // cost does not pay for three neighbours)
+  if (a.out_mode == OUT_KNN && !a.use_radius && a.K <= 24)
     grid_knn_kernel<true><<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);
   else
     grid_knn_kernel<false><<<(unsigned)((queries + 7) / 8), 256, 0, st>>>(k);

@@ -16,6 +16,8 @@ CMD="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-train-
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "ncu launches rc=$?"
+if [ "${SKIP_FULL:-0}" != "1" ]; then
 python tools/prof_kernels.py > $OUT/prof_plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"knn_feat|feat_split|group_|fps_reg|ball_query_kernel|grid_knn|grid_nn1|csr_cluster|edge_affine" -c 80 -f -o $OUT/prof_$TAG python tools/prof_kernels.py > $OUT/ncu_prof_$TAG.log 2>&1
 echo "ncu full rc=$?"
+fi
