@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--sync-bn", action="store_true", help="train_step leg at N > 1: SyncBatchNorm in the discriminators")
-    ap.add_argument("--lanes", type=int, default=64, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
+    ap.add_argument("--lanes", type=int, default=32, help="streams of the dependency-aware CUDA-graph leg (1 = off)")
     ap.add_argument("--quick", action="store_true", help="sweep / chamfer: reduced shape list")
     ap.add_argument("--per-op", action="store_true", help="print the per-op time table to stderr")
     ap.add_argument("--per-call", action="store_true", help="print every call of the schedule with its mean device time")

@@ -27,7 +27,7 @@ for (B, P, D, K) in [(8, 2048, 32, 20), (8, 2048, 64, 12), (8, 2048, 32, 9), (8,
     print(f"B={B} P={P} D={D} K={K}: call {a.elapsed_time(b) * 1e3:.1f} us; per-CTA cycles (mean/max): " +
           "  ".join(f"{nm}={ph[:, j].mean():.0f}/{ph[:, j].max():.0f}" for j, nm in enumerate(names)) +
           f"  total={(dbg[:, 5] - dbg[:, 0]).mean():.0f}  span={(dbg[:, 5].max() - dbg[:, 0].min())}")
-    print('   admission-bound phase: merge+store / barrier wait / radix select / rest =', (dbg[:, 11] - dbg[:, 2]).mean().astype(int), (dbg[:, 12] - dbg[:, 11]).mean().astype(int), (dbg[:, 13] - dbg[:, 12]).mean().astype(int), (dbg[:, 3] - dbg[:, 13]).mean().astype(int))
+    print('   admission-bound phase: merge+store / barrier wait / sorting network / rest =', (dbg[:, 11] - dbg[:, 2]).mean().astype(int), (dbg[:, 12] - dbg[:, 11]).mean().astype(int), (dbg[:, 13] - dbg[:, 12]).mean().astype(int), (dbg[:, 3] - dbg[:, 13]).mean().astype(int))
     print('   issuer cycles per CTA: wait-full / wait-tmem-free / issue =', dbg[:, 8:11].mean(0).astype(int))
     fo = lib.tpg_knn_fallback_count_offset(B)
     print('   flagged for exact fallback:', int(ws[fo:fo + 4].view(torch.int32)[0]), 'of', B * P)
